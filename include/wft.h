@@ -1,0 +1,125 @@
+/*
+ * wft.h -- C ABI of the B200-native Whisper audio front end (libwft_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of i4Ds/whisper-finetune (paths relative to the reference root):
+ *
+ *   PCM -> zero pad -> Hann(400)/hop-160 STFT -> |X|^2 -> mel(80|128) -> log10 / clamp / max-8 -> (x+4)/4
+ *       -> partial-segment cut -> min-value pad_or_trim -> SpecAugment time + frequency masks -> [B, n_mels, T]
+ *
+ * i.e. what AudioDataset.__getitem__/_calculate_mel compute per clip on the CPU
+ * (src/whisper_finetune/data/data_loader.py:273-292, :344-346) and collate_fn stacks (:362-367).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; every pointer marked "device" must be CUDA device memory of the
+ *     current device; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - All calls are asynchronous on `stream`; none of them synchronises the host.
+ *   - Return value 0 = success, negative = error (WFT_ERR_*).  The message for the last error of the calling
+ *     thread is available from wft_last_error().  Nothing aborts, nothing throws across the boundary.
+ *   - Inputs are never modified; outputs and workspaces are caller-owned (the reference's functional
+ *     semantics: masked_fill / F.pad / index_select all allocate, data/utils.py:380-404).
+ *   - There is NO CPU implementation behind this header: without a CUDA device every compute entry point
+ *     fails with WFT_ERR_CUDA.
+ */
+#ifndef WFT_H_
+#define WFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFT_ABI_VERSION 1
+
+/* Front-end constants (whisper.audio: SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES;
+ * imported by the reference at data_loader.py:13 and data/utils.py:10). */
+#define WFT_SAMPLE_RATE 16000
+#define WFT_N_FFT 400
+#define WFT_HOP_LENGTH 160
+#define WFT_N_SAMPLES 480000
+#define WFT_N_FRAMES 3000
+
+enum wft_pcm_dtype { WFT_PCM_F32 = 0, WFT_PCM_I16 = 1 };
+
+enum wft_status {
+  WFT_OK = 0,
+  WFT_ERR_INVALID = -1, /* bad argument (shape, dtype, n_mels not in {80,128}, ...) -> ValueError in Python */
+  WFT_ERR_CUDA = -2,    /* CUDA runtime failure (no device, launch error, ...)       -> RuntimeError        */
+};
+
+/* Per-call description of a batched front-end pass (wft_frontend_forward). */
+typedef struct wft_frontend_args {
+  /* ---- input PCM ---- */
+  const void* pcm;          /* device; clip b starts at element b*clip_stride                                   */
+  int32_t pcm_dtype;        /* enum wft_pcm_dtype; int16 is scaled by 1/32768 like whisper.audio.load_audio      */
+  int32_t batch;            /* B >= 1                                                                           */
+  int64_t clip_stride;      /* elements between consecutive clips                                               */
+  int32_t n_samples;        /* samples stored per clip (<= clip_stride)                                         */
+  int32_t padding;          /* zeros appended after n_samples: the `padding` arg of log_mel_spectrogram;
+                               together with `lengths` this is also the zero pad of data_loader.py:346          */
+  const int32_t* lengths;   /* device [B] or NULL: valid prefix of each clip (rest treated as 0), <= n_samples  */
+  /* ---- features ---- */
+  int32_t n_mels;           /* 80 or 128 (whisper.audio asserts the same set)                                   */
+  int32_t n_frames_out;     /* T of the output; 0 -> (n_samples+padding)/160 (no pad_or_trim)                   */
+  const int32_t* n_valid_frames; /* device [B] or NULL: keep frames [0, n_valid) (data_loader.py:279-280), then
+                               min-value pad up to n_frames_out (data/utils.py:380-404); <0 = keep all           */
+  /* ---- SpecAugment (data_loader.py:286-287), all four NULL = no masking ---- */
+  const int32_t* mask_params; /* device [B,4] = (t0, t1, f0, f1): frames [t0,t1) and rows [f0,f1) := mask_value  */
+  float mask_value;         /* 0.0f in the reference (torchaudio default)                                        */
+  /* ---- output ---- */
+  float* out;               /* device [B, n_mels, n_frames_out] contiguous                                      */
+  void* workspace;          /* device, >= wft_frontend_workspace_bytes(); contents are scratch                  */
+  size_t workspace_bytes;
+} wft_frontend_args;
+
+/* ABI version of the loaded library (== WFT_ABI_VERSION of the header it was built from). */
+int wft_abi_version(void);
+
+/* Message of the last error raised on the calling thread ("" if none). */
+const char* wft_last_error(void);
+
+/* Scratch bytes needed by wft_frontend_forward for (batch, n_samples+padding, n_frames_out). */
+int wft_frontend_workspace_bytes(int32_t batch, int32_t n_samples_total, int32_t n_frames_out, size_t* bytes);
+
+/* The fused front end: replaces, for a whole batch and in one launch,
+ *   np.pad(audio, (0, N_SAMPLES - len))                    data_loader.py:346
+ *   whisper.audio.log_mel_spectrogram(audio, n_mels)       data_loader.py:278   (per-clip max-8 floor)
+ *   mel[:, :int(start * 100)]                              data_loader.py:279-280
+ *   pad_or_trim(mel, N_FRAMES)                             data_loader.py:281-282, data/utils.py:380-404
+ *   time_masking(mel); freq_masking(mel)                   data_loader.py:286-287
+ *   pad_sequence(x, batch_first=True)                      data_loader.py:362-367 (collate_fn)
+ */
+int wft_frontend_forward(const wft_frontend_args* args, void* stream);
+
+/* Stand-alone pad_or_trim on float32 (data/utils.py:380-404): `in` is [outer, len_in, inner], `out` is
+ * [outer, len_out, inner]; trims, or right-pads with the minimum over the WHOLE input (computed on device,
+ * no host sync).  `scratch` is a device buffer of >= 16 bytes.  len_in == 0 with len_out > 0 is an error
+ * (the reference's torch.min raises on an empty tensor). */
+int wft_pad_or_trim_f32(const float* in, int64_t outer, int64_t len_in, int64_t inner, int64_t len_out,
+                        float* out, void* scratch, void* stream);
+
+/* Stand-alone SpecAugment masks (torchaudio mask_along_axis semantics as used at data_loader.py:286-287):
+ * out[b, r, t] = (t0<=t<t1 || f0<=r<f1) ? mask_value : in[b, r, t]; `in == out` is allowed (in place).
+ * mask_params is device int32 [B,4].  Also serves [B, C, T] activations (model/model_utils.py:382-437). */
+int wft_specaug_apply_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames,
+                          const int32_t* mask_params, float mask_value, void* stream);
+
+/* Counter-based draw of the mask intervals on the device: Philox4x32-10 keyed by `seed`, counter = global
+ * clip index (clip_offset + b) so that a rank's shard draws the same masks at any world size.  Interval
+ * arithmetic is torchaudio's (float32): width = u*param, start = trunc(u'*(size-width)), end = start+trunc(width).
+ * `p` is the gate of data_loader.py:294-301 (p>=1 always, p<=0 never, else u_gate < p).
+ * mask_params_out is device int32 [B,4]. */
+int wft_specaug_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_mels, int32_t n_frames,
+                     int32_t time_mask_param, int32_t freq_mask_param, float p, int32_t* mask_params_out,
+                     void* stream);
+
+/* Introspection used by bench.py / tests: number of kernel launches issued by this library on the calling
+ * thread since the last reset, and the persistent grid the fused kernel would use on the current device. */
+int64_t wft_launch_count(int reset);
+int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t* threads, int32_t* smem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFT_H_ */

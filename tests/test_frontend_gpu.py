@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA front end (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): max-abs <= 1e-3 and rel-L2 <= 1e-5 in float32 for the features; mask cells
+and pad_or_trim bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel as O
+from oracle import pipeline as OP
+from oracle import specaug as OS
+from tests import signals as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(got, ref, what=""):
+    ma, rl = S.metrics(got, ref)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert ma <= S.MAX_ABS and rl <= S.REL_L2, f"{what}: max-abs {ma:.3e} rel-L2 {rl:.3e}"
+    return ma, rl
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+@pytest.mark.parametrize("kind", ["white", "hdr", "int16", "zeros", "impulse", "chirp"])
+def test_logmel_full_clip_matches_oracle(wft, cuda, kind, n_mels):
+    x = S.make(kind)
+    got = wft.log_mel_spectrogram(x.to(cuda), n_mels=n_mels).cpu()
+    ref = O.log_mel_spectrogram(x, n_mels)
+    assert got.shape == (n_mels, 3000)
+    _check(got, ref, f"{kind}/{n_mels}")
+
+
+def test_zeros_known_answer(wft, cuda):
+    got = wft.log_mel_spectrogram(torch.zeros(480000, device=cuda), n_mels=80)
+    assert torch.allclose(got, torch.full_like(got, -1.5), atol=2e-6, rtol=0)
+
+
+def test_dynamic_range_property(wft, cuda):
+    x = S.make("hdr")
+    got = wft.log_mel_spectrogram(x.to(cuda), n_mels=128)
+    assert (got.max() - got.min()).item() <= 2.0 + 1e-6
+
+
+@pytest.mark.parametrize("n", [201, 400, 1599, 1600, 1601, 5120, 16000, 48001, 479999])
+def test_short_and_ragged_lengths(wft, cuda, n):
+    x = S.make("white", n=n, seed=n)
+    got = wft.log_mel_spectrogram(x.to(cuda), n_mels=80).cpu()
+    ref = O.log_mel_spectrogram(x, 80)
+    assert got.shape == (80, n // 160)
+    _check(got, ref, f"n={n}")
+
+
+@pytest.mark.parametrize("padding", [1, 160, 4000])
+def test_padding_argument(wft, cuda, padding):
+    x = S.make("white", n=32000, seed=5)
+    got = wft.log_mel_spectrogram(x.to(cuda), n_mels=128, padding=padding).cpu()
+    ref = O.log_mel_spectrogram(x, 128, padding=padding)
+    _check(got, ref, f"padding={padding}")
+
+
+def test_numpy_and_int16_inputs(wft, cuda):
+    xi = S.make("int16", n=64000)
+    got = wft.log_mel_spectrogram(xi.numpy(), n_mels=80, device="cuda").cpu()
+    ref = O.log_mel_spectrogram(xi, 80)
+    _check(got, ref, "int16 ndarray")
+    xf = xi.float() / 32768.0
+    got2 = wft.log_mel_spectrogram(xf.numpy(), n_mels=80, device="cuda").cpu()
+    assert torch.equal(got, got2), "int16 and the equivalent float32 PCM must give identical features"
+
+
+def test_batch_is_per_clip(wft, cuda):
+    """A batch must equal clip-by-clip calls (per-clip max, F6), not whisper's global max over the batch."""
+    xs = torch.stack([S.make("white", n=48000, seed=1), 1e-3 * S.make("white", n=48000, seed=2),
+                      S.make("zeros", n=48000), S.make("chirp", n=48000)])
+    got = wft.log_mel_spectrogram(xs.to(cuda), n_mels=128)
+    for b in range(xs.shape[0]):
+        one = wft.log_mel_spectrogram(xs[b].to(cuda), n_mels=128)
+        assert torch.equal(got[b], one)
+    _check(got.cpu(), O.log_mel_batch(xs, 128), "batch")
+
+
+def test_errors(wft, cuda):
+    with pytest.raises(ValueError):
+        wft.log_mel_spectrogram(torch.zeros(16000, device=cuda), n_mels=64)
+    with pytest.raises(NotImplementedError):
+        wft.log_mel_spectrogram("clip.wav")
+    with pytest.raises(ValueError):
+        wft.log_mel_spectrogram(torch.zeros(100, device=cuda), n_mels=80)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "i16"])
+def test_front_end_variable_length_cut_and_masks(wft, cuda, dtype):
+    """config 3 shape: ragged clips zero-padded in-kernel, 25% partial-segment cuts with min-pad, masks."""
+    rng = np.random.default_rng(42)
+    B = 12
+    lengths = rng.integers(16000, 480001, size=B).astype(np.int32)
+    lengths[0] = 480000
+    lengths[1] = 16000
+    pcm = torch.zeros(B, 480000)
+    for b in range(B):
+        pcm[b, : lengths[b]] = S.make("white", n=int(lengths[b]), seed=100 + b)
+    if dtype == "i16":
+        pcm = torch.round(pcm * 32767).to(torch.int16)
+    n_valid = np.full(B, -1, dtype=np.int32)
+    for b in range(0, B, 4):
+        n_valid[b] = int(rng.uniform(0.02, 30.0) * 100)
+    n_valid[4] = 1
+    masks = OS.draw_mask_params(42, 1000, B, 128, 3000, 100, 27, 1.0)
+    fe = wft.FrontEnd(n_mels=128, spec_augment=True,
+                      spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "p": 1.0}, seed=42)
+    got = fe(pcm.to(cuda), lengths=lengths, n_valid_frames=n_valid, clip_offset=1000).cpu()
+    ref = OP.front_end_batch(pcm, 128, lengths=lengths, n_valid_frames=n_valid, masks=masks)
+    assert got.shape == (B, 128, 3000)
+    _check(got, ref, "front end")
+    for b in range(B):
+        t0, t1, f0, f1 = masks[b]
+        m = torch.zeros(128, 3000, dtype=torch.bool)
+        m[:, t0:t1] = True
+        m[f0:f1, :] = True
+        assert torch.equal(got[b][m], torch.zeros(int(m.sum()))), "masked cells must be exactly 0.0"
+        if n_valid[b] >= 0:  # min-value pad: constant, equal to the minimum of the kept part (bit-exact property)
+            keep = int(n_valid[b])
+            unmasked_pad = got[b][:, keep:][~m[:, keep:]]
+            kept_min = wft.log_mel_spectrogram(pcm[b, : lengths[b]].to(cuda), n_mels=128,
+                                               padding=480000 - int(lengths[b]))[:, :keep].min().item()
+            assert unmasked_pad.numel() == 0 or (unmasked_pad == kept_min).all()
+
+
+def test_device_draw_matches_oracle_draw(wft, cuda):
+    for (seed, off, B, nm, T, F, p) in [(42, 0, 257, 128, 100, 27, 1.0), (7, 2**33 + 5, 64, 80, 100, 43, 0.5),
+                                        (0, 0, 5, 128, 0, 43, 1.0), (1, 9, 33, 80, 100, 43, 0.0)]:
+        got = wft.draw_mask_params(seed, off, B, nm, 3000, T, F, p).cpu().numpy()
+        ref = OS.draw_mask_params(seed, off, B, nm, 3000, T, F, p)
+        assert np.array_equal(got, ref)
+
+
+def test_mask_callables_replay_torchaudio(wft, cuda):
+    """Same torch seed -> same cells masked as the real torchaudio transforms (data_loader.py:286-287)."""
+    import torchaudio.transforms as T
+
+    mel = torch.randn(128, 3000)
+    for seed in range(20):
+        torch.manual_seed(seed)
+        ref = T.FrequencyMasking(27)(T.TimeMasking(100)(mel))
+        torch.manual_seed(seed)
+        got = wft.FrequencyMasking(27)(wft.TimeMasking(100)(mel.to(cuda)))
+        assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("shape,axis,length", [((80, 1234), -1, 3000), ((80, 3000), -1, 1500), ((128, 1), 1, 3000),
+                                               ((7, 50, 3), 1, 64), ((7, 50, 3), 0, 4), ((5000,), 0, 480000)])
+def test_pad_or_trim_bit_exact(wft, cuda, shape, axis, length):
+    from oracle.pad_or_trim import pad_or_trim as ref_pad
+
+    x = torch.randn(*shape) - 0.3
+    got = wft.pad_or_trim(x.to(cuda), length, axis=axis)
+    ref = ref_pad(x, length, axis=axis)
+    assert got.is_cuda and torch.equal(got.cpu(), ref)
+    got_np = wft.pad_or_trim(x.numpy(), length, axis=axis)
+    assert isinstance(got_np, np.ndarray) and np.array_equal(got_np, ref.numpy())
+    same = wft.pad_or_trim(x.to(cuda), x.shape[axis], axis=axis)
+    assert same.data_ptr() == x.to(cuda).data_ptr() or torch.equal(same.cpu(), x)
+
+
+def test_pad_or_trim_empty_raises(wft, cuda):
+    with pytest.raises(RuntimeError):
+        wft.pad_or_trim(torch.zeros(80, 0, device=cuda), 3000)
+
+
+def test_large_batch_roundtrip_properties(wft, cuda):
+    """BASELINE size (B=64, 128 mel): size-independent properties instead of a full oracle run."""
+    g = torch.Generator().manual_seed(0)
+    pcm = (0.1 * torch.randn(64, 480000, generator=g)).clamp(-1, 1)
+    pcm[5] *= 1e-3
+    pcm[9, 100000:] = 0
+    d = pcm.to(cuda)
+    a = wft.log_mel_spectrogram(d, n_mels=128)
+    b = wft.log_mel_spectrogram(d, n_mels=128)
+    assert torch.equal(a, b), "deterministic"
+    assert a.shape == (64, 128, 3000) and torch.isfinite(a).all()
+    rng = a.amax(dim=(1, 2)) - a.amin(dim=(1, 2))
+    assert (rng <= 2.0 + 1e-6).all()
+    perm = torch.randperm(64, generator=g)
+    c = wft.log_mel_spectrogram(d[perm.to(cuda)], n_mels=128)
+    assert torch.equal(c, a[perm.to(cuda)]), "clips are independent: permuting the batch permutes the output"
+    for bidx in (0, 5, 9, 63):
+        _check(a[bidx].cpu(), O.log_mel_spectrogram(pcm[bidx], 128), f"clip {bidx}")

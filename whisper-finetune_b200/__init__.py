@@ -1,0 +1,20 @@
+"""whisper-finetune_b200: the B200-native (sm_100a) Whisper audio front end.
+
+One hot path of i4Ds/whisper-finetune, rebuilt as hand-written CUDA behind the reference's own call surface:
+PCM -> log-mel -> cut / min-pad -> SpecAugment masks -> ``x[B, n_mels, 3000]``
+(``src/whisper_finetune/data/data_loader.py:273-292, 344-346, 362-367``).  See DESIGN.md / INTEGRATION.md.
+"""
+from .audio import (CHUNK_LENGTH, HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, frontend_forward,
+                    log_mel_spectrogram, pad_or_trim)
+from .augment import FrequencyMasking, TimeMasking, apply_masks, draw_mask_params
+from .frontend import FrontEnd
+from .install import install
+from .melbank import slaney_mel_bank
+from .sharding import all_gather_features, shard_indices
+
+__all__ = [
+    "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "CHUNK_LENGTH", "N_SAMPLES", "N_FRAMES",
+    "log_mel_spectrogram", "pad_or_trim", "frontend_forward", "FrontEnd",
+    "TimeMasking", "FrequencyMasking", "apply_masks", "draw_mask_params",
+    "shard_indices", "all_gather_features", "slaney_mel_bank", "install",
+]

@@ -1,0 +1,332 @@
+// C-ABI shim of the B200-native Whisper front end (see include/wft.h for the contract and the reference
+// file:line each entry point replaces).  Host code only validates, sizes the persistent grid and launches;
+// all arithmetic lives in frontend_kernel.cuh and the three small kernels below.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/wft.h"
+#include "frontend_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(WFT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define WFT_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+  } while (0)
+
+struct GridInfo {
+  int ctas = 0;
+  int smem = 0;
+  bool ready = false;
+};
+
+template <typename KernelT>
+int grid_for(KernelT kernel, GridInfo* cache, int* ctas) {
+  int dev = 0;
+  WFT_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(WFT_ERR_CUDA, "device ordinal out of range");
+  GridInfo& gi = cache[dev];
+  if (!gi.ready) {
+    WFT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wft::kSmemBytes));
+    int per_sm = 0, sms = 0;
+    WFT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wft::kThreads, wft::kSmemBytes));
+    WFT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (per_sm < 1) return fail(WFT_ERR_CUDA, "front-end kernel does not fit on this device");
+    gi.ctas = per_sm * sms;
+    gi.smem = wft::kSmemBytes;
+    gi.ready = true;
+  }
+  *ctas = gi.ctas;
+  return WFT_OK;
+}
+
+template <int NM, typename PcmT>
+int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream) {
+  static GridInfo cache[64];
+  int ctas = 0;
+  int rc = grid_for(wft::frontend_kernel<NM, PcmT>, cache, &ctas);
+  if (rc != WFT_OK) return rc;
+  if (ctas > p.total_tiles) ctas = p.total_tiles;
+  wft::frontend_kernel<NM, PcmT><<<ctas, wft::kThreads, wft::kSmemBytes, stream>>>(p);
+  ++g_launches;
+  WFT_CUDA(cudaGetLastError());
+  return WFT_OK;
+}
+
+template <int NM, typename PcmT>
+int query_grid(int32_t* ctas) {
+  static GridInfo cache[64];
+  int c = 0;
+  int rc = grid_for(wft::frontend_kernel<NM, PcmT>, cache, &c);
+  *ctas = c;
+  return rc;
+}
+
+size_t ws_header_bytes(int32_t batch) { return 16 + sizeof(wft::ClipStat) * static_cast<size_t>(batch); }
+
+// ---- small stand-alone kernels ---------------------------------------------------------------------------
+
+__global__ void min_reduce_kernel(const float* __restrict__ in, int64_t n, uint32_t* __restrict__ min_inv) {
+  float mn = INFINITY;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    mn = fminf(mn, __ldg(in + k));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMax(min_inv, ~wft::enc_ordered(mn));
+}
+
+// out[o, l, i] = l < len_in ? in[o, l, i] : min(in)      (data/utils.py:380-404)
+__global__ void pad_or_trim_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t outer,
+                                   int64_t len_in, int64_t inner, int64_t len_out,
+                                   const uint32_t* __restrict__ min_inv) {
+  const int64_t n = outer * len_out * inner;
+  const float fill = (len_out > len_in) ? wft::dec_ordered(~(*min_inv)) : 0.0f;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t i = k % inner;
+    const int64_t l = (k / inner) % len_out;
+    const int64_t o = k / (inner * len_out);
+    out[k] = (l < len_in) ? __ldg(in + (o * len_in + l) * inner + i) : fill;
+  }
+}
+
+// torchaudio mask_along_axis for time then frequency (data_loader.py:286-287), explicit intervals
+__global__ void specaug_apply_kernel(const float* __restrict__ in, float* __restrict__ out, int32_t n_rows,
+                                     int32_t n_frames, const int32_t* __restrict__ mask_params, float mask_value) {
+  const int b = blockIdx.y;
+  const int4 mk = __ldg(reinterpret_cast<const int4*>(mask_params) + b);
+  const int64_t per_clip = static_cast<int64_t>(n_rows) * n_frames;
+  const float* src = in + b * per_clip;
+  float* dst = out + b * per_clip;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < per_clip;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(k / n_frames);
+    const int t = static_cast<int>(k - static_cast<int64_t>(r) * n_frames);
+    const bool masked = (t >= mk.x && t < mk.y) || (r >= mk.z && r < mk.w);
+    if (masked) dst[k] = mask_value;
+    else if (src != dst) dst[k] = src[k];
+  }
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t w) { return static_cast<float>(w >> 8) * 5.9604644775390625e-08f; }
+
+// torchaudio interval: width = u*param ; start = trunc(u' * (size - width)) ; end = start + trunc(width)
+__device__ __forceinline__ void interval(float u_w, float u_s, int param, int size, int& a, int& b) {
+  if (param < 1) { a = 0; b = 0; return; }
+  const float value = __fmul_rn(u_w, static_cast<float>(param));
+  const float minv = __fmul_rn(u_s, __fsub_rn(static_cast<float>(size), value));
+  a = static_cast<int>(minv);
+  b = a + static_cast<int>(value);
+}
+
+__global__ void specaug_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_mels,
+                                    int32_t n_frames, int32_t tparam, int32_t fparam, float p,
+                                    int32_t* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const uint64_t idx = clip_offset + static_cast<uint64_t>(b);
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
+  uint32_t r[4];
+  philox4x32_10(lo, hi, 0u, 0u, k0, k1, r);
+  bool apply = p >= 1.0f;
+  if (!apply && p > 0.0f) {
+    uint32_t g[4];
+    philox4x32_10(lo, hi, 1u, 0u, k0, k1, g);
+    apply = u01(g[0]) < p;
+  }
+  int4 mk = make_int4(0, 0, 0, 0);
+  if (apply) {
+    interval(u01(r[0]), u01(r[1]), tparam, n_frames, mk.x, mk.y);
+    interval(u01(r[2]), u01(r[3]), fparam, n_mels, mk.z, mk.w);
+  }
+  reinterpret_cast<int4*>(out)[b] = mk;
+}
+
+int grid_1d(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int wft_abi_version(void) { return WFT_ABI_VERSION; }
+
+const char* wft_last_error(void) { return g_last_error.c_str(); }
+
+int64_t wft_launch_count(int reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int wft_frontend_workspace_bytes(int32_t batch, int32_t n_samples_total, int32_t n_frames_out, size_t* bytes) {
+  if (bytes == nullptr) return fail(WFT_ERR_INVALID, "bytes is NULL");
+  if (batch < 1) return fail(WFT_ERR_INVALID, "batch must be >= 1");
+  if (n_samples_total <= WFT_N_FFT / 2) return fail(WFT_ERR_INVALID, "clips must be longer than 200 samples (reflect pad)");
+  if (n_frames_out < 0) return fail(WFT_ERR_INVALID, "n_frames_out must be >= 0");
+  const int64_t n_frames = n_samples_total / WFT_HOP_LENGTH;
+  const int64_t span = n_frames_out > n_frames ? n_frames_out : n_frames;
+  const int64_t tiles = (span + wft::kTileFrames - 1) / wft::kTileFrames * batch;
+  if (tiles < 1 || tiles > INT32_MAX / 2) return fail(WFT_ERR_INVALID, "batch x frames out of range");
+  size_t b = ws_header_bytes(batch) + static_cast<size_t>(tiles) * sizeof(int32_t);
+  *bytes = (b + 255) & ~static_cast<size_t>(255);
+  return WFT_OK;
+}
+
+int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
+  if (a == nullptr) return fail(WFT_ERR_INVALID, "args is NULL");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (a->pcm == nullptr || a->out == nullptr || a->workspace == nullptr)
+    return fail(WFT_ERR_INVALID, "pcm, out and workspace must be non-NULL device pointers");
+  if (a->n_mels != 80 && a->n_mels != 128) return fail(WFT_ERR_INVALID, "Unsupported n_mels: " + std::to_string(a->n_mels));
+  if (a->pcm_dtype != WFT_PCM_F32 && a->pcm_dtype != WFT_PCM_I16) return fail(WFT_ERR_INVALID, "pcm_dtype must be WFT_PCM_F32 or WFT_PCM_I16");
+  if (a->batch < 1) return fail(WFT_ERR_INVALID, "batch must be >= 1");
+  if (a->n_samples < 1 || a->padding < 0) return fail(WFT_ERR_INVALID, "n_samples must be >= 1 and padding >= 0");
+  if (a->clip_stride < a->n_samples) return fail(WFT_ERR_INVALID, "clip_stride must be >= n_samples");
+  const int64_t n_total64 = static_cast<int64_t>(a->n_samples) + a->padding;
+  if (n_total64 > INT32_MAX / 4) return fail(WFT_ERR_INVALID, "clip too long");
+  const int32_t n_total = static_cast<int32_t>(n_total64);
+  if (n_total <= WFT_N_FFT / 2) return fail(WFT_ERR_INVALID, "clips must be longer than 200 samples (reflect pad)");
+  const int32_t n_frames = n_total / WFT_HOP_LENGTH;
+  if (n_frames < 1) return fail(WFT_ERR_INVALID, "clip shorter than one hop");
+  const int32_t n_frames_out = a->n_frames_out > 0 ? a->n_frames_out : n_frames;
+  size_t need = 0;
+  int rc = wft_frontend_workspace_bytes(a->batch, n_total, n_frames_out, &need);
+  if (rc != WFT_OK) return rc;
+  if (a->workspace_bytes < need) return fail(WFT_ERR_INVALID, "workspace too small: need " + std::to_string(need) + " bytes");
+  if ((reinterpret_cast<uintptr_t>(a->workspace) & 15) != 0) return fail(WFT_ERR_INVALID, "workspace must be 16-byte aligned");
+  if (a->mask_params != nullptr && (reinterpret_cast<uintptr_t>(a->mask_params) & 15) != 0)
+    return fail(WFT_ERR_INVALID, "mask_params must be 16-byte aligned");
+  if (((n_frames_out & 3) == 0) && (reinterpret_cast<uintptr_t>(a->out) & 15) != 0)
+    return fail(WFT_ERR_INVALID, "out must be 16-byte aligned");
+
+  wft::FrontendParams p{};
+  p.pcm = a->pcm;
+  p.clip_stride = a->clip_stride;
+  p.lengths = a->lengths;
+  p.n_valid = a->n_valid_frames;
+  p.masks = a->mask_params;
+  p.out = a->out;
+  uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+  p.tile_counter = reinterpret_cast<uint32_t*>(ws);
+  p.stats = reinterpret_cast<wft::ClipStat*>(ws + 16);
+  p.next = reinterpret_cast<int32_t*>(ws + ws_header_bytes(a->batch));
+  p.n_samples = a->n_samples;
+  p.n_total = n_total;
+  p.batch = a->batch;
+  p.n_frames = n_frames;
+  p.n_frames_out = n_frames_out;
+  const int32_t span = n_frames_out > n_frames ? n_frames_out : n_frames;
+  p.tiles_per_clip = (span + wft::kTileFrames - 1) / wft::kTileFrames;
+  p.total_tiles = p.tiles_per_clip * a->batch;
+  p.mask_value = a->mask_value;
+
+  WFT_CUDA(cudaMemsetAsync(ws, 0, ws_header_bytes(a->batch), stream));
+  if (a->n_mels == 128) {
+    return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<128, float>(p, stream) : launch_frontend<128, int16_t>(p, stream);
+  }
+  return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<80, float>(p, stream) : launch_frontend<80, int16_t>(p, stream);
+}
+
+int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t* threads, int32_t* smem_bytes) {
+  if (ctas == nullptr || threads == nullptr || smem_bytes == nullptr) return fail(WFT_ERR_INVALID, "NULL output pointer");
+  if (n_mels != 80 && n_mels != 128) return fail(WFT_ERR_INVALID, "Unsupported n_mels: " + std::to_string(n_mels));
+  *threads = wft::kThreads;
+  *smem_bytes = wft::kSmemBytes;
+  if (n_mels == 128) return pcm_dtype == WFT_PCM_I16 ? query_grid<128, int16_t>(ctas) : query_grid<128, float>(ctas);
+  return pcm_dtype == WFT_PCM_I16 ? query_grid<80, int16_t>(ctas) : query_grid<80, float>(ctas);
+}
+
+int wft_pad_or_trim_f32(const float* in, int64_t outer, int64_t len_in, int64_t inner, int64_t len_out, float* out,
+                        void* scratch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (outer < 0 || len_in < 0 || inner < 0 || len_out < 0) return fail(WFT_ERR_INVALID, "negative extent");
+  const int64_t n_out = outer * len_out * inner;
+  if (n_out == 0) return WFT_OK;
+  if (out == nullptr) return fail(WFT_ERR_INVALID, "out is NULL");
+  const int64_t n_in = outer * len_in * inner;
+  if (len_out > len_in) {
+    if (n_in == 0) return fail(WFT_ERR_INVALID, "pad_or_trim: cannot take the minimum of an empty array");
+    if (scratch == nullptr) return fail(WFT_ERR_INVALID, "scratch is NULL");
+    if (in == nullptr) return fail(WFT_ERR_INVALID, "in is NULL");
+    WFT_CUDA(cudaMemsetAsync(scratch, 0, 16, stream));
+    min_reduce_kernel<<<grid_1d(n_in, 256), 256, 0, stream>>>(in, n_in, static_cast<uint32_t*>(scratch));
+    ++g_launches;
+    WFT_CUDA(cudaGetLastError());
+  } else if (in == nullptr) {
+    return fail(WFT_ERR_INVALID, "in is NULL");
+  }
+  pad_or_trim_kernel<<<grid_1d(n_out, 256), 256, 0, stream>>>(in, out, outer, len_in, inner, len_out,
+                                                               static_cast<const uint32_t*>(scratch));
+  ++g_launches;
+  WFT_CUDA(cudaGetLastError());
+  return WFT_OK;
+}
+
+int wft_specaug_apply_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames,
+                          const int32_t* mask_params, float mask_value, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (batch < 0 || n_rows < 0 || n_frames < 0) return fail(WFT_ERR_INVALID, "negative extent");
+  if (static_cast<int64_t>(batch) * n_rows * n_frames == 0) return WFT_OK;
+  if (in == nullptr || out == nullptr || mask_params == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
+  if ((reinterpret_cast<uintptr_t>(mask_params) & 15) != 0) return fail(WFT_ERR_INVALID, "mask_params must be 16-byte aligned");
+  if (batch > 65535) return fail(WFT_ERR_INVALID, "batch too large for one launch (max 65535)");
+  dim3 grid(grid_1d(static_cast<int64_t>(n_rows) * n_frames, 256), batch);
+  specaug_apply_kernel<<<grid, 256, 0, stream>>>(in, out, n_rows, n_frames, mask_params, mask_value);
+  ++g_launches;
+  WFT_CUDA(cudaGetLastError());
+  return WFT_OK;
+}
+
+int wft_specaug_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_mels, int32_t n_frames,
+                     int32_t time_mask_param, int32_t freq_mask_param, float p, int32_t* mask_params_out,
+                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (batch < 1) return fail(WFT_ERR_INVALID, "batch must be >= 1");
+  if (n_mels < 1 || n_frames < 1) return fail(WFT_ERR_INVALID, "n_mels and n_frames must be >= 1");
+  if (!(p >= 0.0f && p <= 1.0f)) return fail(WFT_ERR_INVALID, "spec_augment p must be between 0 and 1");
+  if (mask_params_out == nullptr) return fail(WFT_ERR_INVALID, "mask_params_out is NULL");
+  if ((reinterpret_cast<uintptr_t>(mask_params_out) & 15) != 0) return fail(WFT_ERR_INVALID, "mask_params_out must be 16-byte aligned");
+  specaug_draw_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(seed, clip_offset, batch, n_mels, n_frames,
+                                                               time_mask_param, freq_mask_param, p, mask_params_out);
+  ++g_launches;
+  WFT_CUDA(cudaGetLastError());
+  return WFT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+"""Batched front end: what ``AudioDataset.__getitem__`` + ``collate_fn`` produce for a whole batch, in one launch.
+
+``FrontEnd`` carries the knobs of the reference's YAML (``augmentation.spec_augment.{apply,p,time_mask_param,
+freq_mask_param}``, read at ``src/whisper_finetune/data/data_loader.py:109-117``; ``n_mels`` comes from the model,
+``scripts/finetune.py:644``) and maps a batch of raw PCM to ``x[B, n_mels, 3000]``:
+
+    zero pad to 480000 (data_loader.py:346) -> log-mel (:278) -> partial-segment cut (:279-280) -> min-value
+    pad_or_trim (:281-282) -> time mask, frequency mask (:286-287) -> stacked like collate_fn (:362-367)
+
+The masks of clip ``b`` are a pure function of ``(seed, clip_offset + b)``, so a DistributedSampler shard
+reproduces them on any number of GPUs.
+"""
+from typing import Optional
+
+import torch
+
+from .audio import N_FRAMES, N_SAMPLES, frontend_forward, resolve_device
+from .augment import draw_mask_params
+
+
+class FrontEnd:
+    def __init__(self, n_mels: int = 80, device=None, spec_augment: bool = False,
+                 spec_augment_params: Optional[dict] = None, seed: int = 0, n_samples: int = N_SAMPLES,
+                 n_frames: int = N_FRAMES):
+        if n_mels not in (80, 128):
+            raise ValueError(f"Unsupported n_mels: {n_mels}")
+        self.n_mels = n_mels
+        self.device = resolve_device(device)
+        self.seed = int(seed)
+        self.n_samples = int(n_samples)
+        self.n_frames = int(n_frames)
+        self.spec_augment = bool(spec_augment)
+        if spec_augment:
+            params = spec_augment_params or {}
+            self.spec_augment_p = float(params.get("p", 1.0))
+            if not 0.0 <= self.spec_augment_p <= 1.0:
+                raise ValueError(f"spec_augment p must be between 0 and 1, got {self.spec_augment_p}")
+            self.time_mask_param = int(params["time_mask_param"])
+            self.freq_mask_param = int(params["freq_mask_param"])
+        else:
+            self.spec_augment_p = 0.0
+            self.time_mask_param = 0
+            self.freq_mask_param = 0
+
+    def __call__(self, pcm: torch.Tensor, lengths=None, n_valid_frames=None, clip_offset: int = 0,
+                 mask_params: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``pcm`` ``[B, N<=480000]`` float32 / int16 (host or device) -> ``[B, n_mels, 3000]`` on the device."""
+        if not torch.is_tensor(pcm):
+            pcm = torch.as_tensor(pcm)
+        if pcm.dim() != 2:
+            raise ValueError("pcm must be [B, N]")
+        if pcm.shape[1] > self.n_samples:
+            raise ValueError(f"clips longer than {self.n_samples} samples must be chunked upstream")
+        pcm = pcm.to(self.device, non_blocking=True)
+        B, N = pcm.shape
+        if mask_params is None and self.spec_augment and self.spec_augment_p > 0.0:
+            mask_params = draw_mask_params(self.seed, clip_offset, B, self.n_mels, self.n_frames,
+                                           self.time_mask_param, self.freq_mask_param, self.spec_augment_p,
+                                           self.device)
+        return frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
+                                n_frames_out=self.n_frames, n_valid_frames=n_valid_frames,
+                                mask_params=mask_params, mask_value=0.0, out=out)
