@@ -1,0 +1,34 @@
+// standalone driver: calls the C ABI without torch (fast start under ncu)
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../include/wft.h"
+extern "C" int wft_debug_read(int*);
+int main(int argc, char** argv) {
+  int B = argc > 1 ? atoi(argv[1]) : 16, nm = argc > 2 ? atoi(argv[2]) : 128, iters = argc > 3 ? atoi(argv[3]) : 4;
+  size_t n = (size_t)B * 480000;
+  std::vector<float> h(n);
+  unsigned s = 12345;
+  for (size_t i = 0; i < n; ++i) { s = s * 1664525u + 1013904223u; h[i] = ((s >> 8) * (1.0f / 16777216.0f) - 0.5f) * 0.2f; }
+  float *d_pcm, *d_out; void* ws; size_t wsb = 0;
+  cudaMalloc(&d_pcm, n * 4); cudaMemcpy(d_pcm, h.data(), n * 4, cudaMemcpyHostToDevice);
+  cudaMalloc(&d_out, (size_t)B * nm * 3000 * 4);
+  wft_frontend_workspace_bytes(B, 480000, 3000, &wsb); cudaMalloc(&ws, wsb);
+  wft_frontend_args a{}; a.pcm = d_pcm; a.pcm_dtype = WFT_PCM_F32; a.batch = B; a.clip_stride = 480000; a.n_samples = 480000;
+  a.n_mels = nm; a.n_frames_out = 3000; a.out = d_out; a.workspace = ws; a.workspace_bytes = wsb;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int it = 0; it < iters; ++it) {
+    cudaEventRecord(e0);
+    int rc = wft_frontend_forward(&a, 0);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    printf("iter %d rc=%d cuda=%s %.1f us (%.3f us/clip)\n", it, rc, cudaGetErrorString(e), ms * 1e3, ms * 1e3 / B);
+  }
+#ifdef WFT_DEBUG_SPIN
+  int dbg[8]; wft_debug_read(dbg);
+  printf("debug: hit=%d tile=%d done=%d counter=%d cta=%d n_ring=%d chain=%d total=%d\n", dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[5], dbg[6], dbg[7]);
+#endif
+  return 0;
+}
