@@ -228,6 +228,8 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
   size_t need = 0;
   int rc = wft_frontend_workspace_bytes(a->batch, n_total, n_frames_out, &need);
   if (rc != WFT_OK) return rc;
+  if (static_cast<int64_t>(a->n_mels) * n_frames_out * 4 >= (int64_t(1) << 32))
+    return fail(WFT_ERR_INVALID, "n_frames_out too large");
   if (a->workspace_bytes < need) return fail(WFT_ERR_INVALID, "workspace too small: need " + std::to_string(need) + " bytes");
   if ((reinterpret_cast<uintptr_t>(a->workspace) & 15) != 0) return fail(WFT_ERR_INVALID, "workspace must be 16-byte aligned");
   if (a->mask_params != nullptr && (reinterpret_cast<uintptr_t>(a->mask_params) & 15) != 0)
@@ -255,6 +257,7 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
   p.tiles_per_clip = (span + wft::kTileFrames - 1) / wft::kTileFrames;
   p.total_tiles = p.tiles_per_clip * a->batch;
   p.mask_value = a->mask_value;
+  p.zero = 0u;
 
   WFT_CUDA(cudaMemsetAsync(ws, 0, ws_header_bytes(a->batch), stream));
   if (a->n_mels == 128) {
