@@ -187,3 +187,80 @@ def test_large_batch_roundtrip_properties(wft, cuda):
     assert torch.equal(c, a[perm.to(cuda)]), "clips are independent: permuting the batch permutes the output"
     for bidx in (0, 5, 9, 63):
         _check(a[bidx].cpu(), O.log_mel_spectrogram(pcm[bidx], 128), f"clip {bidx}")
+
+
+def _gold(name):
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name), allow_pickle=False)
+
+
+def test_front_end_against_reference_calculate_mel_goldens(wft, cuda):
+    """The fused kernel against outputs of the reference's own AudioDataset._calculate_mel (tests/golden/make_golden.py):
+    features within tolerance, masked cells and min-pad structure exact."""
+    z = _gold("calculate_mel.npz")
+    for k in range(int(z["n"])):
+        n, n_mels, nv, tp, fp, seed = (int(v) for v in z[f"meta{k}"])
+        x = S.make(str(z[f"kind{k}"]), n=n, seed=seed)
+        fe = wft.FrontEnd(n_mels=n_mels)
+        got = fe(x.unsqueeze(0).to(cuda), n_valid_frames=None if nv < 0 else [nv],
+                 mask_params=None if tp == 0 else z[f"mask{k}"][None, :])[0].cpu()
+        want_sub = torch.from_numpy(z[f"sub{k}"])
+        ma, rl = S.metrics(got[:, ::16], want_sub)
+        assert ma <= S.MAX_ABS and rl <= S.REL_L2, (k, ma, rl)
+        assert torch.equal(got[:, ::16] == 0, want_sub == 0)
+        assert float((got == 0).sum()) == float(z[f"sum{k}"][2])
+        assert abs(got.double().sum().item() - z[f"sum{k}"][0]) <= 1e-5 * z[f"sum{k}"][1]
+
+
+def test_logmel_against_transformers_goldens(wft, cuda):
+    z = _gold("logmel_hf.npz")
+    for k in range(int(z["n"])):
+        n, n_mels, seed = (int(v) for v in z[f"meta{k}"])
+        x = S.make(str(z[f"kind{k}"]), n=n, seed=seed)
+        got = wft.log_mel_spectrogram(x.to(cuda), n_mels=n_mels).cpu().numpy()
+        assert np.abs(got - z[f"out{k}"]).max() <= 3e-4
+
+
+def test_n_frames_out_longer_and_shorter_than_clip(wft, cuda):
+    """pad_or_trim fused both ways: output longer than the clip (min pad) and shorter (trim)."""
+    from oracle.pad_or_trim import pad_or_trim as ref_pad
+
+    x = S.make("white", n=40000, seed=77)
+    ref = O.log_mel_spectrogram(x, 80)  # [80, 250]
+    for T in (96, 250, 251, 300, 1000):
+        got = wft.frontend_forward(x.unsqueeze(0).to(cuda), 80, n_frames_out=T)[0].cpu()
+        want = ref_pad(ref, T)
+        assert got.shape == want.shape
+        ma, rl = S.metrics(got, want)
+        assert ma <= S.MAX_ABS and rl <= S.REL_L2
+        if T > 250:
+            assert (got[:, 250:] == got[:, :250].min()).all()
+
+
+def test_repeated_launches_and_streams_are_deterministic(wft, cuda):
+    x = torch.stack([S.make("white", n=480000, seed=s) for s in range(8)]).to(cuda)
+    ref = wft.log_mel_spectrogram(x, n_mels=128)
+    s1 = torch.cuda.Stream()
+    with torch.cuda.stream(s1):
+        for _ in range(20):
+            again = wft.log_mel_spectrogram(x, n_mels=128)
+            assert torch.equal(again, ref)
+    s1.synchronize()
+
+
+def test_host_pipeline_matches_direct_call(wft, cuda):
+    fe = wft.FrontEnd(n_mels=128, spec_augment=True,
+                      spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "p": 1.0}, seed=3)
+    host = torch.stack([S.make("white", n=480000, seed=40 + s) for s in range(6)]).pin_memory()
+    out = torch.empty(6, 128, 3000).pin_memory()
+    pipe = wft.HostPipeline(fe, 6, n_chunks=3, n_streams=2)
+    pipe(host, out, clip_offset=100)
+    pipe.synchronize()
+    direct = fe(host.to(cuda), clip_offset=100).cpu()
+    assert torch.equal(out, direct)
+    host16 = (host * 32767).round().to(torch.int16).pin_memory()
+    pipe16 = wft.HostPipeline(fe, 6, pcm_dtype=torch.int16, n_chunks=2, n_streams=2)
+    pipe16(host16, out, clip_offset=100)
+    pipe16.synchronize()
+    assert torch.equal(out, fe(host16.to(cuda), clip_offset=100).cpu())

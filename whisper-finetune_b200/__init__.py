@@ -7,14 +7,14 @@ PCM -> log-mel -> cut / min-pad -> SpecAugment masks -> ``x[B, n_mels, 3000]``
 from .audio import (CHUNK_LENGTH, HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, frontend_forward,
                     log_mel_spectrogram, pad_or_trim)
 from .augment import FrequencyMasking, TimeMasking, apply_masks, draw_mask_params
-from .frontend import FrontEnd
+from .frontend import FrontEnd, HostPipeline
 from .install import install
 from .melbank import slaney_mel_bank
 from .sharding import all_gather_features, shard_indices
 
 __all__ = [
     "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "CHUNK_LENGTH", "N_SAMPLES", "N_FRAMES",
-    "log_mel_spectrogram", "pad_or_trim", "frontend_forward", "FrontEnd",
+    "log_mel_spectrogram", "pad_or_trim", "frontend_forward", "FrontEnd", "HostPipeline",
     "TimeMasking", "FrequencyMasking", "apply_masks", "draw_mask_params",
     "shard_indices", "all_gather_features", "slaney_mel_bank", "install",
 ]

@@ -139,6 +139,8 @@ def log_mel_spectrogram(
 
     Returns a float32 CUDA tensor ``[n_mels, (N + padding) // 160]`` (``[B, n_mels, T]`` for a batch).
     """
+    if isinstance(audio, str):
+        raise NotImplementedError("loading audio from a path (ffmpeg) is not part of the front end; pass PCM samples")
     if n_mels not in (80, 128):
         raise ValueError(f"Unsupported n_mels: {n_mels}")
     if padding < 0:

@@ -60,3 +60,50 @@ class FrontEnd:
         return frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
                                 n_frames_out=self.n_frames, n_valid_frames=n_valid_frames,
                                 mask_params=mask_params, mask_value=0.0, out=out)
+
+
+class HostPipeline:
+    """End-to-end path for HOST-resident PCM: pinned host batch -> H2D -> fused front end -> D2H features.
+
+    This is the loader-integration shape of SURVEY 8(f)-4: DataLoader workers hand over raw PCM (``int16`` halves
+    the H2D bytes) and the features come back where ``collate_fn`` (data_loader.py:362-367) would have put them.
+    The batch is cut into ``n_chunks`` slices that travel on ``n_streams`` CUDA streams so that the H2D copy of
+    slice i+1, the kernel of slice i and the D2H copy of slice i-1 overlap (PCIe is full duplex).
+    """
+
+    def __init__(self, front_end: FrontEnd, batch: int, n_samples: int = N_SAMPLES, pcm_dtype=torch.float32,
+                 n_chunks: int = 4, n_streams: int = 2):
+        self.fe = front_end
+        self.batch = int(batch)
+        self.n_samples = int(n_samples)
+        self.n_chunks = max(1, min(int(n_chunks), self.batch))
+        dev = front_end.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, n_streams))]
+        bounds = torch.linspace(0, self.batch, self.n_chunks + 1).round().long().tolist()
+        self.slices = [(bounds[i], bounds[i + 1]) for i in range(self.n_chunks) if bounds[i + 1] > bounds[i]]
+        self.dev_pcm = torch.empty((self.batch, self.n_samples), dtype=pcm_dtype, device=dev)
+        self.dev_out = torch.empty((self.batch, front_end.n_mels, front_end.n_frames), dtype=torch.float32, device=dev)
+        self.h2d_bytes = self.dev_pcm.numel() * self.dev_pcm.element_size()
+        self.d2h_bytes = self.dev_out.numel() * 4
+
+    def __call__(self, pcm_host: torch.Tensor, out_host: torch.Tensor, lengths=None, n_valid_frames=None,
+                 clip_offset: int = 0) -> torch.Tensor:
+        """``pcm_host`` pinned ``[B, N]``, ``out_host`` pinned ``[B, n_mels, 3000]``; returns ``out_host`` once every
+        copy has been enqueued (call ``synchronize()`` before reading it)."""
+        cur = torch.cuda.current_stream(self.fe.device)
+        for k, (a, b) in enumerate(self.slices):
+            st = self.streams[k % len(self.streams)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                self.dev_pcm[a:b].copy_(pcm_host[a:b], non_blocking=True)
+                self.fe(self.dev_pcm[a:b],
+                        lengths=None if lengths is None else lengths[a:b],
+                        n_valid_frames=None if n_valid_frames is None else n_valid_frames[a:b],
+                        clip_offset=clip_offset + a, out=self.dev_out[a:b])
+                out_host[a:b].copy_(self.dev_out[a:b], non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        return out_host
+
+    def synchronize(self) -> None:
+        torch.cuda.current_stream(self.fe.device).synchronize()
