@@ -61,28 +61,47 @@ def synth_pcm(n_clips, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread (the timed region is
+    only milliseconds long, so spawning nvidia-smi per sample would miss it); falls back to nvidia-smi if NVML is absent."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.sm, self.bits = [], 0
+        self.sm_max = None
         self._stop = threading.Event()
         self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self.sm.append(float(self._nvml.nvmlDeviceGetClockInfo(self._h, self._nvml.NVML_CLOCK_SM)))
+                    self.bits |= int(self._nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    self._stop.wait(0.002)
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,"
+                                          "clocks_event_reasons.active", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.sm.append(float(out[0]))
+                    self.sm_max = float(out[1])
+                    self.bits |= int(out[2].strip(), 16)
+                    self._stop.wait(0.05)
             except Exception:
-                pass
-            self._stop.wait(0.1)
+                self._stop.wait(0.05)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -94,14 +113,11 @@ class ClockSampler:
         self._thread.join(timeout=6)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.sm_max,
+                "reasons": [name for bit, name in self.REASONS.items() if self.bits & bit], "samples": len(self.sm),
+                "sampler": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_clips_per_s(min_seconds, max_clips=None, threads=None):
@@ -130,7 +146,7 @@ def cpu_reference_clips_per_s(min_seconds, max_clips=None, threads=None):
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (here: its restatement in oracle/, since
     whisper.audio is a third-party dependency that is not installable offline) on all host threads.  A step is a
-    bounded sample of the workload: 32 of the 64 clips."""
+    bounded sample of the workload: one 64-clip batch (the same batch size the CUDA arm runs per step)."""
     import torch
 
     from oracle import pipeline as OP
@@ -141,7 +157,7 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n = 32
+    n = BATCH
     pcm = synth_pcm(n, SEED)
     masks = OS.draw_mask_params(SEED, 0, n, N_MELS, N_FRAMES, TIME_MASK, FREQ_MASK, 1.0)
     OP.front_end_batch(pcm[:2], N_MELS, masks=masks[:2])
@@ -215,6 +231,15 @@ def run_ours(args):
             step(i)
         ev1.record()
         barrier()
+        # the timed region lasts only milliseconds: keep the very same steps running for another ~0.4 s so that the
+        # clock / throttle-reason samples describe the GPU under this load (not part of the timing)
+        t_end = time.perf_counter() + 0.4
+        i = args.steps
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                step(i)
+                i += 1
+            torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     launches = int(lib.wft_launch_count(0))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
