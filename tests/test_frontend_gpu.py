@@ -224,7 +224,8 @@ def test_front_end_against_reference_calculate_mel_goldens(wft, cuda):
             keepmask[:, max(t0 - n_feat, 0):max(t1 - n_feat, 0)] = False
             unmasked = fe(x.unsqueeze(0).to(cuda), n_valid_frames=[nv])[0].cpu()  # same call without masks
             assert (pad[keepmask] == unmasked[:, :n_feat].min()).all()
-            assert (got_sub[:, ~cols] - want_sub[:, ~cols]).abs().max() <= S.MAX_ABS
+            if (~cols).any():
+                assert (got_sub[:, ~cols] - want_sub[:, ~cols]).abs().max() <= S.MAX_ABS
         assert torch.equal(got_sub == 0, want_sub == 0)
         assert float((got == 0).sum()) == float(z[f"sum{k}"][2])
         assert abs(got.double().sum().item() - z[f"sum{k}"][0]) <= 1e-4 * z[f"sum{k}"][1]

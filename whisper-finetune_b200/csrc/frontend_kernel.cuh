@@ -63,7 +63,7 @@ constexpr int kTwFloats = WFT_TWIDDLE_TABLE_LEN;                 // 880
 constexpr int kTwRow = WFT_TWIDDLE_ROW;                          // 44
 constexpr int kProgVec = WFT_MEL80_PROG_VEC > WFT_MEL128_PROG_VEC ? WFT_MEL80_PROG_VEC : WFT_MEL128_PROG_VEC;
 constexpr int kMaxPending = 8;
-constexpr int kCtlInts = 64;
+constexpr int kCtlInts = 96;
 constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats) * 4 + kProgVec * 16 + kCtlInts * 4;
 
 static_assert(kPFloats <= kAudioBase, "power tile and prefetched audio tile must not overlap");
@@ -233,8 +233,7 @@ struct FixupArgs {
 };
 
 template <int NM>
-__device__ __noinline__ void fixup_tile(const FixupArgs p, int tile, int tid) {
-  const int clip = tile / p.tiles_per_clip;
+__device__ __noinline__ void fixup_tile(const FixupArgs p, int tile, int clip, int tid) {
   const int t0 = (tile - clip * p.tiles_per_clip) * kTileFrames;
   const ClipStat* st = p.stats + clip;
   const float lmax = dec_ordered(__ldcg(&st->max_enc));
@@ -312,7 +311,32 @@ __device__ __forceinline__ FixupArgs make_fixup_args(const FrontendParams& p) {
 }
 
 // sm_ctl slots
-enum { kCtlNext = 0, kCtlReady = 1, kCtlDrain = 2, kCtlList = 8, kCtlRing = 16, kCtlRed = 32 };
+// [kCtlNext .. +5] = next tile: id, clip, first frame, interior flag, PCM element offset (lo, hi)
+enum { kCtlNext = 0, kCtlReady = 6, kCtlDrain = 7, kCtlDrainClip = 8, kCtlList = 16, kCtlListClip = 24, kCtlRing = 32,
+       kCtlRingClip = 40, kCtlRed = 48 };
+
+// thread 0: describe tile `t` for everybody (one division and one lengths[] load per tile instead of 320)
+template <typename PcmT>
+__device__ __forceinline__ void describe_tile(const FrontendParams& p, int t, int* __restrict__ slot) {
+  int clip = 0, t0 = 0, interior = 0;
+  long long off = 0;
+  if (t < p.total_tiles) {
+    clip = t / p.tiles_per_clip;
+    t0 = (t - clip * p.tiles_per_clip) * kTileFrames;
+    if (t0 < p.n_frames) {
+      int len = p.n_samples;
+      if (p.lengths != nullptr) {
+        const int l = __ldg(p.lengths + clip);
+        len = l < 0 ? 0 : (l < len ? l : len);
+      }
+      const int g0 = t0 * kHop - kNfft / 2;
+      off = static_cast<long long>(clip) * p.clip_stride + g0;
+      interior = tile_is_interior(reinterpret_cast<const PcmT*>(p.pcm) + off - g0, g0, len) ? 1 : 0;
+    }
+  }
+  slot[0] = t; slot[1] = clip; slot[2] = t0; slot[3] = interior;
+  slot[4] = static_cast<int>(off & 0xffffffffll); slot[5] = static_cast<int>(off >> 32);
+}
 
 template <int NM, typename PcmT>
 __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendParams p) {
@@ -337,9 +361,9 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
     const uint4* gp = NM == 128 ? g_mel128_prog : g_mel80_prog;
     for (int k = tid; k < kVecs; k += kThreads) sm_prog[k] = gp[k];
   }
-  if (tid == 0) sm_ctl[kCtlNext] = static_cast<int>(atomicAdd(p.tile_counter, 1u));
+  if (tid == 0) describe_tile<PcmT>(p, static_cast<int>(atomicAdd(p.tile_counter, 1u)), sm_ctl + kCtlNext);
   __syncthreads();
-  int cur = sm_ctl[kCtlNext];
+  int cur = sm_ctl[kCtlNext], clip = sm_ctl[kCtlNext + 1], t0 = sm_ctl[kCtlNext + 2];
   bool prefetched = false;
 
   const MelSpan* mel_idx = NM == 128 ? c_mel128_index[warp] : c_mel80_index[warp];
@@ -359,12 +383,10 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
   int chain = -1;
 
   while (cur < p.total_tiles) {
-    const TileCoord tc = tile_coord(p, cur);
-    const int clip = tc.clip, t0 = tc.t0;
     // claim the tile AFTER this one now; the answer is consumed two barriers later (latency hidden by stage A)
     int nxt_claim = 0;
     if (tid == 0) nxt_claim = static_cast<int>(atomicAdd(p.tile_counter, 1u));
-    int nxt = p.total_tiles;
+    int nxt = p.total_tiles, nxt_clip = 0, nxt_t0 = 0;
     uint32_t done_seen = 0;  // warp 0: `done` of the clip of ring[lane], sampled early, consumed at the end
 
     if (t0 < p.n_frames) {
@@ -385,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
 
       // stage A: thread (q, n2 = r): x[n1] = w[20 n1 + n2] * (pa + i pb)[20 n1 + n2] ------------------------------
       {
-        float xr[20], xi[20];
+        cpx x[20];
         {
           float u[28];
           const PcmT* a = sm_audio + (kSkewBlock + kSkew) * q + r;
@@ -399,81 +421,77 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int n1 = 4 * a4 + e;
-              xr[n1] = ww[e] * u[n1];
-              xi[n1] = ww[e] * u[n1 + 8];
+              x[n1] = make_float2(ww[e] * u[n1], ww[e] * u[n1 + 8]);
             }
           }
         }
         __syncthreads();  // audio is dead from here on: the region becomes the exchange buffer
-        dft20(xr, xi);
+        dft20(x);
         const float4* t4 = reinterpret_cast<const float4*>(sm_tw + r * kTwRow);
         float2* e2 = reinterpret_cast<float2*>(sm_region + q * kPairStride) + r;
 #pragma unroll
         for (int h = 0; h < 10; ++h) {
           const float4 t = t4[h];
           const int k0 = 2 * h, k1 = 2 * h + 1;
-          e2[k0 * (kRowStride / 2)] = make_float2(xr[k0] * t.x - xi[k0] * t.y, fmaf(xr[k0], t.y, xi[k0] * t.x));
-          e2[k1 * (kRowStride / 2)] = make_float2(xr[k1] * t.z - xi[k1] * t.w, fmaf(xr[k1], t.w, xi[k1] * t.z));
+          e2[k0 * (kRowStride / 2)] = make_float2(x[k0].x * t.x - x[k0].y * t.y, fmaf(x[k0].x, t.y, x[k0].y * t.x));
+          e2[k1 * (kRowStride / 2)] = make_float2(x[k1].x * t.z - x[k1].y * t.w, fmaf(x[k1].x, t.w, x[k1].y * t.z));
         }
       }
-      if (tid == 0) sm_ctl[kCtlNext] = nxt_claim;
+      if (tid == 0) describe_tile<PcmT>(p, nxt_claim, sm_ctl + kCtlNext);
       __syncthreads();
       nxt = sm_ctl[kCtlNext];
+      nxt_clip = sm_ctl[kCtlNext + 1];
+      nxt_t0 = sm_ctl[kCtlNext + 2];
 
-      // stage B: thread (q, k1 = r): Z[k1 + 20 k2] = DFT20 over n2, written back in place ---------------------------
+      // stage B: thread (q, k1 = r): Z[k1 + 20 k2] = DFT20 over n2.  The lower half (k2 < 10, bins k1 + 20 k2 <= 199)
+      // stays in registers; the upper half is what the mirror thread (q, 20 - k1) needs and goes back to the row.
+      // power: thread (q, j = r): bins j + 20 m (m = 0..9) against their mirrors Z[400 - j - 20 m] = row (20-j)%20,
+      // position 19 - m (row 0 mirrors itself one position further: 20 - m, so it publishes positions 11..20).
       {
-        float yr[20], yi[20];
-        float4* row4 = reinterpret_cast<float4*>(sm_region + q * kPairStride + r * kRowStride);
+        cpx z[10], mz[10];
+        {
+          cpx y[20];
+          float4* row4 = reinterpret_cast<float4*>(sm_region + q * kPairStride + r * kRowStride);
 #pragma unroll
-        for (int a = 0; a < 10; ++a) {
-          const float4 v = row4[a];
-          yr[2 * a] = v.x; yi[2 * a] = v.y;
-          yr[2 * a + 1] = v.z; yi[2 * a + 1] = v.w;
+          for (int a = 0; a < 10; ++a) {
+            const float4 v = row4[a];
+            y[2 * a] = make_float2(v.x, v.y);
+            y[2 * a + 1] = make_float2(v.z, v.w);
+          }
+          dft20(y);
+          if (r != 0) {
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+              row4[5 + a] = make_float4(y[10 + 2 * a].x, y[10 + 2 * a].y, y[11 + 2 * a].x, y[11 + 2 * a].y);
+          } else {
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+              row4[5 + a] = make_float4(y[11 + 2 * a].x, y[11 + 2 * a].y, y[(12 + 2 * a) % 20].x, y[(12 + 2 * a) % 20].y);
+          }
+#pragma unroll
+          for (int m = 0; m < 10; ++m) z[m] = y[m];
         }
-        dft20(yr, yi);
+        __syncthreads();
+        {
+          const float4* mir = reinterpret_cast<const float4*>(sm_region + q * kPairStride + ((20 - r) % 20) * kRowStride) + 5;
 #pragma unroll
-        for (int a = 0; a < 10; ++a) row4[a] = make_float4(yr[2 * a], yi[2 * a], yr[2 * a + 1], yi[2 * a + 1]);
-      }
-      __syncthreads();
-
-      // power: thread (q, j = r): bins j + 20 m (m = 0..9) against their mirrors in row (20 - j) % 20 -------------------
-      {
-        float zr[10], zi[10], mr[10], mi[10];
-        const float* own = sm_region + q * kPairStride + r * kRowStride;
-        const float* mir = sm_region + q * kPairStride + ((20 - r) % 20) * kRowStride + 2 * (10 + (r == 0 ? 1 : 0));
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-          const float4 v = reinterpret_cast<const float4*>(own)[a];
-          zr[2 * a] = v.x; zi[2 * a] = v.y;
-          zr[2 * a + 1] = v.z; zi[2 * a + 1] = v.w;
-        }
-#pragma unroll
-        for (int t = 0; t < 10; ++t) {
-          const float2 v = reinterpret_cast<const float2*>(mir)[t];
-          mr[t] = v.x; mi[t] = v.y;
+          for (int a = 0; a < 5; ++a) {
+            const float4 v = mir[a];
+            mz[2 * a] = make_float2(v.x, v.y);
+            mz[2 * a + 1] = make_float2(v.z, v.w);
+          }
         }
         __syncthreads();  // exchange is dead: the region becomes power tile (bottom) + next audio tile (top)
 
         // prefetch the NEXT tile's PCM into the top of the region
-        prefetched = false;
-        if (nxt < p.total_tiles) {
-          const TileCoord nc = tile_coord(p, nxt);
-          if (nc.t0 < p.n_frames) {
-            const PcmT* x = reinterpret_cast<const PcmT*>(p.pcm) + static_cast<size_t>(nc.clip) * p.clip_stride;
-            int len = p.n_samples;
-            if (p.lengths != nullptr) {
-              const int l = __ldg(p.lengths + nc.clip);
-              len = l < 0 ? 0 : (l < len ? l : len);
-            }
-            const int g0 = nc.t0 * kHop - kNfft / 2;
-            if (tile_is_interior(x, g0, len)) {
-              prefetch_audio<PcmT>(sm_audio, x + g0, tid);
-              prefetched = true;
-            }
-          }
+        prefetched = sm_ctl[kCtlNext + 3] != 0;
+        if (prefetched) {
+          const long long off = (static_cast<long long>(sm_ctl[kCtlNext + 5]) << 32) |
+                                static_cast<unsigned int>(sm_ctl[kCtlNext + 4]);
+          prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, tid);
         }
         if (warp == 0 && lane < n_ring)
-          done_seen = ld_relaxed(&p.stats[sm_ctl[kCtlRing + lane] / p.tiles_per_clip].done);
+          done_seen = ld_relaxed(&p.stats[sm_ctl[kCtlRingClip + lane]].done);
 
         // even frame 2q -> power row q, odd frame 2q+1 -> power row 16+q; row bases keep both the scattered
         // writes here and the lane<->row reads of the mel phase free of bank conflicts
@@ -481,11 +499,11 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
         float* po = pe + kPOddBase;
 #pragma unroll
         for (int m = 0; m < 10; ++m) {
-          // Z[k] = (zr, zi)[m], Z[400-k] = (mr, mi)[9-m] ; |Z[k] + conj Z[400-k]|^2 and |Z[k] - conj Z[400-k]|^2
-          const float sr = zr[m] + mr[9 - m], si = zi[m] - mi[9 - m];
-          const float dr = zr[m] - mr[9 - m], di = zi[m] + mi[9 - m];
-          pe[20 * m] = fmaf(sr, sr, si * si);
-          po[20 * m] = fmaf(dr, dr, di * di);
+          // Z[k] = z[m], Z[400-k] = mz[9-m]
+          const cpx sa = cfma(mz[9 - m], make_float2(1.0f, -1.0f), z[m]);   // Z[k] + conj Z[400-k]
+          const cpx sb = cfma(mz[9 - m], make_float2(-1.0f, 1.0f), z[m]);   // Z[k] - conj Z[400-k]
+          pe[20 * m] = fmaf(sa.x, sa.x, sa.y * sa.y);
+          po[20 * m] = fmaf(sb.x, sb.x, sb.y * sb.y);
         }
       }
       __syncthreads();
@@ -523,12 +541,14 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
       }
     } else {
       // pad-only tile (n_frames_out > n_frames): nothing to compute
-      if (tid == 0) sm_ctl[kCtlNext] = nxt_claim;
+      if (tid == 0) describe_tile<PcmT>(p, nxt_claim, sm_ctl + kCtlNext);
       __syncthreads();
       nxt = sm_ctl[kCtlNext];
+      nxt_clip = sm_ctl[kCtlNext + 1];
+      nxt_t0 = sm_ctl[kCtlNext + 2];
       prefetched = false;
       if (warp == 0 && lane < n_ring)
-        done_seen = ld_relaxed(&p.stats[sm_ctl[kCtlRing + lane] / p.tiles_per_clip].done);
+        done_seen = ld_relaxed(&p.stats[sm_ctl[kCtlRingClip + lane]].done);
       if (lane == 0) {
         reinterpret_cast<float*>(sm_ctl + kCtlRed)[2 * warp] = -INFINITY;
         reinterpret_cast<float*>(sm_ctl + kCtlRed)[2 * warp + 1] = INFINITY;
@@ -539,18 +559,29 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
     if (warp == 0) {
       const bool pending = lane < n_ring;
       const int mine = pending ? sm_ctl[kCtlRing + lane] : -1;
+      const int mine_clip = pending ? sm_ctl[kCtlRingClip + lane] : -1;
       const bool ready = pending && done_seen >= tiles_per_clip_u;
       const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
       const uint32_t wait_mask = __ballot_sync(0xffffffffu, pending && !ready);
       const uint32_t below = (1u << lane) - 1u;
       __syncwarp();
-      if (ready) sm_ctl[kCtlList + __popc(ready_mask & below)] = mine;
-      else if (pending) sm_ctl[kCtlRing + __popc(wait_mask & below)] = mine;
+      if (ready) {
+        sm_ctl[kCtlList + __popc(ready_mask & below)] = mine;
+        sm_ctl[kCtlListClip + __popc(ready_mask & below)] = mine_clip;
+      } else if (pending) {
+        sm_ctl[kCtlRing + __popc(wait_mask & below)] = mine;
+        sm_ctl[kCtlRingClip + __popc(wait_mask & below)] = mine_clip;
+      }
       n_ring = __popc(wait_mask);
       if (lane == 0) {
         sm_ctl[kCtlReady] = __popc(ready_mask);
-        if (n_ring < kMaxPending) sm_ctl[kCtlRing + n_ring] = cur;
-        else { p.next[cur] = chain; chain = cur; }  // park: never wait while tiles are unclaimed
+        if (n_ring < kMaxPending) {
+          sm_ctl[kCtlRing + n_ring] = cur;
+          sm_ctl[kCtlRingClip + n_ring] = clip;
+        } else {  // park: never wait while tiles are unclaimed
+          p.next[cur] = chain;
+          chain = cur;
+        }
       }
       if (n_ring < kMaxPending) ++n_ring;
     }
@@ -574,28 +605,31 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
       }
     }
     const int n_ready = sm_ctl[kCtlReady];
-    for (int k = 0; k < n_ready; ++k) fixup_tile<NM>(make_fixup_args(p), sm_ctl[kCtlList + k], tid);
+    for (int k = 0; k < n_ready; ++k) fixup_tile<NM>(make_fixup_args(p), sm_ctl[kCtlList + k], sm_ctl[kCtlListClip + k], tid);
     if (tid == 0) atomicAdd(&p.stats[clip].done, 1u + (dep & p.zero));
     cur = nxt;
+    clip = nxt_clip;
+    t0 = nxt_t0;
   }
 
   // drain: every tile is claimed by a running CTA now, so waiting on a clip's counter is safe
   for (;;) {
     __syncthreads();  // previous readers of sm_ctl are done
     if (tid == 0) {
-      int t = -1;
-      if (n_ring > 0) t = sm_ctl[kCtlRing + --n_ring];
-      else if (chain >= 0) { t = chain; chain = p.next[chain]; }
+      int t = -1, c = 0;
+      if (n_ring > 0) { --n_ring; t = sm_ctl[kCtlRing + n_ring]; c = sm_ctl[kCtlRingClip + n_ring]; }
+      else if (chain >= 0) { t = chain; c = t / p.tiles_per_clip; chain = p.next[chain]; }
       if (t >= 0) {
-        const uint32_t* d = &p.stats[t / p.tiles_per_clip].done;
+        const uint32_t* d = &p.stats[c].done;
         while (ld_relaxed(d) < tiles_per_clip_u) __nanosleep(100);
       }
       sm_ctl[kCtlDrain] = t;
+      sm_ctl[kCtlDrainClip] = c;
     }
     __syncthreads();
     const int t = sm_ctl[kCtlDrain];
     if (t < 0) break;
-    fixup_tile<NM>(make_fixup_args(p), t, tid);
+    fixup_tile<NM>(make_fixup_args(p), t, sm_ctl[kCtlDrainClip], tid);
   }
 }
 
