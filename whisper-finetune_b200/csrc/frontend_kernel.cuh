@@ -188,17 +188,35 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* addr) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(addr) : "memory");
   return v;
 }
+// one 16-byte snapshot {max_enc, min_inv, done, -} of a clip's statistics (a single L2 sector access)
+__device__ __forceinline__ uint4 ld_stat(const ClipStat* st) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(st) : "memory");
+  return v;
+}
 __device__ __forceinline__ float fast_log2(float x) {  // x is a normal float here: plain MUFU.LG2
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-// ---- mel projection: rows of one tap class; entry = (first_bin*4, row, w[0..C-1]) in (C+2)/4 uint4 -----------------
-// h.y holds the row's byte offset in `out` (row * pitch * 4, patched in at kernel start)
+// ---- mel projection: rows of one tap class; entry = (first_bin*4, row byte offset, w[0..C-1]) in (C+2)/4 uint4 ------
+// h.y holds the row's byte offset in `out` (row * pitch * 4, patched in at kernel start).  The value written is
+// already the final feature (L + 4) / 4 with the SpecAugment masks applied; only the per-clip max-8 floor and the
+// min-value pad are left to the (rare) fix-up.
+struct MelLane {
+  char* obase;        // &out[clip][0][frame]
+  bool store;         // this lane's frame is written
+  bool tmask;         // this lane's frame lies inside the time mask
+  uint32_t row_lo;    // frequency mask as a byte-offset window: masked iff (h.y - row_lo) < row_span
+  uint32_t row_span;
+  float mask_value;
+};
+
 template <int C>
 __device__ __forceinline__ void mel_rows(const uint4* __restrict__ prog, int count, const float* __restrict__ P,
-                                         char* __restrict__ obase, bool store, float& mx, float& mn) {
+                                         const MelLane& ln, float& mx, float& mn) {
 #pragma unroll 2
   for (int e = 0; e < count; ++e) {
     const uint4 h = prog[0];
@@ -217,12 +235,16 @@ __device__ __forceinline__ void mel_rows(const uint4* __restrict__ prog, int cou
     const float L = fast_log2(fmaxf(acc, 1e-10f)) * 0.301029995663981195f;
     mx = fmaxf(mx, L);
     mn = fminf(mn, L);
-    float* dst = reinterpret_cast<float*>(obase + h.y);
-    if (store) *dst = L;
+    const bool masked = ln.tmask || (h.y - ln.row_lo) < ln.row_span;
+    const float v = masked ? ln.mask_value : fmaf(L, 0.25f, 1.0f);   // (L + 4) / 4, exactly
+    if (ln.store) *reinterpret_cast<float*>(ln.obase + h.y) = v;
   }
 }
 
-// ---- deferred fix-up of one tile: floor at max-8, (x+4)/4, min-value pad, SpecAugment masks -------------------
+// ---- deferred fix-up of one tile (only tiles that need it, see `tile_needs_fixup`) -----------------------------------
+// The mel phase wrote v = (L + 4) / 4 with masks applied.  What may still be missing once the clip's max / min are
+// known: the floor max(L, max - 8)  ==  max(v, (max - 8 + 4) / 4)  (monotone map, exact), and the min-value pad of
+// the frames beyond the kept part (data/utils.py:380-404).  Masked cells keep the mask value.
 struct FixupArgs {
   float* out;
   const ClipStat* stats;
@@ -232,6 +254,23 @@ struct FixupArgs {
   float mask_value;
 };
 
+__device__ __forceinline__ int kept_frames(const int32_t* n_valid, int clip, int n_frames) {
+  int keep = n_frames;
+  if (n_valid != nullptr) {
+    const int nv = __ldg(n_valid + clip);
+    if (nv >= 0 && nv < keep) keep = nv;
+  }
+  return keep;
+}
+
+// does tile (clip, t0) still differ from its final value?  tile_min = min log10(mel) over the tile's live cells
+__device__ __forceinline__ bool tile_needs_fixup(float tile_min, uint32_t max_enc, int t0, int keep, int n_frames_out) {
+  const bool floor_binds = tile_min < dec_ordered(max_enc) - 8.0f;
+  const int hi = t0 + kTileFrames < n_frames_out ? t0 + kTileFrames : n_frames_out;
+  const bool has_pad = (t0 > keep ? t0 : keep) < hi;
+  return floor_binds || has_pad;
+}
+
 template <int NM>
 __device__ __noinline__ void fixup_tile(const FixupArgs p, int tile, int clip, int tid) {
   const int t0 = (tile - clip * p.tiles_per_clip) * kTileFrames;
@@ -239,12 +278,9 @@ __device__ __noinline__ void fixup_tile(const FixupArgs p, int tile, int clip, i
   const float lmax = dec_ordered(__ldcg(&st->max_enc));
   const float lmin = dec_ordered(~__ldcg(&st->min_inv));
   const float floorv = lmax - 8.0f;
+  const float floorn = fmaf(floorv, 0.25f, 1.0f);
   const float padv = fmaf(fmaxf(lmin, floorv), 0.25f, 1.0f);
-  int keep = p.n_frames;
-  if (p.n_valid != nullptr) {
-    const int nv = __ldg(p.n_valid + clip);
-    if (nv >= 0 && nv < keep) keep = nv;
-  }
+  const int keep = kept_frames(p.n_valid, clip, p.n_frames);
   int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
   if (p.masks != nullptr) {
     const int4 mk = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
@@ -265,25 +301,18 @@ __device__ __noinline__ void fixup_tile(const FixupArgs p, int tile, int clip, i
       v[it] = make_float4(padv, padv, padv, padv);
       if (row < NM && f < keep) v[it] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * pitch + f));
     }
-    // plain tile (no cut, no time mask inside): (max(x, floor) + 4) / 4 == fma(max(x, floor), 0.25, 1) exactly
-    const bool plain = (t0 + kTileFrames <= keep) && (mt1 <= t0 || mt0 >= t0 + kTileFrames || mt1 <= mt0);
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
       const int row = (tid + kThreads * it) >> 3;
       if (row < NM) {
         const bool rowmask = row >= mf0 && row < mf1;
         float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-        if (plain) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) e[c] = rowmask ? mv : fmaf(fmaxf(e[c], floorv), 0.25f, 1.0f);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int fc = f + c;
-            float r = (fc < keep) ? fmaf(fmaxf(e[c], floorv), 0.25f, 1.0f) : padv;
-            if (rowmask || (fc >= mt0 && fc < mt1)) r = mv;
-            e[c] = r;
-          }
+        for (int c = 0; c < 4; ++c) {
+          const int fc = f + c;
+          float r = (fc < keep) ? fmaxf(e[c], floorn) : padv;
+          if (rowmask || (fc >= mt0 && fc < mt1)) r = mv;
+          e[c] = r;
         }
         *reinterpret_cast<float4*>(base + static_cast<size_t>(row) * pitch + f) = make_float4(e[0], e[1], e[2], e[3]);
       }
@@ -295,7 +324,7 @@ __device__ __noinline__ void fixup_tile(const FixupArgs p, int tile, int clip, i
       if (f >= pitch) continue;
       float* ptr = base + static_cast<size_t>(row) * pitch + f;
       float r = padv;
-      if (f < keep) r = fmaf(fmaxf(__ldcg(ptr), floorv), 0.25f, 1.0f);
+      if (f < keep) r = fmaxf(__ldcg(ptr), floorn);
       if ((row >= mf0 && row < mf1) || (f >= mt0 && f < mt1)) r = mv;
       *ptr = r;
     }
@@ -313,7 +342,7 @@ __device__ __forceinline__ FixupArgs make_fixup_args(const FrontendParams& p) {
 // sm_ctl slots
 // [kCtlNext .. +5] = next tile: id, clip, first frame, interior flag, PCM element offset (lo, hi)
 enum { kCtlNext = 0, kCtlReady = 6, kCtlDrain = 7, kCtlDrainClip = 8, kCtlList = 16, kCtlListClip = 24, kCtlRing = 32,
-       kCtlRingClip = 40, kCtlRed = 48 };
+       kCtlRingClip = 40, kCtlRingMin = 48, kCtlRed = 56 };   // kCtlRed: 3 floats per warp (max, kept min, live min)
 
 // thread 0: describe tile `t` for everybody (one division and one lengths[] load per tile instead of 320)
 template <typename PcmT>
@@ -387,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
     int nxt_claim = 0;
     if (tid == 0) nxt_claim = static_cast<int>(atomicAdd(p.tile_counter, 1u));
     int nxt = p.total_tiles, nxt_clip = 0, nxt_t0 = 0;
-    uint32_t done_seen = 0;  // warp 0: `done` of the clip of ring[lane], sampled early, consumed at the end
+    uint4 stat_seen = make_uint4(0u, 0u, 0u, 0u);  // warp 0: snapshot of the clip of ring[lane], sampled early
 
     if (t0 < p.n_frames) {
       // stage 0 ---------------------------------------------------------------------------------------------
@@ -490,8 +519,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
                                 static_cast<unsigned int>(sm_ctl[kCtlNext + 4]);
           prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, tid);
         }
-        if (warp == 0 && lane < n_ring)
-          done_seen = ld_relaxed(&p.stats[sm_ctl[kCtlRingClip + lane]].done);
+        if (warp == 0 && lane < n_ring) stat_seen = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
 
         // even frame 2q -> power row q, odd frame 2q+1 -> power row 16+q; row bases keep both the scattered
         // writes here and the lane<->row reads of the mel phase free of bank conflicts
@@ -513,30 +541,44 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
         const int frame = t0 + (lane < 16 ? 2 * lane : 2 * (lane - 16) + 1);
         const float* P = sm_region + (lane < 16 ? lane * kPStride + (lane >= 8 ? 1 : 0)
                                                 : kPOddBase + (lane - 16) * kPStride + (lane >= 24 ? 1 : 0));
-        int keep = p.n_frames;
-        if (p.n_valid != nullptr) {
-          const int nv = __ldg(p.n_valid + clip);
-          if (nv >= 0 && nv < keep) keep = nv;
-        }
+        const int keep = kept_frames(p.n_valid, clip, p.n_frames);
         const bool live = frame < p.n_frames;           // real frame of the clip: counts for the max
-        const bool kept = frame < keep;                 // survives the partial-segment cut: counts for the min
-        const bool store = live && frame < p.n_frames_out;
-        char* obase = reinterpret_cast<char*>(p.out + static_cast<size_t>(clip) * NM * p.n_frames_out + frame);
+        const bool kept = frame < keep;                 // survives the partial-segment cut: counts for the pad min
+        MelLane ln;
+        ln.store = live && frame < p.n_frames_out;
+        ln.obase = reinterpret_cast<char*>(p.out + static_cast<size_t>(clip) * NM * p.n_frames_out + frame);
+        ln.tmask = false;
+        ln.row_lo = 0u;
+        ln.row_span = 0u;
+        ln.mask_value = p.mask_value;
+        if (p.masks != nullptr) {
+          const int4 mk = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
+          const uint32_t row_bytes = static_cast<uint32_t>(p.n_frames_out) * 4u;
+          ln.tmask = frame >= mk.x && frame < mk.y;
+          if (mk.w > mk.z) {
+            ln.row_lo = static_cast<uint32_t>(mk.z) * row_bytes;
+            ln.row_span = static_cast<uint32_t>(mk.w - mk.z) * row_bytes;
+          }
+        }
         float mx = -INFINITY, mn = INFINITY;
-        mel_rows<2>(sm_prog + mel_idx[0].first, mel_idx[0].count, P, obase, store, mx, mn);
-        mel_rows<6>(sm_prog + mel_idx[1].first, mel_idx[1].count, P, obase, store, mx, mn);
-        mel_rows<10>(sm_prog + mel_idx[2].first, mel_idx[2].count, P, obase, store, mx, mn);
-        if constexpr (NM == 80) mel_rows<14>(sm_prog + mel_idx[3].first, mel_idx[3].count, P, obase, store, mx, mn);
+        mel_rows<2>(sm_prog + mel_idx[0].first, mel_idx[0].count, P, ln, mx, mn);
+        mel_rows<6>(sm_prog + mel_idx[1].first, mel_idx[1].count, P, ln, mx, mn);
+        mel_rows<10>(sm_prog + mel_idx[2].first, mel_idx[2].count, P, ln, mx, mn);
+        if constexpr (NM == 80) mel_rows<14>(sm_prog + mel_idx[3].first, mel_idx[3].count, P, ln, mx, mn);
         if (!live) mx = -INFINITY;
-        if (!kept) mn = INFINITY;
+        float mn_kept = kept ? mn : INFINITY;   // pad value of pad_or_trim: minimum over the kept frames
+        float mn_live = live ? mn : INFINITY;   // does the max-8 floor bind anywhere in this tile?
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          mn_kept = fminf(mn_kept, __shfl_xor_sync(0xffffffffu, mn_kept, o));
+          mn_live = fminf(mn_live, __shfl_xor_sync(0xffffffffu, mn_live, o));
         }
         if (lane == 0) {
-          reinterpret_cast<float*>(sm_ctl + kCtlRed)[2 * warp] = mx;
-          reinterpret_cast<float*>(sm_ctl + kCtlRed)[2 * warp + 1] = mn;
+          float* red = reinterpret_cast<float*>(sm_ctl + kCtlRed) + 3 * warp;
+          red[0] = mx;
+          red[1] = mn_kept;
+          red[2] = mn_live;
         }
       }
     } else {
@@ -547,66 +589,79 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
       nxt_clip = sm_ctl[kCtlNext + 1];
       nxt_t0 = sm_ctl[kCtlNext + 2];
       prefetched = false;
-      if (warp == 0 && lane < n_ring)
-        done_seen = ld_relaxed(&p.stats[sm_ctl[kCtlRingClip + lane]].done);
+      if (warp == 0 && lane < n_ring) stat_seen = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
       if (lane == 0) {
-        reinterpret_cast<float*>(sm_ctl + kCtlRed)[2 * warp] = -INFINITY;
-        reinterpret_cast<float*>(sm_ctl + kCtlRed)[2 * warp + 1] = INFINITY;
+        float* red = reinterpret_cast<float*>(sm_ctl + kCtlRed) + 3 * warp;
+        red[0] = -INFINITY;
+        red[1] = INFINITY;
+        red[2] = INFINITY;
       }
     }
 
-    // warp 0 sorts the pending ring into "ready" (fix up now) and "still waiting", before the barrier
+    // warp 0 looks at the pending ring: a tile whose clip is complete either needs the fix-up (floor binds or it
+    // carries pad frames) or is already final and simply leaves the ring; everything else keeps waiting
     if (warp == 0) {
       const bool pending = lane < n_ring;
       const int mine = pending ? sm_ctl[kCtlRing + lane] : -1;
-      const int mine_clip = pending ? sm_ctl[kCtlRingClip + lane] : -1;
-      const bool ready = pending && done_seen >= tiles_per_clip_u;
+      const int mine_clip = pending ? sm_ctl[kCtlRingClip + lane] : 0;
+      const float mine_min = pending ? __int_as_float(sm_ctl[kCtlRingMin + lane]) : 0.0f;
+      const bool complete = pending && stat_seen.z >= tiles_per_clip_u;
+      bool ready = false;
+      if (complete) {
+        const int mt0 = (mine - mine_clip * p.tiles_per_clip) * kTileFrames;
+        ready = tile_needs_fixup(mine_min, stat_seen.x, mt0, kept_frames(p.n_valid, mine_clip, p.n_frames), p.n_frames_out);
+      }
       const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
-      const uint32_t wait_mask = __ballot_sync(0xffffffffu, pending && !ready);
+      const uint32_t wait_mask = __ballot_sync(0xffffffffu, pending && !complete);
       const uint32_t below = (1u << lane) - 1u;
       __syncwarp();
       if (ready) {
         sm_ctl[kCtlList + __popc(ready_mask & below)] = mine;
         sm_ctl[kCtlListClip + __popc(ready_mask & below)] = mine_clip;
-      } else if (pending) {
+      } else if (pending && !complete) {
         sm_ctl[kCtlRing + __popc(wait_mask & below)] = mine;
         sm_ctl[kCtlRingClip + __popc(wait_mask & below)] = mine_clip;
+        sm_ctl[kCtlRingMin + __popc(wait_mask & below)] = __float_as_int(mine_min);
       }
       n_ring = __popc(wait_mask);
-      if (lane == 0) {
-        sm_ctl[kCtlReady] = __popc(ready_mask);
-        if (n_ring < kMaxPending) {
-          sm_ctl[kCtlRing + n_ring] = cur;
-          sm_ctl[kCtlRingClip + n_ring] = clip;
-        } else {  // park: never wait while tiles are unclaimed
-          p.next[cur] = chain;
-          chain = cur;
-        }
-      }
-      if (n_ring < kMaxPending) ++n_ring;
+      if (lane == 0) sm_ctl[kCtlReady] = __popc(ready_mask);
     }
     __syncthreads();  // tile finished: power tile free, ready list and per-warp max/min visible
 
-    // publish the tile's statistics: two returning atomics now, the completion count after they have returned
-    // (true data dependency through p.zero) -- no fence, so nobody waits for the tile's stores to drain
-    uint32_t dep = 0;
+    // publish the tile's statistics: two returning atomics, then the completion count with a true data dependency on
+    // their results (through p.zero) -- no fence, so nobody waits for the tile's stores to drain.  The tile itself
+    // joins the pending ring (or is parked: a CTA never waits while tiles are unclaimed).
     if (warp == 0) {
-      float mx = lane < kWarps ? reinterpret_cast<const float*>(sm_ctl + kCtlRed)[2 * lane] : -INFINITY;
-      float mn = lane < kWarps ? reinterpret_cast<const float*>(sm_ctl + kCtlRed)[2 * lane + 1] : INFINITY;
+      const float* red = reinterpret_cast<const float*>(sm_ctl + kCtlRed) + 3 * (lane < kWarps ? lane : 0);
+      float mx = lane < kWarps ? red[0] : -INFINITY;
+      float mn_kept = lane < kWarps ? red[1] : INFINITY;
+      float mn_live = lane < kWarps ? red[2] : INFINITY;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mn_kept = fminf(mn_kept, __shfl_xor_sync(0xffffffffu, mn_kept, o));
+        mn_live = fminf(mn_live, __shfl_xor_sync(0xffffffffu, mn_live, o));
       }
       if (lane == 0) {
         ClipStat* cs = p.stats + clip;
+        uint32_t dep = 0;
         if (mx > -INFINITY) dep |= atomicMax(&cs->max_enc, enc_ordered(mx));
-        if (mn < INFINITY) dep |= atomicMax(&cs->min_inv, ~enc_ordered(mn));
+        if (mn_kept < INFINITY) dep |= atomicMax(&cs->min_inv, ~enc_ordered(mn_kept));
+        if (n_ring < kMaxPending) {
+          sm_ctl[kCtlRing + n_ring] = cur;
+          sm_ctl[kCtlRingClip + n_ring] = clip;
+          sm_ctl[kCtlRingMin + n_ring] = __float_as_int(mn_live);
+        } else {
+          p.next[cur] = chain;                       // parked tiles are re-examined (conservatively) in the drain
+          chain = cur;
+        }
+        atomicAdd(&cs->done, 1u + (dep & p.zero));
       }
+      if (n_ring < kMaxPending) ++n_ring;
+      __syncwarp();
     }
     const int n_ready = sm_ctl[kCtlReady];
     for (int k = 0; k < n_ready; ++k) fixup_tile<NM>(make_fixup_args(p), sm_ctl[kCtlList + k], sm_ctl[kCtlListClip + k], tid);
-    if (tid == 0) atomicAdd(&p.stats[clip].done, 1u + (dep & p.zero));
     cur = nxt;
     clip = nxt_clip;
     t0 = nxt_t0;
@@ -617,11 +672,28 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
     __syncthreads();  // previous readers of sm_ctl are done
     if (tid == 0) {
       int t = -1, c = 0;
-      if (n_ring > 0) { --n_ring; t = sm_ctl[kCtlRing + n_ring]; c = sm_ctl[kCtlRingClip + n_ring]; }
-      else if (chain >= 0) { t = chain; c = t / p.tiles_per_clip; chain = p.next[chain]; }
-      if (t >= 0) {
-        const uint32_t* d = &p.stats[c].done;
-        while (ld_relaxed(d) < tiles_per_clip_u) __nanosleep(100);
+      for (;;) {
+        float tmin = -INFINITY;  // parked tiles lost their minimum: treat them as needing the fix-up
+        if (n_ring > 0) {
+          --n_ring;
+          t = sm_ctl[kCtlRing + n_ring];
+          c = sm_ctl[kCtlRingClip + n_ring];
+          tmin = __int_as_float(sm_ctl[kCtlRingMin + n_ring]);
+        } else if (chain >= 0) {
+          t = chain;
+          c = t / p.tiles_per_clip;
+          chain = p.next[chain];
+        } else {
+          t = -1;
+          break;
+        }
+        uint4 st = ld_stat(p.stats + c);
+        while (st.z < tiles_per_clip_u) {
+          __nanosleep(100);
+          st = ld_stat(p.stats + c);
+        }
+        const int tt0 = (t - c * p.tiles_per_clip) * kTileFrames;
+        if (tile_needs_fixup(tmin, st.x, tt0, kept_frames(p.n_valid, c, p.n_frames), p.n_frames_out)) break;
       }
       sm_ctl[kCtlDrain] = t;
       sm_ctl[kCtlDrainClip] = c;
