@@ -188,6 +188,12 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* addr) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(addr) : "memory");
   return v;
 }
+// barrier over one half of the CTA (warps 0-4 = frame pairs 0-7, warps 5-9 = pairs 8-15): the stage A -> stage B ->
+// power hand-offs only involve the 20 threads of a pair, so the halves need not wait for each other there
+__device__ __forceinline__ void half_cta_sync(int half) {
+  asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(kThreads / 2) : "memory");
+}
+
 // one 16-byte snapshot {max_enc, min_inv, done, -} of a clip's statistics (a single L2 sector access)
 __device__ __forceinline__ uint4 ld_stat(const ClipStat* st) {
   uint4 v;
@@ -207,7 +213,7 @@ __device__ __forceinline__ float fast_log2(float x) {  // x is a normal float he
 // min-value pad are left to the (rare) fix-up.
 struct MelLane {
   char* obase;        // &out[clip][0][frame]
-  bool store;         // this lane's frame is written
+  uint32_t store;     // != 0: this lane's frame is written
   bool tmask;         // this lane's frame lies inside the time mask
   uint32_t row_lo;    // frequency mask as a byte-offset window: masked iff (h.y - row_lo) < row_span
   uint32_t row_span;
@@ -237,7 +243,10 @@ __device__ __forceinline__ void mel_rows(const uint4* __restrict__ prog, int cou
     mn = fminf(mn, L);
     const bool masked = ln.tmask || (h.y - ln.row_lo) < ln.row_span;
     const float v = masked ? ln.mask_value : fmaf(L, 0.25f, 1.0f);   // (L + 4) / 4, exactly
-    if (ln.store) *reinterpret_cast<float*>(ln.obase + h.y) = v;
+    // predicated store at obase + h.y (one IMAD.WIDE, no branch around the store)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %3, 0;\n\tmad.wide.u32 a, %1, 1, %0;\n\t"
+        "@p st.global.f32 [a], %2;\n\t}\n" ::"l"(ln.obase), "r"(h.y), "f"(v), "r"(ln.store) : "memory");
   }
 }
 
@@ -410,6 +419,13 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
   // warp-0 scheduler state: ring of tiles whose fix-up is pending (in sm_ctl), lane 0 owns the parked chain
   int n_ring = 0;  // uniform across warp 0
   int chain = -1;
+#ifndef WFT_DEFER_PUBLISH
+#define WFT_DEFER_PUBLISH 0
+#endif
+  // thread 0: the completion count of the previous tile is owed until its two stat atomics have returned; it is
+  // paid one stage later, when that L2 round trip is long over, so the CTA never waits for it at a barrier
+  int owed_clip = -1;
+  uint32_t owed_dep = 0;
 
   while (cur < p.total_tiles) {
     // claim the tile AFTER this one now; the answer is consumed two barriers later (latency hidden by stage A)
@@ -430,9 +446,9 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
         const int g0 = t0 * kHop - kNfft / 2;
         if (tile_is_interior(x, g0, len)) prefetch_audio<PcmT>(sm_audio, x + g0, tid);
         else stage_audio_edge<PcmT>(sm_audio, x, g0, len, p.n_total, tid);
-      }
-      cp_async_commit_wait_all();
-      __syncthreads();
+        cp_async_commit_wait_all();
+        __syncthreads();
+      }  // a prefetched tile was waited for before the previous tile's closing barrier
 
       // stage A: thread (q, n2 = r): x[n1] = w[20 n1 + n2] * (pa + i pb)[20 n1 + n2] ------------------------------
       {
@@ -466,11 +482,12 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
           e2[k1 * (kRowStride / 2)] = make_float2(x[k1].x * t.z - x[k1].y * t.w, fmaf(x[k1].x, t.w, x[k1].y * t.z));
         }
       }
-      if (tid == 0) describe_tile<PcmT>(p, nxt_claim, sm_ctl + kCtlNext);
-      __syncthreads();
-      nxt = sm_ctl[kCtlNext];
-      nxt_clip = sm_ctl[kCtlNext + 1];
-      nxt_t0 = sm_ctl[kCtlNext + 2];
+      if (tid == 0) {
+        describe_tile<PcmT>(p, nxt_claim, sm_ctl + kCtlNext);
+        if (owed_clip >= 0) atomicAdd(&p.stats[owed_clip].done, 1u + (owed_dep & p.zero));
+        owed_clip = -1;
+      }
+      half_cta_sync(warp / (kWarps / 2));
 
       // stage B: thread (q, k1 = r): Z[k1 + 20 k2] = DFT20 over n2.  The lower half (k2 < 10, bins k1 + 20 k2 <= 199)
       // stays in registers; the upper half is what the mirror thread (q, 20 - k1) needs and goes back to the row.
@@ -500,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
 #pragma unroll
           for (int m = 0; m < 10; ++m) z[m] = y[m];
         }
-        __syncthreads();
+        half_cta_sync(warp / (kWarps / 2));
         {
           const float4* mir = reinterpret_cast<const float4*>(sm_region + q * kPairStride + ((20 - r) % 20) * kRowStride) + 5;
 #pragma unroll
@@ -511,6 +528,9 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
           }
         }
         __syncthreads();  // exchange is dead: the region becomes power tile (bottom) + next audio tile (top)
+        nxt = sm_ctl[kCtlNext];
+        nxt_clip = sm_ctl[kCtlNext + 1];
+        nxt_t0 = sm_ctl[kCtlNext + 2];
 
         // prefetch the NEXT tile's PCM into the top of the region
         prefetched = sm_ctl[kCtlNext + 3] != 0;
@@ -545,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
         const bool live = frame < p.n_frames;           // real frame of the clip: counts for the max
         const bool kept = frame < keep;                 // survives the partial-segment cut: counts for the pad min
         MelLane ln;
-        ln.store = live && frame < p.n_frames_out;
+        ln.store = (live && frame < p.n_frames_out) ? 1u : 0u;
         ln.obase = reinterpret_cast<char*>(p.out + static_cast<size_t>(clip) * NM * p.n_frames_out + frame);
         ln.tmask = false;
         ln.row_lo = 0u;
@@ -583,7 +603,11 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
       }
     } else {
       // pad-only tile (n_frames_out > n_frames): nothing to compute
-      if (tid == 0) describe_tile<PcmT>(p, nxt_claim, sm_ctl + kCtlNext);
+      if (tid == 0) {
+        describe_tile<PcmT>(p, nxt_claim, sm_ctl + kCtlNext);
+        if (owed_clip >= 0) atomicAdd(&p.stats[owed_clip].done, 1u + (owed_dep & p.zero));
+        owed_clip = -1;
+      }
       __syncthreads();
       nxt = sm_ctl[kCtlNext];
       nxt_clip = sm_ctl[kCtlNext + 1];
@@ -626,7 +650,8 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
       n_ring = __popc(wait_mask);
       if (lane == 0) sm_ctl[kCtlReady] = __popc(ready_mask);
     }
-    __syncthreads();  // tile finished: power tile free, ready list and per-warp max/min visible
+    if (prefetched) cp_async_commit_wait_all();  // the next tile's PCM has landed (this thread's share)
+    __syncthreads();  // tile finished: power tile free, next audio tile, ready list and per-warp max/min visible
 
     // publish the tile's statistics: two returning atomics, then the completion count with a true data dependency on
     // their results (through p.zero) -- no fence, so nobody waits for the tile's stores to drain.  The tile itself
@@ -655,7 +680,12 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
           p.next[cur] = chain;                       // parked tiles are re-examined (conservatively) in the drain
           chain = cur;
         }
+#if WFT_DEFER_PUBLISH
+        owed_clip = clip;
+        owed_dep = dep;
+#else
         atomicAdd(&cs->done, 1u + (dep & p.zero));
+#endif
       }
       if (n_ring < kMaxPending) ++n_ring;
       __syncwarp();
@@ -667,6 +697,7 @@ __global__ void __launch_bounds__(kThreads, 3) frontend_kernel(const FrontendPar
     t0 = nxt_t0;
   }
 
+  if (tid == 0 && owed_clip >= 0) atomicAdd(&p.stats[owed_clip].done, 1u + (owed_dep & p.zero));
   // drain: every tile is claimed by a running CTA now, so waiting on a clip's counter is safe
   for (;;) {
     __syncthreads();  // previous readers of sm_ctl are done
