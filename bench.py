@@ -231,6 +231,7 @@ def run_ours(args):
             step(i)
         ev1.record()
         barrier()
+        launches = int(lib.wft_launch_count(0))
         # the timed region lasts only milliseconds: keep the very same steps running for another ~0.4 s so that the
         # clock / throttle-reason samples describe the GPU under this load (not part of the timing)
         t_end = time.perf_counter() + 0.4
@@ -241,7 +242,6 @@ def run_ours(args):
                 i += 1
             torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    launches = int(lib.wft_launch_count(0))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
