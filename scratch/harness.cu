@@ -6,7 +6,7 @@
 #include "../include/wft.h"
 extern "C" int wft_debug_read(int*);
 int main(int argc, char** argv) {
-  int B = argc > 1 ? atoi(argv[1]) : 16, nm = argc > 2 ? atoi(argv[2]) : 128, iters = argc > 3 ? atoi(argv[3]) : 4;
+  int B = argc > 1 ? atoi(argv[1]) : 16, nm = argc > 2 ? atoi(argv[2]) : 128, iters = argc > 3 ? atoi(argv[3]) : 4; int ragged = argc > 4 ? atoi(argv[4]) : 0;
   size_t n = (size_t)B * 480000;
   std::vector<float> h(n);
   unsigned s = 12345;
@@ -15,8 +15,11 @@ int main(int argc, char** argv) {
   cudaMalloc(&d_pcm, n * 4); cudaMemcpy(d_pcm, h.data(), n * 4, cudaMemcpyHostToDevice);
   cudaMalloc(&d_out, (size_t)B * nm * 3000 * 4);
   wft_frontend_workspace_bytes(B, 480000, 3000, &wsb); cudaMalloc(&ws, wsb);
+  int32_t* d_len = nullptr;
+  if (ragged) { std::vector<int32_t> hl(B); unsigned r = 777; for (int i = 0; i < B; ++i) { r = r * 1664525u + 1013904223u; hl[i] = 16000 + (r >> 8) % 464001; }
+    cudaMalloc(&d_len, B * 4); cudaMemcpy(d_len, hl.data(), B * 4, cudaMemcpyHostToDevice); }
   wft_frontend_args a{}; a.pcm = d_pcm; a.pcm_dtype = WFT_PCM_F32; a.batch = B; a.clip_stride = 480000; a.n_samples = 480000;
-  a.n_mels = nm; a.n_frames_out = 3000; a.out = d_out; a.workspace = ws; a.workspace_bytes = wsb;
+  a.lengths = d_len; a.n_mels = nm; a.n_frames_out = 3000; a.out = d_out; a.workspace = ws; a.workspace_bytes = wsb;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < iters; ++it) {
     cudaEventRecord(e0);

@@ -282,3 +282,39 @@ def test_host_pipeline_matches_direct_call(wft, cuda):
     pipe16(host16, out, clip_offset=100)
     pipe16.synchronize()
     assert torch.equal(out, fe(host16.to(cuda), clip_offset=100).cpu())
+
+
+@pytest.mark.parametrize("dtype", ["f32", "i16"])
+def test_zero_padded_tails_take_the_silent_path(wft, cuda, dtype):
+    """Clips much shorter than 30 s: every tile past the valid samples is all-zero PCM (skipped FFT, constant rows written
+    by the fix-up).  Lengths straddle the tile geometry (tile = 16 frames = 2560 samples, halo 200/240)."""
+    lens = [0, 1, 199, 200, 201, 2359, 2360, 2361, 2559, 2560, 2561, 5000, 16000, 239999, 240000, 476999, 479759, 479760, 480000]
+    B = len(lens)
+    pcm = torch.zeros(B, 480000)
+    for b, n in enumerate(lens):
+        if n:
+            pcm[b, :n] = S.make("white", n=n, seed=500 + b)
+    pcm[:, 300000:] += 0.0  # keep the tail exactly zero even where lengths would hide it
+    if dtype == "i16":
+        pcm = torch.round(pcm * 32767).to(torch.int16)
+    lengths = np.asarray(lens, dtype=np.int32)
+    masks = OS.draw_mask_params(9, 0, B, 80, 3000, 100, 43, 1.0)
+    n_valid = np.full(B, -1, dtype=np.int32)
+    n_valid[5], n_valid[11], n_valid[13] = 7, 2000, 1499
+    fe = wft.FrontEnd(n_mels=80)
+    got = fe(pcm.to(cuda), lengths=lengths, n_valid_frames=n_valid, mask_params=masks).cpu()
+    ref = OP.front_end_batch(pcm, 80, lengths=lengths, n_valid_frames=n_valid, masks=masks)
+    for b in range(B):
+        keep = 3000 if n_valid[b] < 0 else int(n_valid[b])
+        _check(got[b, :, :keep], ref[b, :, :keep], f"len={lens[b]} (kept frames)")
+        assert (got[b] - ref[b]).abs().max() <= S.MAX_ABS
+        assert torch.equal(got[b] == 0, ref[b] == 0)
+    # garbage beyond `lengths` must not leak in: same result when the hidden samples are non-zero
+    noisy = pcm.clone().float()
+    for b, n in enumerate(lens):
+        noisy[b, n:] = 0.25
+    if dtype == "i16":
+        noisy = torch.round(noisy).to(torch.int16) if pcm.dtype == torch.int16 else noisy
+        noisy = torch.where(torch.arange(480000)[None, :] < torch.as_tensor(lens)[:, None], pcm, torch.full_like(pcm, 8191))
+    got2 = fe(noisy.to(cuda), lengths=lengths, n_valid_frames=n_valid, mask_params=masks).cpu()
+    assert torch.equal(got2, got)

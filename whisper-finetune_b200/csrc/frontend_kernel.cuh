@@ -67,7 +67,7 @@ constexpr int kWinFloats = WFT_WINDOW_TABLE_LEN;                 // 400
 constexpr int kTwFloats = WFT_TWIDDLE_TABLE_LEN;                 // 880
 constexpr int kTwRow = WFT_TWIDDLE_ROW;                          // 44
 constexpr int kProgVec = WFT_MEL80_PROG_VEC > WFT_MEL128_PROG_VEC ? WFT_MEL80_PROG_VEC : WFT_MEL128_PROG_VEC;
-constexpr int kMaxPending = 8;
+constexpr int kMaxPending = 8;   // <= 8: ring slots in sm_ctl
 constexpr int kCtlInts = 80;
 constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats) * 4 + kProgVec * 16 + kCtlInts * 4;
 
@@ -177,13 +177,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 }
 
 // interior tile: the 2800 samples travel as 9 bulk copies (8 blocks of 320 samples + a 240-sample tail), block b landing
-// at element 340 * b (the 20-element skew that keeps stage A's stride-20 gathers conflict free).  Called by ONE thread.
+// at element (320 + skew) * b (the skew keeps stage A's stride-20 gathers conflict free).  Called by ONE thread, as a real
+// call (measured: inlining it, or spreading the 9 copies over 9 lanes, made the kernel 2 % slower).
 template <typename PcmT>
-__device__ __forceinline__ void prefetch_audio(PcmT* __restrict__ sm_audio, const PcmT* __restrict__ src, uint64_t* bar) {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the region is ordered first
+__device__ __noinline__ void prefetch_audio(PcmT* __restrict__ sm_audio, const PcmT* __restrict__ src, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the region comes first
   mbar_expect_tx(bar, kTileSamples * sizeof(PcmT));
   constexpr int kBlocks = (kTileSamples + kSkewBlock - 1) / kSkewBlock;  // 9
-#pragma unroll
+#pragma unroll 1
   for (int b = 0; b < kBlocks; ++b) {
     const int n = (b + 1) * kSkewBlock <= kTileSamples ? kSkewBlock : kTileSamples - b * kSkewBlock;
     tma_bulk_g2s(sm_audio + b * (kSkewBlock + Skew<PcmT>::value), src + b * kSkewBlock, n * sizeof(PcmT), bar);
@@ -219,6 +220,12 @@ __device__ __forceinline__ float fast_log2(float x) {  // x is a normal float he
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+constexpr int kSilentBit = 1 << 30;   // flag carried by the tile id inside the pending ring / parked chain
+constexpr int kTileIdMask = kSilentBit - 1;
+
+// log10 of the 1e-10 clamp exactly as the mel phase computes it for an all-zero frame
+__device__ __forceinline__ float silent_log_mel() { return fast_log2(1e-10f) * 0.301029995663981195f; }
 
 // ---- mel projection: rows of one tap class; entry = (first_bin*4, row byte offset, w[0..C-1]) in (C+2)/4 uint4 ------
 // h.y holds the row's byte offset in `out` (row * pitch * 4, patched in at kernel start).  The value written is
@@ -294,8 +301,10 @@ __device__ __forceinline__ bool tile_needs_fixup(float tile_min, uint32_t max_en
 }
 
 template <int NM>
-__device__ __noinline__ void fixup_tile(const FixupArgs p, int tile, int clip, int tid) {
-  const int t0 = (tile - clip * p.tiles_per_clip) * kTileFrames;
+__device__ __noinline__ void fixup_tile(const FixupArgs p, int tagged_tile, int clip, int tid) {
+  const bool silent = (tagged_tile & kSilentBit) != 0;   // nothing was written yet: every cell is the clamp constant
+  const int tile = tagged_tile & kTileIdMask;
+  const float vsilent = fmaf(silent_log_mel(), 0.25f, 1.0f);
   const ClipStat* st = p.stats + clip;
   const float lmax = dec_ordered(__ldcg(&st->max_enc));
   const float lmin = dec_ordered(~__ldcg(&st->min_inv));
@@ -311,45 +320,49 @@ __device__ __noinline__ void fixup_tile(const FixupArgs p, int tile, int clip, i
   const float mv = p.mask_value;
   const int pitch = p.n_frames_out;
   float* base = p.out + static_cast<size_t>(clip) * NM * pitch;
-  if ((pitch & 3) == 0) {
-    constexpr int kGroups = kTileFrames / 4;                      // float4 groups per row (4)
-    constexpr int kVec = NM * kGroups;                            // float4 groups per tile
-    constexpr int kIters = (kVec + kThreads - 1) / kThreads;      // 4 (128 mel) / 2 (80 mel)
-    const int f = t0 + ((tid & (kGroups - 1)) << 2);              // kThreads % kGroups == 0: same column group every iter
-    if (f >= pitch) return;
-    float4 v[kIters];
+  const int t0 = (tile - clip * p.tiles_per_clip) * kTileFrames;
+  {
+    if ((pitch & 3) == 0) {
+      constexpr int kGroups = kTileFrames / 4;                      // float4 groups per row (4)
+      constexpr int kVec = NM * kGroups;                            // float4 groups per tile
+      constexpr int kIters = (kVec + kThreads - 1) / kThreads;      // 4 (128 mel) / 2 (80 mel)
+      const int f = t0 + ((tid & (kGroups - 1)) << 2);              // kThreads % kGroups == 0: same column group every iter
+      if (f >= pitch) return;
+      float4 v[kIters];
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int row = (tid + kThreads * it) / kGroups;
-      v[it] = make_float4(padv, padv, padv, padv);
-      if (row < NM && f < keep) v[it] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * pitch + f));
-    }
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int row = (tid + kThreads * it) / kGroups;
-      if (row < NM) {
-        const bool rowmask = row >= mf0 && row < mf1;
-        float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int fc = f + c;
-          float r = (fc < keep) ? fmaxf(e[c], floorn) : padv;
-          if (rowmask || (fc >= mt0 && fc < mt1)) r = mv;
-          e[c] = r;
-        }
-        *reinterpret_cast<float4*>(base + static_cast<size_t>(row) * pitch + f) = make_float4(e[0], e[1], e[2], e[3]);
+      for (int it = 0; it < kIters; ++it) {
+        const int row = (tid + kThreads * it) / kGroups;
+        v[it] = make_float4(vsilent, vsilent, vsilent, vsilent);
+        if (!silent && row < NM && f < keep)
+          v[it] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * pitch + f));
       }
-    }
-  } else {
-    for (int idx = tid; idx < NM * kTileFrames; idx += kThreads) {
-      const int row = idx / kTileFrames;
-      const int f = t0 + (idx % kTileFrames);
-      if (f >= pitch) continue;
-      float* ptr = base + static_cast<size_t>(row) * pitch + f;
-      float r = padv;
-      if (f < keep) r = fmaxf(__ldcg(ptr), floorn);
-      if ((row >= mf0 && row < mf1) || (f >= mt0 && f < mt1)) r = mv;
-      *ptr = r;
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int row = (tid + kThreads * it) / kGroups;
+        if (row < NM) {
+          const bool rowmask = row >= mf0 && row < mf1;
+          float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int fc = f + c;
+            float r = (fc < keep) ? fmaxf(e[c], floorn) : padv;
+            if (rowmask || (fc >= mt0 && fc < mt1)) r = mv;
+            e[c] = r;
+          }
+          *reinterpret_cast<float4*>(base + static_cast<size_t>(row) * pitch + f) = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+    } else {
+      for (int idx = tid; idx < NM * kTileFrames; idx += kThreads) {
+        const int row = idx / kTileFrames;
+        const int f = t0 + (idx % kTileFrames);
+        if (f >= pitch) continue;
+        float* ptr = base + static_cast<size_t>(row) * pitch + f;
+        float r = padv;
+        if (f < keep) r = fmaxf(silent ? vsilent : __ldcg(ptr), floorn);
+        if ((row >= mf0 && row < mf1) || (f >= mt0 && f < mt1)) r = mv;
+        *ptr = r;
+      }
     }
   }
 }
@@ -365,25 +378,63 @@ __device__ __forceinline__ FixupArgs make_fixup_args(const FrontendParams& p) {
 // sm_ctl slots
 // [kCtlNext .. +5] = next tile: id, clip, first frame, interior flag, PCM element offset (lo, hi)
 enum { kCtlNext = 0, kCtlReady = 6, kCtlDrain = 7, kCtlDrainClip = 8, kCtlList = 16, kCtlListClip = 24, kCtlRing = 32,
-       kCtlRingClip = 40, kCtlRingMin = 48, kCtlRed = 56, kCtlMbar = 72 };   // kCtlRed: 3 floats per warp (max, kept min, live min)
+       kCtlRingClip = 40, kCtlRingMin = 48, kCtlRed = 56, kCtlMbar = 72, kCtlMemo = 74 };   // kCtlRed: 3 floats per warp (max, kept min, live min)
 
-// thread 0: describe tile `t` for everybody (one division and one lengths[] load per tile instead of 320)
+// how a tile's PCM reaches shared memory
+enum { kTileEdge = 0,      // reflection / zero extension / unaligned source: scalar staging
+       kTileInterior = 1,  // plain in-range samples: TMA bulk copies, one tile ahead
+       kTileSilent = 2,    // every sample it touches is zero padding: no FFT, the fix-up later writes the constant rows;
+                           // this is the FIRST such tile of its clip and records the clamp value in the clip statistics
+       kTileSilentRest = 3 };  // a later tile of the same silent tail: the statistics are already in, only counted
+// thread 0: describe tile `t` for everybody (one division and one lengths[] load per tile instead of 160)
+__device__ __forceinline__ bool tile_is_silent(int t0, int len, int n_total) {
+  const int g0 = t0 * kHop - kNfft / 2;
+  const int last = g0 + kTileSamples - 1;  // beyond n_total the samples are mirrored around n_total - 1
+  return len == 0 || (g0 >= len && (last < n_total || 2 * (n_total - 1) - last >= len));
+}
+
+struct TileGeom {   // the few launch constants describe_tile needs (passed by value: it is a real call, thread 0 only)
+  const void* pcm;
+  const int32_t* lengths;
+  int64_t clip_stride;
+  int32_t n_samples, n_total, n_frames, tiles_per_clip, total_tiles;
+};
+__device__ __forceinline__ TileGeom tile_geom(const FrontendParams& q) {
+  TileGeom g;
+  g.pcm = q.pcm; g.lengths = q.lengths; g.clip_stride = q.clip_stride; g.n_samples = q.n_samples; g.n_total = q.n_total;
+  g.n_frames = q.n_frames; g.tiles_per_clip = q.tiles_per_clip; g.total_tiles = q.total_tiles;
+  return g;
+}
+
+// (forced inline: as a real call this sat on thread 0's critical path before a CTA barrier and cost 2.5 % overall)
 template <typename PcmT>
-__device__ __forceinline__ void describe_tile(const FrontendParams& p, int t, int* __restrict__ slot) {
-  int clip = 0, t0 = 0, interior = 0;
+__device__ __forceinline__ void describe_tile(const TileGeom p, int t, int* __restrict__ slot, int* __restrict__ memo) {
+  int& memo_clip = memo[0];   // lengths[] of the last clip described (kept in shared memory, not in registers)
+  int& memo_len = memo[1];
+  int clip = 0, t0 = 0, interior = kTileEdge;
   long long off = 0;
   if (t < p.total_tiles) {
     clip = t / p.tiles_per_clip;
     t0 = (t - clip * p.tiles_per_clip) * kTileFrames;
     if (t0 < p.n_frames) {
-      int len = p.n_samples;
-      if (p.lengths != nullptr) {
-        const int l = __ldg(p.lengths + clip);
-        len = l < 0 ? 0 : (l < len ? l : len);
+      if (clip != memo_clip) {  // consecutive tiles mostly belong to the same clip: one lengths[] load per clip
+        int len = p.n_samples;
+        if (p.lengths != nullptr) {
+          const int l = __ldg(p.lengths + clip);
+          len = l < 0 ? 0 : (l < len ? l : len);
+        }
+        memo_clip = clip;
+        memo_len = len;
       }
+      const int len = memo_len;
       const int g0 = t0 * kHop - kNfft / 2;
       off = static_cast<long long>(clip) * p.clip_stride + g0;
-      interior = tile_is_interior(reinterpret_cast<const PcmT*>(p.pcm) + off - g0, g0, len) ? 1 : 0;
+      if (tile_is_silent(t0, len, p.n_total)) {
+        // silence is a suffix of the clip: only its first tile does any bookkeeping
+        interior = (t0 == 0 || !tile_is_silent(t0 - kTileFrames, len, p.n_total)) ? kTileSilent : kTileSilentRest;
+      } else if (tile_is_interior(reinterpret_cast<const PcmT*>(p.pcm) + off - g0, g0, len)) {
+        interior = kTileInterior;
+      }
     }
   }
   slot[0] = t; slot[1] = clip; slot[2] = t0; slot[3] = interior;
@@ -417,11 +468,12 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   uint32_t audio_phase = 0;
   constexpr int kTmaThread = kThreads - 32;                               // the thread that issues the bulk copies
   if (tid == 0) {
+    sm_ctl[kCtlMemo] = -1;
     mbar_init(audio_bar, 1);
-    describe_tile<PcmT>(p, static_cast<int>(atomicAdd(p.tile_counter, 1u)), sm_ctl + kCtlNext);
+    describe_tile<PcmT>(tile_geom(p), static_cast<int>(atomicAdd(p.tile_counter, 1u)), sm_ctl + kCtlNext, sm_ctl + kCtlMemo);
   }
   __syncthreads();
-  int cur = sm_ctl[kCtlNext], clip = sm_ctl[kCtlNext + 1], t0 = sm_ctl[kCtlNext + 2];
+  int cur = sm_ctl[kCtlNext], clip = sm_ctl[kCtlNext + 1], t0 = sm_ctl[kCtlNext + 2], kind = sm_ctl[kCtlNext + 3];
   bool prefetched = false;
 
   // row group of this half-warp (lanes 0-15 and 16-31 of a warp run different row programs on the same 16 frames)
@@ -440,22 +492,17 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   // warp-0 scheduler state: ring of tiles whose fix-up is pending (in sm_ctl), lane 0 owns the parked chain
   int n_ring = 0;  // uniform across warp 0
   int chain = -1;
-#ifndef WFT_DEFER_PUBLISH
-#define WFT_DEFER_PUBLISH 0
-#endif
-  // thread 0: the completion count of the previous tile is owed until its two stat atomics have returned; it is
-  // paid one stage later, when that L2 round trip is long over, so the CTA never waits for it at a barrier
-  int owed_clip = -1;
-  uint32_t owed_dep = 0;
 
   while (cur < p.total_tiles) {
     // claim the tile AFTER this one now; the answer is consumed two barriers later (latency hidden by stage A)
     int nxt_claim = 0;
     if (tid == 0) nxt_claim = static_cast<int>(atomicAdd(p.tile_counter, 1u));
-    int nxt = p.total_tiles, nxt_clip = 0, nxt_t0 = 0;
+    int nxt = p.total_tiles, nxt_clip = 0, nxt_t0 = 0, nxt_kind = kTileEdge;
     uint4 stat_seen = make_uint4(0u, 0u, 0u, 0u);  // warp 0: snapshot of the clip of ring[lane], sampled early
 
-    if (t0 < p.n_frames) {
+    const bool silent = (kind == kTileSilent || kind == kTileSilentRest) && t0 < p.n_frames;
+    const bool silent_head = kind == kTileSilent;   // only the first silent tile of a clip touches the clip statistics
+    if (t0 < p.n_frames && !silent) {
       // stage 0 ---------------------------------------------------------------------------------------------
       if (!prefetched) {
         const PcmT* x = reinterpret_cast<const PcmT*>(p.pcm) + static_cast<size_t>(clip) * p.clip_stride;
@@ -511,11 +558,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           e2[k1 * (kRowStride / 2)] = make_float2(x[k1].x * t.z - x[k1].y * t.w, fmaf(x[k1].x, t.w, x[k1].y * t.z));
         }
       }
-      if (tid == 0) {
-        describe_tile<PcmT>(p, nxt_claim, sm_ctl + kCtlNext);
-        if (owed_clip >= 0) atomicAdd(&p.stats[owed_clip].done, 1u + (owed_dep & p.zero));
-        owed_clip = -1;
-      }
+      if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, sm_ctl + kCtlNext, sm_ctl + kCtlMemo);
       __syncthreads();
 
       // stage B: thread (q, k1 = r): Z[k1 + 20 k2] = DFT20 over n2.  The lower half (k2 < 10, bins k1 + 20 k2 <= 199)
@@ -560,9 +603,10 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         nxt = sm_ctl[kCtlNext];
         nxt_clip = sm_ctl[kCtlNext + 1];
         nxt_t0 = sm_ctl[kCtlNext + 2];
+        nxt_kind = sm_ctl[kCtlNext + 3];
 
         // prefetch the NEXT tile's PCM into the top of the region
-        prefetched = sm_ctl[kCtlNext + 3] != 0;
+        prefetched = nxt_kind == kTileInterior;
         if (prefetched) {
           const long long off = (static_cast<long long>(sm_ctl[kCtlNext + 5]) << 32) |
                                 static_cast<unsigned int>(sm_ctl[kCtlNext + 4]);
@@ -631,23 +675,27 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         }
       }
     } else {
-      // pad-only tile (n_frames_out > n_frames): nothing to compute
-      if (tid == 0) {
-        describe_tile<PcmT>(p, nxt_claim, sm_ctl + kCtlNext);
-        if (owed_clip >= 0) atomicAdd(&p.stats[owed_clip].done, 1u + (owed_dep & p.zero));
-        owed_clip = -1;
-      }
+      // nothing to compute: a pad-only tile (n_frames_out > n_frames) or a silent tile (all-zero PCM: every mel value is
+      // the 1e-10 clamp, so only its statistics are recorded here and the fix-up later writes the constant rows)
+      if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, sm_ctl + kCtlNext, sm_ctl + kCtlMemo);
       __syncthreads();
       nxt = sm_ctl[kCtlNext];
       nxt_clip = sm_ctl[kCtlNext + 1];
       nxt_t0 = sm_ctl[kCtlNext + 2];
-      prefetched = false;
+      nxt_kind = sm_ctl[kCtlNext + 3];
+      prefetched = nxt_kind == kTileInterior;
+      if (prefetched && tid == kTmaThread) {
+        const long long off = (static_cast<long long>(sm_ctl[kCtlNext + 5]) << 32) |
+                              static_cast<unsigned int>(sm_ctl[kCtlNext + 4]);
+        prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
+      }
       if (warp == 0 && lane < n_ring) stat_seen = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
       if (lane == 0) {
         float* red = reinterpret_cast<float*>(sm_ctl + kCtlRed) + 3 * warp;
-        red[0] = -INFINITY;
-        red[1] = INFINITY;
-        red[2] = INFINITY;
+        const float lc = silent_log_mel();
+        red[0] = (silent && silent_head) ? lc : -INFINITY;                                                 // live frames
+        red[1] = (silent && silent_head && t0 < kept_frames(p.n_valid, clip, p.n_frames)) ? lc : INFINITY;  // kept frames
+        red[2] = silent ? lc : INFINITY;
       }
     }
 
@@ -661,8 +709,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       const bool complete = pending && stat_seen.z >= tiles_per_clip_u;
       bool ready = false;
       if (complete) {
-        const int mt0 = (mine - mine_clip * p.tiles_per_clip) * kTileFrames;
-        ready = tile_needs_fixup(mine_min, stat_seen.x, mt0, kept_frames(p.n_valid, mine_clip, p.n_frames), p.n_frames_out);
+        const int mt0 = ((mine & kTileIdMask) - mine_clip * p.tiles_per_clip) * kTileFrames;
+        ready = (mine & kSilentBit) != 0 ||
+                tile_needs_fixup(mine_min, stat_seen.x, mt0, kept_frames(p.n_valid, mine_clip, p.n_frames), p.n_frames_out);
       }
       const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
       const uint32_t wait_mask = __ballot_sync(0xffffffffu, pending && !complete);
@@ -700,20 +749,16 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         uint32_t dep = 0;
         if (mx > -INFINITY) dep |= atomicMax(&cs->max_enc, enc_ordered(mx));
         if (mn_kept < INFINITY) dep |= atomicMax(&cs->min_inv, ~enc_ordered(mn_kept));
+        const int tagged = cur | (silent ? kSilentBit : 0);
         if (n_ring < kMaxPending) {
-          sm_ctl[kCtlRing + n_ring] = cur;
+          sm_ctl[kCtlRing + n_ring] = tagged;
           sm_ctl[kCtlRingClip + n_ring] = clip;
           sm_ctl[kCtlRingMin + n_ring] = __float_as_int(mn_live);
         } else {
           p.next[cur] = chain;                       // parked tiles are re-examined (conservatively) in the drain
-          chain = cur;
+          chain = tagged;
         }
-#if WFT_DEFER_PUBLISH
-        owed_clip = clip;
-        owed_dep = dep;
-#else
-        atomicAdd(&cs->done, 1u + (dep & p.zero));
-#endif
+        atomicAdd(&cs->done, 1u + (dep & p.zero));  // (paying this one stage later was measured 2 % slower)
       }
       if (n_ring < kMaxPending) ++n_ring;
       __syncwarp();
@@ -723,9 +768,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     cur = nxt;
     clip = nxt_clip;
     t0 = nxt_t0;
+    kind = nxt_kind;
   }
 
-  if (tid == 0 && owed_clip >= 0) atomicAdd(&p.stats[owed_clip].done, 1u + (owed_dep & p.zero));
   // drain: every tile is claimed by a running CTA now, so waiting on a clip's counter is safe
   for (;;) {
     __syncthreads();  // previous readers of sm_ctl are done
@@ -740,8 +785,8 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           tmin = __int_as_float(sm_ctl[kCtlRingMin + n_ring]);
         } else if (chain >= 0) {
           t = chain;
-          c = t / p.tiles_per_clip;
-          chain = p.next[chain];
+          c = (t & kTileIdMask) / p.tiles_per_clip;
+          chain = p.next[t & kTileIdMask];
         } else {
           t = -1;
           break;
@@ -751,8 +796,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           __nanosleep(100);
           st = ld_stat(p.stats + c);
         }
-        const int tt0 = (t - c * p.tiles_per_clip) * kTileFrames;
-        if (tile_needs_fixup(tmin, st.x, tt0, kept_frames(p.n_valid, c, p.n_frames), p.n_frames_out)) break;
+        const int tt0 = ((t & kTileIdMask) - c * p.tiles_per_clip) * kTileFrames;
+        if ((t & kSilentBit) != 0 ||
+            tile_needs_fixup(tmin, st.x, tt0, kept_frames(p.n_valid, c, p.n_frames), p.n_frames_out)) break;
       }
       sm_ctl[kCtlDrain] = t;
       sm_ctl[kCtlDrainClip] = c;
