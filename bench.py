@@ -40,7 +40,7 @@ BYTES_PER_CLIP = 4 * N_SAMPLES + 4 * N_MELS * N_FRAMES  # 3 456 000 (SURVEY 8d: 
 METRIC = "30-s clips/sec log-mel+SpecAugment"
 UNIT = "clips/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one B=64 launch, from profiles/r01_ncu_summary.md
-NCU_DRAM_BYTES_PER_LAUNCH = 182.7e6
+NCU_DRAM_BYTES_PER_LAUNCH = 182.6e6
 
 
 def workload_config(n_gpus):
@@ -129,7 +129,7 @@ def cpu_reference_clips_per_s(min_seconds, max_clips=None, threads=None):
 
     if threads:
         torch.set_num_threads(threads)
-    n = 16
+    n = BATCH  # the same 64-clip batch the CUDA arm runs per step
     pcm = synth_pcm(n, SEED)
     masks = OS.draw_mask_params(SEED, 0, n, N_MELS, N_FRAMES, TIME_MASK, FREQ_MASK, 1.0)
     OP.front_end_batch(pcm[:2], N_MELS, masks=masks[:2])  # warm-up (FFT plans, filter cache)

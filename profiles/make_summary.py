@@ -123,7 +123,7 @@ def main():
             continue
         top = " ".join(f"{k}:{v / n_tiles:.0f}" for k, v in sorted(x["ops"].items(), key=lambda kv: -kv[1])[:6])
         out.append(f"| {i} | {x['n']} | {x['exec'] / n_tiles:.0f} | {100 * x['exec'] / tot_e:.1f} % | {100 * x['samp'] / tot_s:.1f} % | {top} |")
-    out += ["", f"Total {tot_e / n_tiles:.0f} warp-instructions per 32-frame tile."]
+    out += ["", f"Total {tot_e / n_tiles:.0f} warp-instructions per 16-frame tile ({n_tiles:.0f} tiles in the launch)."]
     hot = sorted(data, key=lambda r: -f(r, "# Samples"))[:8]
     out += ["", "### Hottest instructions (warp-state samples)", "", "| share | SASS | dominant stall |", "|---|---|---|"]
     for r in hot:

@@ -5,30 +5,30 @@
 //   (src/whisper_finetune/data/data_loader.py:346, :278, :279-282, :286-287, :362-367; data/utils.py:380-404).
 //
 // Work decomposition
-//   tile      = 32 consecutive frames of one clip = 16 frame PAIRS; 320 threads = 16 pairs x 20 threads.
+//   tile      = 16 consecutive frames of one clip = 8 frame PAIRS; 160 threads = 8 pairs x 20 threads; 6 CTAs per SM.
 //   pair      = frames (2q, 2q+1) packed as re/im of ONE 400-point complex FFT (two real frames per transform).
-//   400-point = 20 x 20 Cooley-Tukey, one register-resident 20-point DFT (dft20.cuh) per thread per stage:
+//   400-point = 20 x 20 Cooley-Tukey, one register-resident 20-point DFT (dft20.cuh, packed f32x2) per thread per stage:
 //               stage A: thread (q, n2) transforms over n1, multiplies by W400^(n2 k1), scatters to the exchange;
-//               stage B: thread (q, k1) transforms over n2 and writes Z[k1 + 20 k2] back in place;
-//               power  : thread (q, j) pairs Z[j + 20 m] with its mirror Z[400 - j - 20 m] (rows j and 20-j)
-//                        and separates the two real spectra: 4|Xa|^2 = |Z[k] + conj Z[400-k]|^2,
-//                        4|Xb|^2 = |Z[k] - conj Z[400-k]|^2.
-//   mel phase = warp g owns a row group, lane <-> frame; the sparse triangular filters are walked as a table
-//               of bin steps (wft_tables.inc) so the code stays small; log10 via MUFU.LG2; the un-floored
-//               log-mel is written once to `out`.
-//   per-clip max / min = ordered-int atomicMax into the workspace; the max-8 floor, (x+4)/4, the min-value
-//               pad and the SpecAugment masks are applied by a deferred in-place "fix-up" of the CTA's OWN
-//               tiles once the clip's tile counter is complete -- while those lines are still L2-resident,
-//               so HBM sees each output byte once.
-//   scheduling = persistent CTAs pulling tiles from an atomic counter in clip-major order, one tile ahead
-//               (the next tile's PCM is copied global->shared with cp.async under the current tile's mel
-//               phase); a CTA never waits while tiles are still unclaimed (pending fix-ups are parked), so the
-//               kernel is deadlock-free for any grid size.
+//               stage B: thread (q, k1) transforms over n2, keeps Z[k1 + 20 k2] for k2 < 10 in registers and hands the
+//                        upper half to the mirror thread (q, 20 - k1) through its exchange row;
+//               power  : thread (q, j) pairs Z[j + 20 m] with its mirror Z[400 - j - 20 m] and separates the two real
+//                        spectra: 4|Xa|^2 = |Z[k] + conj Z[400-k]|^2, 4|Xb|^2 = |Z[k] - conj Z[400-k]|^2.
+//   mel phase = lane <-> frame, every half-warp owns a cost-balanced set of mel rows; the sparse triangular filters are
+//               walked as a table-driven "row program" (wft_tables.inc) so the code stays small; log10 via MUFU.LG2;
+//               the FINAL feature (L + 4) / 4 with the SpecAugment masks applied is written once to `out`.
+//   per-clip max / min = ordered-int atomicMax into the workspace, completion counted per tile.  Once a clip is complete
+//               each CTA re-visits ITS OWN tiles of that clip only if something is still missing: the max-8 floor binds
+//               somewhere in the tile, the tile holds min-value pad frames, or it is a silent (all-zero PCM) tile that
+//               was never computed.  That fix-up runs on L2-resident lines, so HBM sees each output byte once.
+//   scheduling = persistent CTAs pulling tiles from an atomic counter in clip-major order, one tile ahead; the next tile's
+//               PCM travels global->shared by TMA bulk copies (mbarrier completion) under the current tile's mel phase;
+//               a CTA never waits while tiles are still unclaimed (pending tiles are ringed / parked), so the kernel is
+//               deadlock-free for any grid size.
 //
-// Shared memory per CTA (3 CTAs/SM): one 57.9 KB region time-multiplexed as
+// Shared memory per CTA: one 28.9 KB region time-multiplexed as
 //   [audio tile at the top] -> stage A->B exchange -> [power tile at the bottom | next audio tile at the top],
-// plus ~9 KB of window / twiddle / mel-step tables.  The whole hot loop is < 32 KB of SASS (one DFT20 copy per
-// stage) so that it stays resident in the SM's instruction cache.
+// plus ~8.7 KB of window / twiddle / mel-program tables and control words.  The hot loop is one DFT20 copy per stage and
+// ~2.6 k SASS instructions so that it stays resident in the SM's instruction cache.
 #pragma once
 
 #include <cuda_runtime.h>
