@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WFT_ABI_VERSION 1
+#define WFT_ABI_VERSION 2
 
 /* Front-end constants (whisper.audio: SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES;
  * imported by the reference at data_loader.py:13 and data/utils.py:10). */
@@ -113,6 +113,18 @@ int wft_specaug_apply_f32(const float* in, float* out, int32_t batch, int32_t n_
 int wft_specaug_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_mels, int32_t n_frames,
                      int32_t time_mask_param, int32_t freq_mask_param, float p, int32_t* mask_params_out,
                      void* stream);
+
+/* ---- "next" rows of the path, stand-alone ------------------------------------------------------------
+ * SpecAugment time-warp, the step between pad_or_trim and the masks (data_loader.py:285, data/utils.py:41-143):
+ * out[b] = in[b] resampled along time through the 3-knot cubic Hermite map defined by (warp_p, warp_d), bilinear,
+ * zeros outside, grid_sample(align_corners=True) semantics.  warp_params is device int32 [B,2]; in != out. */
+int wft_time_warp_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames,
+                      const int32_t* warp_params, void* stream);
+
+/* Counter-based draw of (warp_p in [W, T-W), warp_d in [-W, W)) per clip (the reference's torch.randint ranges,
+ * data/utils.py:107-111), Philox keyed like wft_specaug_draw; (T/2, 0) = identity when the p gate rejects the clip. */
+int wft_time_warp_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t time_warp_w, float p,
+                       int32_t* warp_params_out, void* stream);
 
 /* Introspection used by bench.py / tests: number of kernel launches issued by this library on the calling
  * thread since the last reset, and the persistent grid the fused kernel would use on the current device. */

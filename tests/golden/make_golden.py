@@ -15,6 +15,9 @@ What gets pinned, and by what:
 * ``logmel_hf.npz``        -- log-mel of short seeded clips from the independent ``transformers`` Whisper feature extractor
                               (feature_extraction_whisper.py ``_np_extract_fbank_features``), the closest published
                               implementation available offline; cross-checks the oracle's STFT / mel / log recipe.
+* ``timewarp.npz``         -- outputs of the REFERENCE'S OWN ``TimeWarpAugmenter`` and ``ExtremesFrequencyMasking``
+                              (data/utils.py:41-190) on oracle log-mels under fixed torch seeds, with the replayed
+                              (warp_p, warp_d) / (low, high) parameters; sub-sampled rows to stay small.
 * ``mel_filters.npz``      -- ``transformers.audio_utils.mel_filter_bank`` (slaney / slaney) for 80 and 128 rows.
 
 Inputs are regenerated from seeds by ``tests/signals.py``; only outputs are stored.
@@ -132,6 +135,32 @@ def golden_logmel_hf():
     np.savez_compressed(os.path.join(HERE, "logmel_hf.npz"), n=len(cases), **out)
 
 
+def golden_timewarp():
+    from whisper_finetune.data.utils import ExtremesFrequencyMasking, TimeWarpAugmenter
+
+    out = {}
+    cases = [("white", 128, 80, 3), ("hdr", 80, 80, 4), ("chirp", 128, 50, 5), ("int16", 80, 20, 6)]
+    for k, (kind, n_mels, W, seed) in enumerate(cases):
+        x = S.make(kind, seed=seed)
+        if x.dtype == torch.int16:
+            x = x.float() / 32768.0
+        mel = O.log_mel_spectrogram(x, n_mels)
+        torch.manual_seed(seed)
+        warped = TimeWarpAugmenter(W=W)(mel)
+        torch.manual_seed(seed)
+        wp = int(torch.randint(W, 3000 - W, (1,)))
+        wd = int(torch.randint(-W, W, (1,)))
+        torch.manual_seed(seed + 100)
+        ext = ExtremesFrequencyMasking(low_freq_range=10, high_freq_range=15)(mel.clone())
+        torch.manual_seed(seed + 100)
+        r = torch.rand(1).item()
+        out[f"warp{k}"] = warped[::8].numpy().copy()
+        out[f"ext_zero_rows{k}"] = (ext == 0).all(dim=1).numpy()
+        out[f"meta{k}"] = np.array([n_mels, W, seed, wp, wd, int(round(r * 10)), int(round(r * 15))], dtype=np.int64)
+        out[f"kind{k}"] = np.array(kind)
+    np.savez_compressed(os.path.join(HERE, "timewarp.npz"), n=len(cases), **out)
+
+
 def golden_mel_filters():
     from transformers.audio_utils import mel_filter_bank
 
@@ -144,6 +173,7 @@ if __name__ == "__main__":
     golden_pad_or_trim()
     golden_calculate_mel()
     golden_logmel_hf()
+    golden_timewarp()
     golden_mel_filters()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -318,3 +318,62 @@ def test_zero_padded_tails_take_the_silent_path(wft, cuda, dtype):
         noisy = torch.where(torch.arange(480000)[None, :] < torch.as_tensor(lens)[:, None], pcm, torch.full_like(pcm, 8191))
     got2 = fe(noisy.to(cuda), lengths=lengths, n_valid_frames=n_valid, mask_params=masks).cpu()
     assert torch.equal(got2, got)
+
+
+def test_time_warp_matches_oracle_and_reference_golden(wft, cuda):
+    from oracle import timewarp as OT
+
+    z = _gold("timewarp.npz")
+    for k in range(int(z["n"])):
+        n_mels, W, seed, wp, wd, low, high = (int(v) for v in z[f"meta{k}"])
+        x = S.make(str(z[f"kind{k}"]), seed=seed)
+        mel = O.log_mel_spectrogram(x, n_mels)
+        got = wft.time_warp(mel.to(cuda), torch.tensor([[wp, wd]], dtype=torch.int32)).cpu()
+        ref = OT.time_warp(mel, wp, wd)
+        assert (got - ref).abs().max() <= 2e-5, "CUDA vs oracle (same float64 spline)"
+        assert np.abs(got[::8].numpy() - z[f"warp{k}"]).max() <= 1e-3, "CUDA vs the reference class (float32 spline)"
+        # drop-in class: same torch seed -> same (warp_p, warp_d) as the reference
+        torch.manual_seed(seed)
+        via_class = wft.TimeWarpAugmenter(W=W)(mel.to(cuda)).cpu()
+        assert torch.equal(via_class, got)
+    batch = torch.stack([mel, mel.flip(1)]).to(cuda)
+    wps = torch.tensor([[700, 33], [2500, -41]], dtype=torch.int32)
+    out = wft.time_warp(batch, wps).cpu()
+    for b in range(2):
+        assert (out[b] - OT.time_warp(batch[b].cpu(), int(wps[b, 0]), int(wps[b, 1]))).abs().max() <= 2e-5
+    draws = wft.draw_warp_params(42, 0, 4096, 3000, 80).cpu()
+    assert (draws[:, 0] >= 80).all() and (draws[:, 0] < 2920).all() and (draws[:, 1] >= -80).all() and (draws[:, 1] < 80).all()
+    assert torch.equal(draws[100:200], wft.draw_warp_params(42, 100, 100, 3000, 80).cpu())
+    assert (wft.draw_warp_params(42, 0, 16, 3000, 80, p=0.0).cpu() == torch.tensor([1500, 0])).all()
+
+
+def test_extremes_mask_matches_reference_golden(wft, cuda):
+    z = _gold("timewarp.npz")
+    for k in range(int(z["n"])):
+        n_mels, W, seed, wp, wd, low, high = (int(v) for v in z[f"meta{k}"])
+        x = S.make(str(z[f"kind{k}"]), seed=seed)
+        mel = O.log_mel_spectrogram(x, n_mels).to(cuda)
+        keep = mel.clone()
+        torch.manual_seed(seed + 100)
+        res = wft.ExtremesFrequencyMasking(10, 15)(mel)
+        assert res.data_ptr() == mel.data_ptr(), "in place, like the reference"
+        zero_rows = (res == 0).all(dim=1).cpu().numpy()
+        assert np.array_equal(zero_rows, z[f"ext_zero_rows{k}"])
+        assert torch.equal(res[~torch.from_numpy(zero_rows).to(cuda)], keep[~torch.from_numpy(zero_rows).to(cuda)])
+
+
+def test_front_end_with_time_warp_follows_reference_order(wft, cuda):
+    """warp -> time mask -> frequency mask (data_loader.py:285-287)."""
+    from oracle import timewarp as OT
+
+    x = torch.stack([S.make("white", seed=61), S.make("chirp", seed=62)])
+    fe = wft.FrontEnd(n_mels=80, spec_augment=True, seed=5,
+                      spec_augment_params={"time_mask_param": 100, "freq_mask_param": 43, "time_warp_w": 80,
+                                           "fuse_time_warp": True, "p": 1.0})
+    got = fe(x.to(cuda), clip_offset=10).cpu()
+    warps = wft.draw_warp_params(5, 10, 2, 3000, 80).cpu().numpy()
+    masks = OS.draw_mask_params(5, 10, 2, 80, 3000, 100, 43, 1.0)
+    for b in range(2):
+        ref = OS.apply_masks(OT.time_warp(O.log_mel_spectrogram(x[b], 80), int(warps[b, 0]), int(warps[b, 1])), *masks[b])
+        assert (got[b] - ref).abs().max() <= 1e-3
+        assert torch.equal(got[b] == 0, ref == 0)

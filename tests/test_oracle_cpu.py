@@ -162,3 +162,22 @@ def test_sampler_restatement_matches_torch(n, world, drop_last, shuffle):
             ds = DistributedSampler(range(n), num_replicas=world, rank=rank, shuffle=shuffle, seed=42, drop_last=drop_last)
             ds.set_epoch(epoch)
             assert list(iter(ds)) == OSamp.rank_indices(n, world, rank, epoch, 42, shuffle, drop_last)
+
+
+def test_timewarp_and_extremes_against_reference_goldens():
+    """oracle/timewarp.py vs the reference's TimeWarpAugmenter / ExtremesFrequencyMasking outputs.  The reference evaluates
+    its spline in float32 (pow + matmul), which moves source coordinates by ~1e-4 frames: tolerance max-abs 1e-3."""
+    from oracle import timewarp as OT
+
+    z = _npz("timewarp.npz")
+    for k in range(int(z["n"])):
+        n_mels, W, seed, wp, wd, low, high = (int(v) for v in z[f"meta{k}"])
+        x = S.make(str(z[f"kind{k}"]), seed=seed)
+        mel = O.log_mel_spectrogram(x, n_mels)
+        got = OT.time_warp(mel, wp, wd)
+        assert np.abs(got[::8].numpy() - z[f"warp{k}"]).max() <= 1e-3
+        assert W <= wp < 3000 - W and -W <= wd < W
+        ext = OT.extremes_mask(mel, low, high)
+        assert np.array_equal((ext == 0).all(dim=1).numpy(), z[f"ext_zero_rows{k}"])
+    ident = OT.time_warp(mel, 1500, 0)  # warp_d = 0: the spline is the identity map
+    assert (ident - mel).abs().max() <= 2e-4

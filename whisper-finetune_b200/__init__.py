@@ -6,7 +6,8 @@ PCM -> log-mel -> cut / min-pad -> SpecAugment masks -> ``x[B, n_mels, 3000]``
 """
 from .audio import (CHUNK_LENGTH, HOP_LENGTH, N_FFT, N_FRAMES, N_SAMPLES, SAMPLE_RATE, frontend_forward,
                     log_mel_spectrogram, pad_or_trim)
-from .augment import FrequencyMasking, TimeMasking, apply_masks, draw_mask_params
+from .augment import (ExtremesFrequencyMasking, FrequencyMasking, TimeMasking, TimeWarpAugmenter, apply_masks,
+                      draw_mask_params, draw_warp_params, time_warp)
 from .frontend import FrontEnd, HostPipeline
 from .install import install
 from .melbank import slaney_mel_bank
@@ -16,5 +17,6 @@ __all__ = [
     "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "CHUNK_LENGTH", "N_SAMPLES", "N_FRAMES",
     "log_mel_spectrogram", "pad_or_trim", "frontend_forward", "FrontEnd", "HostPipeline",
     "TimeMasking", "FrequencyMasking", "apply_masks", "draw_mask_params",
+    "TimeWarpAugmenter", "ExtremesFrequencyMasking", "time_warp", "draw_warp_params",
     "shard_indices", "all_gather_features", "slaney_mel_bank", "install",
 ]

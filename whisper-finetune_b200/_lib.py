@@ -15,7 +15,7 @@ WFT_PCM_F32 = 0
 WFT_PCM_I16 = 1
 WFT_ERR_INVALID = -1
 WFT_ERR_CUDA = -2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class FrontendArgs(Structure):
@@ -50,6 +50,8 @@ SIGNATURES = {
     "wft_specaug_apply_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_float, c_void_p]),
     "wft_specaug_draw": (c_int, [c_uint64, c_uint64, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                  c_void_p, c_void_p]),
+    "wft_time_warp_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "wft_time_warp_draw": (c_int, [c_uint64, c_uint64, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
     "wft_launch_count": (c_int64, [c_int]),
     "wft_frontend_grid": (c_int, [c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
 }

@@ -103,3 +103,94 @@ class FrequencyMasking(_AxisMask):
 
     def __init__(self, freq_mask_param: int):
         super().__init__(freq_mask_param)
+
+
+# ---- "next" rows: time-warp and extremes mask -------------------------------------------------------
+
+def time_warp(mel: torch.Tensor, warp_params: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``mel`` CUDA float32 ``[B, R, T]`` (or ``[R, T]``), ``warp_params`` int32 ``[B, 2]`` = (warp_p, warp_d) ->
+    time-warped copy (``wft_time_warp_f32``: cubic Hermite source map, bilinear resampling, zeros outside)."""
+    lib = _lib.load()
+    if not mel.is_cuda or mel.dtype != torch.float32:
+        raise ValueError("mel must be a CUDA float32 tensor")
+    squeeze = mel.dim() == 2
+    x = (mel.unsqueeze(0) if squeeze else mel).contiguous()
+    if x.dim() != 3:
+        raise ValueError("You sure it's a Spectrogram?")
+    B, R, T = x.shape
+    wp = torch.as_tensor(warp_params, dtype=torch.int32).to(x.device).contiguous()
+    if tuple(wp.shape) != (B, 2):
+        raise ValueError(f"warp_params must have shape {(B, 2)}")
+    res = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _lib.check(lib.wft_time_warp_f32(x.data_ptr(), res.data_ptr(), B, R, T, wp.data_ptr(), _stream_ptr(x.device)))
+    return res[0] if squeeze else res
+
+
+def draw_warp_params(seed: int, clip_offset: int, batch: int, n_frames: int, time_warp_w: int, p: float = 1.0,
+                     device=None) -> torch.Tensor:
+    """Device-side counter-based draw of (warp_p, warp_d) -> int32 ``[batch, 2]`` (``wft_time_warp_draw``)."""
+    if not 0.0 <= p <= 1.0:
+        raise ValueError(f"spec_augment p must be between 0 and 1, got {p}")
+    lib = _lib.load()
+    dev = resolve_device(device)
+    out = torch.empty((batch, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.wft_time_warp_draw(ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(clip_offset), batch,
+                                          n_frames, time_warp_w, float(p), out.data_ptr(), _stream_ptr(dev)))
+    return out
+
+
+class TimeWarpAugmenter:
+    """Drop-in for the reference's ``TimeWarpAugmenter(W)`` (data/utils.py:41-143, used at data_loader.py:117,285).
+
+    ``warp_p = randint(W, T - W)`` and ``warp_d = randint(-W, W)`` come from torch's global CPU generator in the
+    reference's order, so a seeded run warps by the same amount; the resampling runs on the GPU.  A 3-D input
+    ``[C, R, T]`` gets ONE warp for all slices, exactly like the reference (it treats the leading axis as channels)."""
+
+    def __init__(self, W: int = 50):
+        self.W = int(W)
+
+    def __call__(self, specs):
+        if not torch.is_tensor(specs):
+            specs = torch.from_numpy(specs)
+        if specs.dim() < 2 or specs.dim() > 3:
+            raise ValueError("You sure it's a Spectrogram?")
+        T = specs.shape[-1]
+        warp_p = int(torch.randint(self.W, T - self.W, (1,)))
+        warp_d = int(torch.randint(-self.W, self.W, (1,)))
+        dev = resolve_device(None, specs)
+        x = specs.to(dev, torch.float32)
+        lead = x.shape[0] if x.dim() == 3 else 1
+        wp = torch.tensor([[warp_p, warp_d]] * lead, dtype=torch.int32)
+        res = time_warp(x, wp)
+        return res if specs.is_cuda else res.to(specs.device)
+
+
+class ExtremesFrequencyMasking:
+    """Drop-in for the reference's ``ExtremesFrequencyMasking`` (data/utils.py:146-190, used at data_loader.py:124-130,
+    289-290): per sample ONE ``torch.rand(1)`` ratio; the ``round(r * low)`` lowest and ``round(r * high)`` highest mel
+    rows are zeroed.  Like the reference it works IN PLACE on tensors and returns its argument."""
+
+    def __init__(self, low_freq_range: int = 10, high_freq_range: int = 10):
+        self.low_freq_range = low_freq_range
+        self.high_freq_range = high_freq_range
+
+    def __call__(self, specs: torch.Tensor) -> torch.Tensor:
+        if not torch.is_tensor(specs):
+            specs = torch.tensor(specs)
+        x = specs.unsqueeze(0) if specs.dim() == 2 else specs
+        batch, n_mels, _ = x.shape
+        rows = []
+        for _ in range(batch):
+            r = torch.rand(1).item()
+            low = min(int(round(r * self.low_freq_range)), n_mels)
+            high = min(int(round(r * self.high_freq_range)), n_mels)
+            rows.append((low, high))
+        if not specs.is_cuda or specs.dtype != torch.float32 or not x.is_contiguous():
+            raise ValueError("ExtremesFrequencyMasking expects a contiguous CUDA float32 spectrogram (in-place op)")
+        low_p = torch.tensor([[0, 0, 0, lo] for lo, _ in rows], dtype=torch.int32)
+        high_p = torch.tensor([[0, 0, n_mels - hi, n_mels] for _, hi in rows], dtype=torch.int32)
+        apply_masks(x, low_p, 0.0, out=x)
+        apply_masks(x, high_p, 0.0, out=x)
+        return specs

@@ -174,6 +174,83 @@ __global__ void specaug_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t
   reinterpret_cast<int4*>(out)[b] = mk;
 }
 
+
+// SpecAugment time-warp (data/utils.py:95-143): out[b, r, t] = bilinear sample of in[b] at the source frame given by a
+// cubic Hermite spline through (0,-1), (warp_p, (warp_p - warp_d) * 2 / (T-1) - 1), (T-1, 1) in grid_sample's normalised
+// (align_corners=True) coordinates, zeros outside.  The spline is evaluated in float64 and rounded once; the bilinear
+// stage mirrors torch.nn.functional.grid_sample's float32 arithmetic.  warp_params is device int32 [B,2] = (warp_p, warp_d).
+__global__ void time_warp_kernel(const float* __restrict__ in, float* __restrict__ out, int32_t n_rows, int32_t n_frames,
+                                 const int32_t* __restrict__ warp_params) {
+  const int b = blockIdx.z;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_frames) return;
+  const int2 wp = __ldg(reinterpret_cast<const int2*>(warp_params) + b);
+  const int T = n_frames, R = n_rows;
+  // source coordinate of output frame t
+  const double x1 = static_cast<double>(wp.x), x2 = static_cast<double>(T - 1);
+  const double y0 = -1.0, y1 = static_cast<double>(wp.x - wp.y) * 2.0 / (T - 1.0) - 1.0, y2 = 1.0;
+  const double s0 = (y1 - y0) / x1, s1 = (y2 - y1) / (x2 - x1);
+  const double m0 = s0, m1 = 0.5 * (s0 + s1), m2 = s1;
+  const bool second = static_cast<double>(t) > x1;
+  const double xa = second ? x1 : 0.0, dx = second ? (x2 - x1) : x1;
+  const double ya = second ? y1 : y0, yb = second ? y2 : y1, ma = second ? m1 : m0, mb = second ? m2 : m1;
+  const double u = (static_cast<double>(t) - xa) / dx, u2 = u * u, u3 = u2 * u;
+  const double gx64 = (1.0 - 3.0 * u2 + 2.0 * u3) * ya + (u - 2.0 * u2 + u3) * ma * dx + (3.0 * u2 - 2.0 * u3) * yb +
+                      (-u2 + u3) * mb * dx;
+  const float gx = static_cast<float>(gx64);
+  const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(T - 1);
+  const float ix0f = floorf(ix);
+  const int ix0 = static_cast<int>(ix0f), ix1 = ix0 + 1;
+  const float wx1 = ix - ix0f, wx0 = (ix0f + 1.0f) - ix;
+  const float step = 2.0f / static_cast<float>(R - 1);  // torch.linspace(-1, 1, R)
+  const size_t clip = static_cast<size_t>(b) * R * T;
+  for (int r = blockIdx.y; r < R; r += gridDim.y) {
+    const float gy = (r < R / 2) ? (-1.0f + step * static_cast<float>(r)) : (1.0f - step * static_cast<float>(R - 1 - r));
+    const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
+    const float iy0f = floorf(iy);
+    const int iy0 = static_cast<int>(iy0f), iy1 = iy0 + 1;
+    const float wy1 = iy - iy0f, wy0 = (iy0f + 1.0f) - iy;
+    float acc = 0.0f;
+    const bool cx0 = ix0 >= 0 && ix0 < T, cx1 = ix1 >= 0 && ix1 < T;
+    if (iy0 >= 0 && iy0 < R) {
+      const float* row = in + clip + static_cast<size_t>(iy0) * T;
+      if (cx0) acc += __ldg(row + ix0) * (wx0 * wy0);
+      if (cx1) acc += __ldg(row + ix1) * (wx1 * wy0);
+    }
+    if (iy1 >= 0 && iy1 < R && wy1 != 0.0f) {
+      const float* row = in + clip + static_cast<size_t>(iy1) * T;
+      if (cx0) acc += __ldg(row + ix0) * (wx0 * wy1);
+      if (cx1) acc += __ldg(row + ix1) * (wx1 * wy1);
+    }
+    out[clip + static_cast<size_t>(r) * T + t] = acc;
+  }
+}
+
+// counter-based draw of (warp_p, warp_d): warp_p uniform in [W, T-W), warp_d uniform in [-W, W) (the reference's randint
+// ranges, data/utils.py:107-111), Philox block 2 of the clip's counter; (T/2, 0) == identity when the p gate rejects
+__global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t W,
+                                      float p, int32_t* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const uint64_t idx = clip_offset + static_cast<uint64_t>(b);
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
+  bool apply = p >= 1.0f;
+  if (!apply && p > 0.0f) {
+    uint32_t g[4];
+    philox4x32_10(lo, hi, 1u, 0u, k0, k1, g);
+    apply = u01(g[0]) < p;
+  }
+  int2 w = make_int2(n_frames / 2, 0);
+  if (apply && W > 0 && n_frames > 2 * W) {
+    uint32_t r[4];
+    philox4x32_10(lo, hi, 2u, 0u, k0, k1, r);
+    w.x = W + static_cast<int>(__fmul_rn(u01(r[0]), static_cast<float>(n_frames - 2 * W)));
+    w.y = -W + static_cast<int>(__fmul_rn(u01(r[1]), static_cast<float>(2 * W)));
+  }
+  reinterpret_cast<int2*>(out)[b] = w;
+}
+
 int grid_1d(int64_t n, int threads) {
   int64_t g = (n + threads - 1) / threads;
   const int64_t cap = 148 * 16;
@@ -327,6 +404,38 @@ int wft_specaug_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t
   if ((reinterpret_cast<uintptr_t>(mask_params_out) & 15) != 0) return fail(WFT_ERR_INVALID, "mask_params_out must be 16-byte aligned");
   specaug_draw_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(seed, clip_offset, batch, n_mels, n_frames,
                                                                time_mask_param, freq_mask_param, p, mask_params_out);
+  ++g_launches;
+  WFT_CUDA(cudaGetLastError());
+  return WFT_OK;
+}
+
+int wft_time_warp_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames,
+                      const int32_t* warp_params, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (batch < 0 || n_rows < 0 || n_frames < 0) return fail(WFT_ERR_INVALID, "negative extent");
+  if (static_cast<int64_t>(batch) * n_rows * n_frames == 0) return WFT_OK;
+  if (in == nullptr || out == nullptr || warp_params == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
+  if (in == out) return fail(WFT_ERR_INVALID, "time warp cannot run in place");
+  if (n_rows < 2 || n_frames < 3) return fail(WFT_ERR_INVALID, "time warp needs at least 2 rows and 3 frames");
+  if ((reinterpret_cast<uintptr_t>(warp_params) & 7) != 0) return fail(WFT_ERR_INVALID, "warp_params must be 8-byte aligned");
+  if (batch > 65535) return fail(WFT_ERR_INVALID, "batch too large for one launch (max 65535)");
+  dim3 grid((n_frames + 255) / 256, n_rows < 16 ? n_rows : 16, batch);
+  time_warp_kernel<<<grid, 256, 0, stream>>>(in, out, n_rows, n_frames, warp_params);
+  ++g_launches;
+  WFT_CUDA(cudaGetLastError());
+  return WFT_OK;
+}
+
+int wft_time_warp_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t time_warp_w, float p,
+                       int32_t* warp_params_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (batch < 1) return fail(WFT_ERR_INVALID, "batch must be >= 1");
+  if (n_frames < 3 || time_warp_w < 0) return fail(WFT_ERR_INVALID, "n_frames must be >= 3 and time_warp_w >= 0");
+  if (!(p >= 0.0f && p <= 1.0f)) return fail(WFT_ERR_INVALID, "spec_augment p must be between 0 and 1");
+  if (warp_params_out == nullptr) return fail(WFT_ERR_INVALID, "warp_params_out is NULL");
+  if ((reinterpret_cast<uintptr_t>(warp_params_out) & 7) != 0) return fail(WFT_ERR_INVALID, "warp_params_out must be 8-byte aligned");
+  time_warp_draw_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(seed, clip_offset, batch, n_frames, time_warp_w, p,
+                                                                 warp_params_out);
   ++g_launches;
   WFT_CUDA(cudaGetLastError());
   return WFT_OK;

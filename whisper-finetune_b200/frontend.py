@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 from .audio import N_FRAMES, N_SAMPLES, frontend_forward, resolve_device
-from .augment import draw_mask_params
+from .augment import apply_masks, draw_mask_params, draw_warp_params, time_warp
 
 
 class FrontEnd:
@@ -37,10 +37,14 @@ class FrontEnd:
                 raise ValueError(f"spec_augment p must be between 0 and 1, got {self.spec_augment_p}")
             self.time_mask_param = int(params["time_mask_param"])
             self.freq_mask_param = int(params["freq_mask_param"])
+            # time_warp_w (data_loader.py:117): off unless asked for -- the warp sits between pad_or_trim and the masks and
+            # needs the finished (floored) features, so it runs as a second kernel and the masks as a third
+            self.time_warp_w = int(params.get("time_warp_w", 0)) if params.get("fuse_time_warp", False) else 0
         else:
             self.spec_augment_p = 0.0
             self.time_mask_param = 0
             self.freq_mask_param = 0
+            self.time_warp_w = 0
 
     def __call__(self, pcm: torch.Tensor, lengths=None, n_valid_frames=None, clip_offset: int = 0,
                  mask_params: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -57,6 +61,14 @@ class FrontEnd:
             mask_params = draw_mask_params(self.seed, clip_offset, B, self.n_mels, self.n_frames,
                                            self.time_mask_param, self.freq_mask_param, self.spec_augment_p,
                                            self.device)
+        if self.time_warp_w > 0 and self.spec_augment_p > 0.0:
+            # reference order (data_loader.py:285-287): warp -> time mask -> frequency mask
+            plain = frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
+                                     n_frames_out=self.n_frames, n_valid_frames=n_valid_frames)
+            warps = draw_warp_params(self.seed, clip_offset, B, self.n_frames, self.time_warp_w, self.spec_augment_p,
+                                     self.device)
+            warped = time_warp(plain, warps, out=out)
+            return apply_masks(warped, mask_params, 0.0, out=warped) if mask_params is not None else warped
         return frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
                                 n_frames_out=self.n_frames, n_valid_frames=n_valid_frames,
                                 mask_params=mask_params, mask_value=0.0, out=out)

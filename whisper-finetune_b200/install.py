@@ -25,6 +25,11 @@ def install(data_loader_module: Optional[ModuleType] = None, patch_whisper_audio
         if patch_masks and hasattr(dl, "T"):
             dl.T.TimeMasking = augment.TimeMasking
             dl.T.FrequencyMasking = augment.FrequencyMasking
+        if patch_masks:
+            if hasattr(dl, "TimeWarpAugmenter"):
+                dl.TimeWarpAugmenter = augment.TimeWarpAugmenter
+            if hasattr(dl, "ExtremesFrequencyMasking"):
+                dl.ExtremesFrequencyMasking = augment.ExtremesFrequencyMasking
     du = sys.modules.get("whisper_finetune.data.utils")
     if du is not None:
         du.pad_or_trim = audio.pad_or_trim
