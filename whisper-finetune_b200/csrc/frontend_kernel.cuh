@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     } else {
       // nothing to compute: a pad-only tile (n_frames_out > n_frames) or a silent tile (all-zero PCM: every mel value is
       // the 1e-10 clamp, so only its statistics are recorded here and the fix-up later writes the constant rows)
+      __syncthreads();  // everyone has read the descriptor of THIS tile (matters when it is the CTA's first tile)
       if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, sm_ctl + kCtlNext, sm_ctl + kCtlMemo);
       __syncthreads();
       nxt = sm_ctl[kCtlNext];
