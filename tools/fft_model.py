@@ -1,5 +1,5 @@
 import numpy as np, torch, sys, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from oracle.logmel import log_mel_spectrogram
 from oracle.mel_filters import mel_filters
 f32 = np.float32

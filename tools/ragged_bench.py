@@ -1,5 +1,5 @@
 import sys, torch, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import whisper_finetune_b200 as w
 torch.cuda.set_device(0)
 rng = np.random.default_rng(42)

@@ -1,5 +1,5 @@
 import sys, json, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import whisper_finetune_b200 as w
 torch.cuda.set_device(0)
 res = []
@@ -24,4 +24,4 @@ for dtype in (torch.float32, torch.int16):
       r = dict(dtype=str(dtype).split('.')[-1], n_mels=nm, B=B, us=ms*1e3, clips_per_s=B/ms*1e3, us_per_clip=ms*1e3/B, GBps=byts/ms/1e6, frac=byts/ms/1e6/6551.7)
       res.append(r); print(json.dumps(r), flush=True)
       del pcm, out
-json.dump(res, open('/root/repo/gpurun_out/sweep_r1.json','w'))
+json.dump(res, open('gpurun_out/sweep_r1.json','w'))
