@@ -166,7 +166,7 @@ perm = torch.randperm(n, generator=g).tolist()
 want = torch.stack([torch.from_numpy(OS.draw_mask_params(42, i, 1, 128, 3000, 100, 27, 1.0)[0]).float() for i in perm])
 assert torch.equal(order, want), "gathered shards must equal the single-process result"
 dist.barrier(); dist.destroy_process_group()
-print("rank", rank, "ok")
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"rank{rank}.ok"), "w").write("ok")
 """
 
 
@@ -178,7 +178,7 @@ def test_two_rank_gloo_sharding_and_gather(tmp_path):
            "--master-port", "29631", str(script), ROOT]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists()  # (stdout of the two ranks interleaves)
 
 
 def test_bench_reference_arm_prints_contract_line():
