@@ -262,26 +262,41 @@ def run_ours(args):
     kernel_ms = k0.elapsed_time(k1) / args.steps
 
     # end to end through the public API with host buffers (pinned): H2D + kernels + D2H every step
-    host_pcm = [synth_pcm(BATCH, SEED + 1000 * rank + s).pin_memory() for s in range(2)]
-    host_out = [torch.empty(BATCH, N_MELS, N_FRAMES).pin_memory() for _ in range(2)]
-    pipe = wft.HostPipeline(fe, BATCH, n_chunks=8, n_streams=3)
-    e2e_steps = max(3, min(args.steps, 20))
-    for i in range(2):
-        pipe(host_pcm[i % 2], host_out[i % 2], clip_offset=i * BATCH)
-    pipe.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(e2e_steps):
-        pipe(host_pcm[i % 2], host_out[i % 2], clip_offset=(i * world + rank) * BATCH)
-    e1.record()
-    pipe.synchronize()
-    barrier()
-    checksum = float(host_out[(e2e_steps - 1) % 2][0, 0, :8].sum())  # the result really is on the host
-    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * BATCH * e2e_steps / (float(te.item()) * 1e-3)
+    def run_e2e(pcm_dtype, readback):
+        host_pcm = [synth_pcm(BATCH, SEED + 1000 * rank + s) for s in range(2)]
+        if pcm_dtype == torch.int16:
+            host_pcm = [(x * 32767).round().to(torch.int16) for x in host_pcm]
+        host_pcm = [x.pin_memory() for x in host_pcm]
+        shape = (BATCH, N_MELS, N_FRAMES) if readback == "features" else (BATCH,)
+        host_out = [torch.empty(shape).pin_memory() for _ in range(2)]
+        pipe = wft.HostPipeline(fe, BATCH, pcm_dtype=pcm_dtype, n_chunks=8, n_streams=3, readback=readback)
+        steps = max(3, min(args.steps, 20))
+        for i in range(2):
+            pipe(host_pcm[i % 2], host_out[i % 2], clip_offset=i * BATCH)
+        pipe.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            pipe(host_pcm[i % 2], host_out[i % 2], clip_offset=(i * world + rank) * BATCH)
+        e1.record()
+        pipe.synchronize()
+        barrier()
+        probe = float(host_out[(steps - 1) % 2].reshape(BATCH, -1)[0, :8].sum())  # the result really is on the host
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * BATCH * steps / (float(te.item()) * 1e-3), pipe.h2d_bytes, pipe.d2h_bytes, steps, probe
+
+    e2e_value, e2e_h2d, e2e_d2h, e2e_steps, checksum = run_e2e(torch.float32, "features")
+    # informational variants (not the headline): int16 PCM halves the H2D bytes; a training step consumes the features
+    # on the device, so only a per-clip probe has to return
+    e2e_variants = {}
+    for name, dt, rb in (("int16_pcm_features_to_host", torch.int16, "features"),
+                         ("f32_pcm_features_stay_on_device", torch.float32, "probe"),
+                         ("int16_pcm_features_stay_on_device", torch.int16, "probe")):
+        v, h2d, d2h, _, _ = run_e2e(dt, rb)
+        e2e_variants[name] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -296,8 +311,10 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "audio_hours_per_s": value * 30.0 / 3600.0,
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-                    "steps": e2e_steps, "pipeline": "8 chunks on 3 streams, pinned host buffers", "checksum": checksum},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
+                    "steps": e2e_steps, "pipeline": "8 chunks on 3 streams, pinned host buffers, float32 PCM in, full "
+                    "float32 features back to the host", "checksum": checksum},
+            "e2e_variants": e2e_variants,
             "gpu_launches": launches,
             "gpu_launches_per_step": launches / max(args.steps, 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -84,7 +84,10 @@ class HostPipeline:
     """
 
     def __init__(self, front_end: FrontEnd, batch: int, n_samples: int = N_SAMPLES, pcm_dtype=torch.float32,
-                 n_chunks: int = 4, n_streams: int = 2):
+                 n_chunks: int = 4, n_streams: int = 2, readback: str = "features"):
+        """``readback="features"``: the whole feature tensor returns to the host (what the reference's CPU path yields);
+        ``readback="probe"``: features stay in HBM for the model (``train_step`` moves ``x`` to the device anyway,
+        model/model_utils.py:60) and only one float per clip comes back as a liveness probe."""
         self.fe = front_end
         self.batch = int(batch)
         self.n_samples = int(n_samples)
@@ -95,13 +98,16 @@ class HostPipeline:
         self.slices = [(bounds[i], bounds[i + 1]) for i in range(self.n_chunks) if bounds[i + 1] > bounds[i]]
         self.dev_pcm = torch.empty((self.batch, self.n_samples), dtype=pcm_dtype, device=dev)
         self.dev_out = torch.empty((self.batch, front_end.n_mels, front_end.n_frames), dtype=torch.float32, device=dev)
+        if readback not in ("features", "probe"):
+            raise ValueError("readback must be 'features' or 'probe'")
+        self.readback = readback
         self.h2d_bytes = self.dev_pcm.numel() * self.dev_pcm.element_size()
-        self.d2h_bytes = self.dev_out.numel() * 4
+        self.d2h_bytes = self.dev_out.numel() * 4 if readback == "features" else self.batch * 4
 
     def __call__(self, pcm_host: torch.Tensor, out_host: torch.Tensor, lengths=None, n_valid_frames=None,
                  clip_offset: int = 0) -> torch.Tensor:
-        """``pcm_host`` pinned ``[B, N]``, ``out_host`` pinned ``[B, n_mels, 3000]``; returns ``out_host`` once every
-        copy has been enqueued (call ``synchronize()`` before reading it)."""
+        """``pcm_host`` pinned ``[B, N]``, ``out_host`` pinned ``[B, n_mels, 3000]`` (``[B]`` for ``readback="probe"``);
+        returns ``out_host`` once every copy has been enqueued (call ``synchronize()`` before reading it)."""
         cur = torch.cuda.current_stream(self.fe.device)
         for k, (a, b) in enumerate(self.slices):
             st = self.streams[k % len(self.streams)]
@@ -112,7 +118,10 @@ class HostPipeline:
                         lengths=None if lengths is None else lengths[a:b],
                         n_valid_frames=None if n_valid_frames is None else n_valid_frames[a:b],
                         clip_offset=clip_offset + a, out=self.dev_out[a:b])
-                out_host[a:b].copy_(self.dev_out[a:b], non_blocking=True)
+                if self.readback == "features":
+                    out_host[a:b].copy_(self.dev_out[a:b], non_blocking=True)
+                else:
+                    out_host[a:b].copy_(self.dev_out[a:b, 0, 0], non_blocking=True)
         for st in self.streams:
             cur.wait_stream(st)
         return out_host
