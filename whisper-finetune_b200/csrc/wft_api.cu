@@ -279,7 +279,7 @@ int wft_frontend_workspace_bytes(int32_t batch, int32_t n_samples_total, int32_t
   const int64_t n_frames = n_samples_total / WFT_HOP_LENGTH;
   const int64_t span = n_frames_out > n_frames ? n_frames_out : n_frames;
   const int64_t tiles = (span + wft::kTileFrames - 1) / wft::kTileFrames * batch;
-  if (tiles < 1 || tiles > INT32_MAX / 2) return fail(WFT_ERR_INVALID, "batch x frames out of range");
+  if (tiles < 1 || tiles >= wft::kSilentBit) return fail(WFT_ERR_INVALID, "batch x frames out of range (tile ids must stay below 2^30)");
   size_t b = ws_header_bytes(batch) + static_cast<size_t>(tiles) * sizeof(int32_t);
   *bytes = (b + 255) & ~static_cast<size_t>(255);
   return WFT_OK;
