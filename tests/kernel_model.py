@@ -1,5 +1,8 @@
+"""numpy float32 model of the fused kernel's algorithm (TEST INFRASTRUCTURE): frame pairs packed as one complex
+400-point FFT, 20 x 20 Cooley-Tukey with prime-factor 4 x 5 DFT20s, mirror split of the two real spectra, sparse mel
+projection with the 0.25 factor folded in, log2-based log10, per-clip floor.  Used by tests/test_kernel_model_cpu.py to
+show on the CPU that the ALGORITHM the CUDA kernel implements meets the parity tolerance against the oracle."""
 import numpy as np, torch, sys, time
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from oracle.logmel import log_mel_spectrogram
 from oracle.mel_filters import mel_filters
 f32 = np.float32
@@ -33,14 +36,9 @@ def dft20(x):  # x: [..., 20] complex64 -> [..., 20]
         for kb in range(5): out[(5*ka + 16*kb) % 20] = o[kb]
     return np.stack(out, -1).astype(np.complex64)
 
-# check dft20
-rng = np.random.default_rng(0)
-x = (rng.standard_normal((3,20)) + 1j*rng.standard_normal((3,20))).astype(np.complex64)
-print('dft20 err', np.abs(dft20(x) - np.fft.fft(x.astype(np.complex128))).max())
 
 WIN = (0.5 - 0.5*np.cos(2*np.pi*np.arange(400)/400)).astype(f32)
 WIN_T = torch.hann_window(400).numpy()
-print('win diff vs torch', np.abs(WIN - WIN_T).max())
 TW = np.exp(-2j*np.pi*np.outer(np.arange(20), np.arange(20))/400).astype(np.complex64)  # [k1][n2]
 
 def frames_of(x):
