@@ -85,7 +85,7 @@ def test_package_mel_bank_equals_oracle_bank(wft, n_mels):
 
 
 def test_generated_tables_are_current(wft):
-    """csrc/wft_tables.inc on disk is what gen_tables.py generates (window = torch.hann_window, twiddles, mel program)."""
+    """csrc/wft_tables.inc on disk is what gen_tables.py generates (window = torch.hann_window, twiddles, mel plan)."""
     import importlib.util
 
     path = os.path.join(ROOT, "whisper-finetune_b200", "csrc", "gen_tables.py")
@@ -95,12 +95,14 @@ def test_generated_tables_are_current(wft):
     assert gen.generate() == open(os.path.join(os.path.dirname(path), "wft_tables.inc")).read()
     w = gen.window_table()
     assert np.array_equal(w.T.reshape(-1), torch.hann_window(400).numpy())  # [n2][n1] -> w[20 n1 + n2]
-    # mel row program == dense bank product, for both banks (also run inside generate())
+    # thread-level mel plan == dense bank product with every (row, frame) cell computed exactly once, for both banks
     for n_mels in (80, 128):
         bank = wft.slaney_mel_bank(n_mels)
-        words, index, rows_of = gen.row_program(bank)
-        gen.simulate(bank, words, index)
-        assert sorted(r for g in rows_of for r in g) == list(range(n_mels))
+        plan = gen.mel_plan(bank)
+        gen.simulate(bank, plan)
+        assert len(plan["thread"]) == 160 and sorted({t[0] for t in plan["thread"]}) == list(range(n_mels))
+        assert all(1 <= t[1] and t[1] + plan["classes"][plan["warp_class"][i // 32]][0] - 1 <= 199
+                   for i, t in enumerate(plan["thread"]))
 
 
 @pytest.mark.parametrize("n,world,drop_last,shuffle", [(100, 4, False, True), (101, 4, True, True), (7, 8, False, True),

@@ -13,9 +13,11 @@
 //                        upper half to the mirror thread (q, 20 - k1) through its exchange row;
 //               power  : thread (q, j) pairs Z[j + 20 m] with its mirror Z[400 - j - 20 m] and separates the two real
 //                        spectra: 4|Xa|^2 = |Z[k] + conj Z[400-k]|^2, 4|Xb|^2 = |Z[k] - conj Z[400-k]|^2.
-//   mel phase = lane <-> frame, every half-warp owns a cost-balanced set of mel rows; the sparse triangular filters are
-//               walked as a table-driven "row program" (wft_tables.inc) so the code stays small; log10 via MUFU.LG2;
-//               the FINAL feature (L + 4) / 4 with the SpecAugment masks applied is written once to `out`.
+//   mel phase = thread <-> one mel row x 16 (or 8) consecutive frames: the power tile is stored [bin][frame], so one tap of
+//               the sparse triangular filter is LDS.128 + 2 FFMA2 per 4 frames with the weight held in a register; rows
+//               are banded over the warps by tap count (wft_tables.inc) and each band's tap loop is fully unrolled;
+//               log10 via MUFU.LG2; the FINAL feature (L + 4) / 4 with the SpecAugment masks applied is written once to
+//               `out` as 32-byte stores (STG.256).
 //   per-clip max / min = ordered-int atomicMax into the workspace, completion counted per tile.  Once a clip is complete
 //               each CTA re-visits ITS OWN tiles of that clip only if something is still missing: the max-8 floor binds
 //               somewhere in the tile, the tile holds min-value pad frames, or it is a silent (all-zero PCM) tile that
@@ -45,8 +47,7 @@ constexpr int kTileFrames = 16;
 constexpr int kPairs = kTileFrames / 2;                          // 8
 constexpr int kPairThreads = 20;
 constexpr int kThreads = kPairs * kPairThreads;                  // 160
-constexpr int kWarps = kThreads / 32;                            // 5; every half-warp owns one of the 10 mel row groups
-static_assert(2 * kWarps == WFT_MEL_GROUPS, "one mel row group per half-warp");
+constexpr int kWarps = kThreads / 32;                            // 5
 constexpr int kTileSamples = kTileFrames * kHop + (kNfft - kHop);  // 2800
 constexpr int kSkewBlock = 320;                                  // samples per frame pair
 // extra elements after every block of 320 samples: keeps stage A's stride-20 gathers on distinct banks AND every block on
@@ -59,17 +60,16 @@ constexpr int kAudioElems = kTileSamples + 20 * ((kTileSamples - 1) / kSkewBlock
 constexpr int kRowStride = 44;                                   // floats per exchange row (20 complex + pad)
 constexpr int kPairStride = 20 * kRowStride + 24;                // 904: pair stride == 8 (mod 32) banks
 constexpr int kRegionFloats = kPairs * kPairStride;              // 7232 floats = 28928 B
-constexpr int kPStride = 212;                                    // power rows: stride == 20 (mod 32)
-constexpr int kPOddBase = kPairs * kPStride + 2;                 // odd frames: +2 banks -> all 16 rows on distinct banks
-constexpr int kPFloats = kTileFrames * kPStride + 4;
+constexpr int kPStride = WFT_MEL_P_STRIDE;                       // power tile [bin][frame]: 20 floats per bin (16 frames + pad)
+constexpr int kPFloats = 200 * kPStride;                         // bins 0..199 (bin 200 carries no mel weight)
 constexpr int kAudioBase = kRegionFloats - kAudioElems;          // float32 audio tile sits at the TOP of the region
 constexpr int kWinFloats = WFT_WINDOW_TABLE_LEN;                 // 400
 constexpr int kTwFloats = WFT_TWIDDLE_TABLE_LEN;                 // 880
 constexpr int kTwRow = WFT_TWIDDLE_ROW;                          // 44
-constexpr int kProgVec = WFT_MEL80_PROG_VEC > WFT_MEL128_PROG_VEC ? WFT_MEL80_PROG_VEC : WFT_MEL128_PROG_VEC;
+constexpr int kMelWFloats = ((WFT_MEL80_W_LEN > WFT_MEL128_W_LEN ? WFT_MEL80_W_LEN : WFT_MEL128_W_LEN) + 3) & ~3;
 constexpr int kMaxPending = 8;   // <= 8: ring slots in sm_ctl
-constexpr int kCtlInts = 80;
-constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats) * 4 + kProgVec * 16 + kCtlInts * 4;
+constexpr int kCtlInts = 84;
+constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats + kMelWFloats) * 4 + kCtlInts * 4;
 
 static_assert(kPFloats <= kAudioBase, "power tile and prefetched audio tile must not overlap");
 static_assert((kAudioBase & 3) == 0 && ((kSkewBlock + Skew<float>::value) * 4) % 16 == 0 &&
@@ -79,13 +79,40 @@ static_assert(6 * (kSmemBytes + 1024) <= 228 * 1024, "6 CTAs per SM: 6 x (dynami
 
 __device__ const float g_window_table[kWinFloats] = WFT_WINDOW_TABLE_INIT;
 __device__ const float g_twiddle_table[kTwFloats] = WFT_TWIDDLE_TABLE_INIT;
-__device__ const uint4 g_mel80_prog[WFT_MEL80_PROG_VEC] = WFT_MEL80_PROG_INIT;
-__device__ const uint4 g_mel128_prog[WFT_MEL128_PROG_VEC] = WFT_MEL128_PROG_INIT;
-struct MelSpan {
-  int first, count;  // first uint4 of the entries, number of rows
-};
-__constant__ MelSpan c_mel80_index[WFT_MEL_GROUPS][WFT_MEL_CLASSES] = WFT_MEL80_INDEX_INIT;
-__constant__ MelSpan c_mel128_index[WFT_MEL_GROUPS][WFT_MEL_CLASSES] = WFT_MEL128_INDEX_INIT;
+__device__ const float g_mel80_w[WFT_MEL80_W_LEN] = WFT_MEL80_W_INIT;
+__device__ const float g_mel128_w[WFT_MEL128_W_LEN] = WFT_MEL128_W_INIT;
+__device__ const uint32_t g_mel80_thread[kThreads] = WFT_MEL80_THREAD_INIT;
+__device__ const uint32_t g_mel128_thread[kThreads] = WFT_MEL128_THREAD_INIT;
+
+// mel plan (gen_tables.py): warp w runs tap class mel_warp_class(w) = (taps, quads of 4 frames per thread, weight stride)
+template <int NM>
+__host__ __device__ constexpr int mel_n_classes() { return NM == 80 ? WFT_MEL80_NCLASS : WFT_MEL128_NCLASS; }
+template <int NM>
+__host__ __device__ constexpr int mel_class_taps(int c) {
+  constexpr int a[WFT_MEL_MAX_CLASSES] = WFT_MEL80_CLASS_T, b[WFT_MEL_MAX_CLASSES] = WFT_MEL128_CLASS_T;
+  return NM == 80 ? a[c] : b[c];
+}
+template <int NM>
+__host__ __device__ constexpr int mel_class_quads(int c) {
+  constexpr int a[WFT_MEL_MAX_CLASSES] = WFT_MEL80_CLASS_NQ, b[WFT_MEL_MAX_CLASSES] = WFT_MEL128_CLASS_NQ;
+  return NM == 80 ? a[c] : b[c];
+}
+template <int NM>
+__host__ __device__ constexpr int mel_class_wstride(int c) {
+  constexpr int a[WFT_MEL_MAX_CLASSES] = WFT_MEL80_CLASS_WS, b[WFT_MEL_MAX_CLASSES] = WFT_MEL128_CLASS_WS;
+  return NM == 80 ? a[c] : b[c];
+}
+template <int NM>
+__host__ __device__ constexpr int mel_warp_class(int w) {
+  constexpr int a[kWarps] = WFT_MEL80_WARP_CLASS, b[kWarps] = WFT_MEL128_WARP_CLASS;
+  return NM == 80 ? a[w] : b[w];
+}
+template <int NM>
+__host__ __device__ constexpr bool mel_any_wide() {   // does any class hold 16 frames (4 quads) per thread?
+  for (int c = 0; c < mel_n_classes<NM>(); ++c)
+    if (mel_class_quads<NM>(c) == 4) return true;
+  return false;
+}
 
 struct ClipStat {
   uint32_t max_enc;   // ordered-int encoding of max log10(mel) over ALL frames of the clip
@@ -221,53 +248,120 @@ __device__ __forceinline__ float fast_log2(float x) {  // x is a normal float he
   return y;
 }
 
+// whole-warp float max / min in one instruction (CREDUX.{MAX,MIN}.F32, sm_100a)
+__device__ __forceinline__ float warp_max(float x) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float warp_min(float x) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// (pair, slot) of this thread, re-derived from %tid wherever a phase needs it: the volatile read keeps the compiler from
+// carrying ~10 phase-local shared-memory addresses in registers (or on the stack) across the whole tile loop
+// opaque copy of a register value: stops the compiler from keeping addresses derived from it alive (on the stack) for a
+// whole tile when one ADD re-derives them
+__device__ __forceinline__ int launder(int x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+struct PairCoord {
+  int q, r;
+};
+__device__ __forceinline__ PairCoord pair_coord() {
+  int t;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+  PairCoord c;
+  c.q = t / kPairThreads;
+  c.r = t - c.q * kPairThreads;
+  return c;
+}
+
 constexpr int kSilentBit = 1 << 30;   // flag carried by the tile id inside the pending ring / parked chain
 constexpr int kTileIdMask = kSilentBit - 1;
 
 // log10 of the 1e-10 clamp exactly as the mel phase computes it for an all-zero frame
 __device__ __forceinline__ float silent_log_mel() { return fast_log2(1e-10f) * 0.301029995663981195f; }
 
-// ---- mel projection: rows of one tap class; entry = (first_bin*4, row byte offset, w[0..C-1]) in (C+2)/4 uint4 ------
-// h.y holds the row's byte offset in `out` (row * pitch * 4, patched in at kernel start).  The value written is
-// already the final feature (L + 4) / 4 with the SpecAugment masks applied; only the per-clip max-8 floor and the
-// min-value pad are left to the (rare) fix-up.
-struct MelLane {
-  char* obase;        // &out[clip][0][frame]
-  uint32_t store;     // != 0: this lane's frame is written
-  bool tmask;         // this lane's frame lies inside the time mask
-  uint32_t row_lo;    // frequency mask as a byte-offset window: masked iff (h.y - row_lo) < row_span
-  uint32_t row_span;
-  float mask_value;
-};
-
-template <int C>
-__device__ __forceinline__ void mel_rows(const uint4* __restrict__ prog, int count, const float* __restrict__ P,
-                                         const MelLane& ln, float& mx, float& mn) {
-#pragma unroll 2
-  for (int e = 0; e < count; ++e) {
-    const uint4 h = prog[0];
-    const float* pk = reinterpret_cast<const float*>(reinterpret_cast<const char*>(P) + h.x);
-    float acc = __uint_as_float(h.z) * pk[0];
-    acc = fmaf(__uint_as_float(h.w), pk[1], acc);
+// ---- mel projection ---------------------------------------------------------------------------------------------------
+// A thread owns ONE mel row for 16 or 8 consecutive frames and walks them 8 at a time.  pk = &P[start_bin][first frame]
+// in the [bin][frame] power tile, w = the thread's weight column (tap j at w[j * WS]).  Taps run in ascending bin order;
+// padded taps carry a zero weight on an always-finite bin, so the sum is exactly the dense row product.
+template <int T, int WS>
+__device__ __forceinline__ void mel_taps(const float* __restrict__ pk, const float* __restrict__ w, cpx (&acc)[4]) {
 #pragma unroll
-    for (int v = 1; v < (C + 2) / 4; ++v) {
-      const uint4 w = prog[v];
-      acc = fmaf(__uint_as_float(w.x), pk[4 * v - 2], acc);
-      acc = fmaf(__uint_as_float(w.y), pk[4 * v - 1], acc);
-      acc = fmaf(__uint_as_float(w.z), pk[4 * v], acc);
-      acc = fmaf(__uint_as_float(w.w), pk[4 * v + 1], acc);
+  for (int j = 0; j < T; ++j) {
+    const cpx ww = splat(w[j * WS]);
+#pragma unroll
+    for (int qd = 0; qd < 2; ++qd) {
+      const float4 v = *reinterpret_cast<const float4*>(pk + j * kPStride + 4 * qd);
+      if (j == 0) {
+        acc[2 * qd] = cmul(ww, make_float2(v.x, v.y));
+        acc[2 * qd + 1] = cmul(ww, make_float2(v.z, v.w));
+      } else {
+        acc[2 * qd] = cfma(ww, make_float2(v.x, v.y), acc[2 * qd]);
+        acc[2 * qd + 1] = cfma(ww, make_float2(v.z, v.w), acc[2 * qd + 1]);
+      }
     }
-    prog += (C + 2) / 4;
-    const float L = fast_log2(fmaxf(acc, 1e-10f)) * 0.301029995663981195f;
-    mx = fmaxf(mx, L);
-    mn = fminf(mn, L);
-    const bool masked = ln.tmask || (h.y - ln.row_lo) < ln.row_span;
-    const float v = masked ? ln.mask_value : fmaf(L, 0.25f, 1.0f);   // (L + 4) / 4, exactly
-    // predicated store at obase + h.y (one IMAD.WIDE, no branch around the store)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %3, 0;\n\tmad.wide.u32 a, %1, 1, %0;\n\t"
-        "@p st.global.f32 [a], %2;\n\t}\n" ::"l"(ln.obase), "r"(h.y), "f"(v), "r"(ln.store) : "memory");
   }
+}
+// warp-uniform dispatch on the warp's tap class: one fully unrolled tap loop per class
+template <int NM, int C>
+__device__ __forceinline__ void mel_dispatch(int cls, const float* __restrict__ pk, const float* __restrict__ w, cpx (&acc)[4]) {
+  if constexpr (C < mel_n_classes<NM>()) {
+    if (C == mel_n_classes<NM>() - 1 || cls == C)
+      mel_taps<mel_class_taps<NM>(C), mel_class_wstride<NM>(C)>(pk, w, acc);
+    else
+      mel_dispatch<NM, C + 1>(cls, pk, w, acc);
+  }
+}
+
+// frame windows of a tile as 16-bit masks (bit f = frame t0 + f); only edge tiles look at them
+struct MelEdge {
+  uint32_t live;    // real frame of the clip: counts for the max and for the floor test
+  uint32_t kept;    // survives the partial-segment cut: counts for the pad minimum
+  uint32_t store;   // has a cell in `out`
+  uint32_t tmask;   // inside the SpecAugment time mask
+};
+__device__ __forceinline__ uint32_t frame_window(int lo, int hi, int t0) {   // frames [lo, hi) as bits of the tile at t0
+  lo = min(max(lo - t0, 0), kTileFrames);
+  hi = min(max(hi - t0, 0), kTileFrames);
+  return hi > lo ? (1u << hi) - (1u << lo) : 0u;
+}
+__device__ __forceinline__ void st_global_256(float* dst, const float (&v)[8]) {   // one full 32-byte sector per thread
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
+// 8 consecutive frames of one mel row: log10, statistics, final feature (L + 4) / 4 (row mask folded into sc / of), store.
+// kFast: every frame is live, kept, stored and outside the time mask, `dst` is 32-byte aligned.
+// Otherwise bit i of the (already shifted) windows in `e` describes frame i of these 8.
+template <bool kFast>
+__device__ __forceinline__ void mel_post8(const cpx* __restrict__ acc, float sc, float of, float mask_value,
+                                          float* __restrict__ dst, const MelEdge& e, float& mx, float& mn_kept, float& mn_live) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = (i & 1) ? acc[i >> 1].y : acc[i >> 1].x;
+    const float L = fast_log2(fmaxf(a, 1e-10f)) * 0.301029995663981195f;
+    v[i] = fmaf(L, sc, of);   // (L + 4) / 4, exactly
+    if (kFast) {
+      mx = fmaxf(mx, L);
+      mn_live = fminf(mn_live, L);
+    } else {
+      if ((e.live >> i) & 1u) {
+        mx = fmaxf(mx, L);
+        mn_live = fminf(mn_live, L);
+      }
+      if ((e.kept >> i) & 1u) mn_kept = fminf(mn_kept, L);
+      if ((e.tmask >> i) & 1u) v[i] = mask_value;
+      if ((e.store >> i) & 1u) dst[i] = v[i];
+    }
+  }
+  if (kFast) st_global_256(dst, v);
 }
 
 // ---- deferred fix-up of one tile (only tiles that need it, see `tile_needs_fixup`) -----------------------------------
@@ -376,8 +470,10 @@ __device__ __forceinline__ FixupArgs make_fixup_args(const FrontendParams& p) {
 }
 
 // sm_ctl slots
-// [kCtlNext .. +5] = next tile: id, clip, first frame, interior flag, PCM element offset (lo, hi)
-enum { kCtlNext = 0, kCtlReady = 6, kCtlDrain = 7, kCtlDrainClip = 8, kCtlList = 16, kCtlListClip = 24, kCtlRing = 32,
+// [kCtlDesc .. +5] and [kCtlDesc + kCtlSlot .. +5] = two tile descriptors {id, clip, first frame, kind, PCM element offset
+// (lo, hi)}: the tile being worked on and the one after it, swapping roles every iteration.  Every phase re-reads the few
+// fields it needs from here instead of carrying them in registers across the FFT stages.
+enum { kCtlDesc = 0, kCtlSlot = 8, kCtlReady = 76, kCtlDrain = 77, kCtlDrainClip = 78, kCtlNRing = 79, kCtlChain = 80, kCtlList = 16, kCtlListClip = 24, kCtlRing = 32,
        kCtlRingClip = 40, kCtlRingMin = 48, kCtlRed = 56, kCtlMbar = 72, kCtlMemo = 74 };   // kCtlRed: 3 floats per warp (max, kept min, live min)
 
 // how a tile's PCM reaches shared memory
@@ -448,11 +544,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   PcmT* sm_audio = reinterpret_cast<PcmT*>(smem + kAudioBase);
   float* sm_win = smem + kRegionFloats;
   float* sm_tw = sm_win + kWinFloats;
-  uint4* sm_prog = reinterpret_cast<uint4*>(sm_tw + kTwFloats);
-  int* sm_ctl = reinterpret_cast<int*>(sm_prog + kProgVec);
+  float* sm_melw = sm_tw + kTwFloats;
+  int* sm_ctl = reinterpret_cast<int*>(sm_melw + kMelWFloats);
   const int tid = threadIdx.x;
-  const int q = tid / kPairThreads;       // frame pair of the tile
-  const int r = tid - q * kPairThreads;   // n2 (stage A) / k1 (stage B) / j (power)
   const int warp = tid >> 5, lane = tid & 31;
 
   {
@@ -460,69 +554,64 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     const float wscale = sizeof(PcmT) == 2 ? (1.0f / 32768.0f) : 1.0f;
     for (int k = tid; k < kWinFloats; k += kThreads) sm_win[k] = g_window_table[k] * wscale;
     for (int k = tid; k < kTwFloats; k += kThreads) sm_tw[k] = g_twiddle_table[k];
-    constexpr int kVecs = NM == 128 ? WFT_MEL128_PROG_VEC : WFT_MEL80_PROG_VEC;
-    const uint4* gp = NM == 128 ? g_mel128_prog : g_mel80_prog;
-    for (int k = tid; k < kVecs; k += kThreads) sm_prog[k] = gp[k];
+    constexpr int kMelW = NM == 128 ? WFT_MEL128_W_LEN : WFT_MEL80_W_LEN;
+    const float* gw = NM == 128 ? g_mel128_w : g_mel80_w;
+    for (int k = tid; k < kMelW; k += kThreads) sm_melw[k] = gw[k];
   }
   uint64_t* audio_bar = reinterpret_cast<uint64_t*>(sm_ctl + kCtlMbar);  // completion of the audio tile's bulk copies
-  uint32_t audio_phase = 0;
   constexpr int kTmaThread = kThreads - 32;                               // the thread that issues the bulk copies
   if (tid == 0) {
     sm_ctl[kCtlMemo] = -1;
+    sm_ctl[kCtlNRing] = 0;
+    sm_ctl[kCtlChain] = -1;
     mbar_init(audio_bar, 1);
-    describe_tile<PcmT>(tile_geom(p), static_cast<int>(atomicAdd(p.tile_counter, 1u)), sm_ctl + kCtlNext, sm_ctl + kCtlMemo);
+    describe_tile<PcmT>(tile_geom(p), static_cast<int>(atomicAdd(p.tile_counter, 1u)), sm_ctl + kCtlDesc, sm_ctl + kCtlMemo);
   }
   __syncthreads();
-  int cur = sm_ctl[kCtlNext], clip = sm_ctl[kCtlNext + 1], t0 = sm_ctl[kCtlNext + 2], kind = sm_ctl[kCtlNext + 3];
-  bool prefetched = false;
-
-  // row group of this half-warp (lanes 0-15 and 16-31 of a warp run different row programs on the same 16 frames)
-  const MelSpan* mel_idx = NM == 128 ? c_mel128_index[2 * warp + (lane >> 4)] : c_mel80_index[2 * warp + (lane >> 4)];
-  {
-    // turn each entry's row index into the row's byte offset in `out` (the host guarantees it fits 32 bits)
-    const uint32_t row_bytes = static_cast<uint32_t>(p.n_frames_out) * 4u;
-    constexpr int kClassVecs[WFT_MEL_CLASSES] = {1, 2, 3, 4};
-#pragma unroll
-    for (int c = 0; c < WFT_MEL_CLASSES; ++c)
-      if ((lane & 15) < mel_idx[c].count) sm_prog[mel_idx[c].first + (lane & 15) * kClassVecs[c]].y *= row_bytes;
-    __syncwarp();
+  // a tile of kind kTileInterior always arrives by TMA: the first one is sent here, every later one under the tile before it
+  if (tid == kTmaThread && sm_ctl[kCtlDesc + 3] == kTileInterior) {
+    const long long off = (static_cast<long long>(sm_ctl[kCtlDesc + 5]) << 32) | static_cast<unsigned int>(sm_ctl[kCtlDesc + 4]);
+    prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
   }
+  // loop state in ONE register: bit 3 (kCtlSlot) = descriptor slot of the CURRENT tile, bit 0 = parity of the audio mbarrier
+  int lstate = 0;
+
+  // mel phase role of this thread (fixed for the whole launch): row | start_bin << 8 | first_quad << 16 | weight_offset << 18
+  // (kept packed in ONE register across the FFT stages; unpacked again in every mel phase)
+  const uint32_t mel_desc = (NM == 128 ? g_mel128_thread : g_mel80_thread)[tid];
   const uint32_t tiles_per_clip_u = static_cast<uint32_t>(p.tiles_per_clip);
 
-  // warp-0 scheduler state: ring of tiles whose fix-up is pending (in sm_ctl), lane 0 owns the parked chain
-  int n_ring = 0;  // uniform across warp 0
-  int chain = -1;
+  // warp-0 scheduler state lives in sm_ctl (not in registers): ring of tiles whose fix-up is pending, its fill count
+  // kCtlNRing and the head kCtlChain of the parked chain
 
-  while (cur < p.total_tiles) {
+  for (;;) {
+    // current tile: {id, clip, t0, kind} at DESC; thread 0 describes the next tile at NDESC (behind this tile's first barrier)
+    // (one 16-byte read {id, clip, t0, kind} per phase that needs them)
+#define DESC (sm_ctl + (launder(lstate) & kCtlSlot))
+#define NDESC (sm_ctl + ((launder(lstate) & kCtlSlot) ^ kCtlSlot))
+#define DESC4 (*reinterpret_cast<const int4*>(DESC))
+    const int4 d_top = DESC4;
+    if (d_top.x >= p.total_tiles) break;
     // claim the tile AFTER this one now; the answer is consumed two barriers later (latency hidden by stage A)
     int nxt_claim = 0;
     if (tid == 0) nxt_claim = static_cast<int>(atomicAdd(p.tile_counter, 1u));
-    int nxt = p.total_tiles, nxt_clip = 0, nxt_t0 = 0, nxt_kind = kTileEdge;
-    uint4 stat_seen = make_uint4(0u, 0u, 0u, 0u);  // warp 0: snapshot of the clip of ring[lane], sampled early
+    uint32_t seen_max = 0u, seen_done = 0u;  // warp 0: snapshot of the clip of ring[lane] (max_enc, done), sampled early
 
-    const bool silent = (kind == kTileSilent || kind == kTileSilentRest) && t0 < p.n_frames;
-    const bool silent_head = kind == kTileSilent;   // only the first silent tile of a clip touches the clip statistics
-    if (t0 < p.n_frames && !silent) {
+    if (d_top.z < p.n_frames && d_top.w != kTileSilent && d_top.w != kTileSilentRest) {
       // stage 0 ---------------------------------------------------------------------------------------------
-      if (!prefetched) {
+      if (d_top.w != kTileInterior) {   // clip edge, ragged end or unaligned source: scalar staging, now
+        const int clip = d_top.y, t0 = d_top.z;
         const PcmT* x = reinterpret_cast<const PcmT*>(p.pcm) + static_cast<size_t>(clip) * p.clip_stride;
         int len = p.n_samples;
         if (p.lengths != nullptr) {
           const int l = __ldg(p.lengths + clip);
           len = l < 0 ? 0 : (l < len ? l : len);
         }
-        const int g0 = t0 * kHop - kNfft / 2;
-        if (tile_is_interior(x, g0, len)) {
-          if (tid == kTmaThread) prefetch_audio<PcmT>(sm_audio, x + g0, audio_bar);
-          prefetched = true;
-        } else {
-          stage_audio_edge<PcmT>(sm_audio, x, g0, len, p.n_total, tid);
-          __syncthreads();
-        }
-      }
-      if (prefetched) {  // the tile was sent by TMA (normally one tile ago): wait for its bytes
-        mbar_wait(audio_bar, audio_phase);
-        audio_phase ^= 1u;
+        stage_audio_edge<PcmT>(sm_audio, x, t0 * kHop - kNfft / 2, len, p.n_total, tid);
+        __syncthreads();
+      } else {                          // the tile was sent by TMA (normally one tile ago): wait for its bytes
+        mbar_wait(audio_bar, static_cast<uint32_t>(lstate) & 1u);
+        lstate ^= 1;
       }
 
       // stage A: thread (q, n2 = r): x[n1] = w[20 n1 + n2] * (pa + i pb)[20 n1 + n2] ------------------------------
@@ -530,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         cpx x[20];
         {
           float u[28];
+          const auto [q, r] = pair_coord();
           const PcmT* a = sm_audio + (kSkewBlock + Skew<PcmT>::value) * q + r;
 #pragma unroll
           for (int j = 0; j < 28; ++j) u[j] = pcm_as_float(a[20 * j + (j >= 16 ? Skew<PcmT>::value : 0)]);
@@ -548,6 +638,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         __syncthreads();  // audio is dead from here on: the region becomes the exchange buffer
         // (letting half 0 run ahead here with bar.arrive / bar.sync was measured 2-3 % slower)
         dft20(x);
+        const auto [q, r] = pair_coord();
         const float4* t4 = reinterpret_cast<const float4*>(sm_tw + r * kTwRow);
         float2* e2 = reinterpret_cast<float2*>(sm_region + q * kPairStride) + r;
 #pragma unroll
@@ -558,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           e2[k1 * (kRowStride / 2)] = make_float2(x[k1].x * t.z - x[k1].y * t.w, fmaf(x[k1].x, t.w, x[k1].y * t.z));
         }
       }
-      if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, sm_ctl + kCtlNext, sm_ctl + kCtlMemo);
+      if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, NDESC, sm_ctl + kCtlMemo);
       __syncthreads();
 
       // stage B: thread (q, k1 = r): Z[k1 + 20 k2] = DFT20 over n2.  The lower half (k2 < 10, bins k1 + 20 k2 <= 199)
@@ -569,14 +660,19 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         cpx z[10], mz[10];
         {
           cpx y[20];
-          float4* row4 = reinterpret_cast<float4*>(sm_region + q * kPairStride + r * kRowStride);
+          {
+            const auto [q, r] = pair_coord();
+            const float4* row4 = reinterpret_cast<const float4*>(sm_region + q * kPairStride + r * kRowStride);
 #pragma unroll
-          for (int a = 0; a < 10; ++a) {
-            const float4 v = row4[a];
-            y[2 * a] = make_float2(v.x, v.y);
-            y[2 * a + 1] = make_float2(v.z, v.w);
+            for (int a = 0; a < 10; ++a) {
+              const float4 v = row4[a];
+              y[2 * a] = make_float2(v.x, v.y);
+              y[2 * a + 1] = make_float2(v.z, v.w);
+            }
           }
           dft20(y);
+          const auto [q, r] = pair_coord();
+          float4* row4 = reinterpret_cast<float4*>(sm_region + q * kPairStride + r * kRowStride);
           if (r != 0) {
 #pragma unroll
             for (int a = 0; a < 5; ++a)
@@ -591,6 +687,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         }
         __syncthreads();
         {
+          const auto [q, r] = pair_coord();
           const float4* mir = reinterpret_cast<const float4*>(sm_region + q * kPairStride + ((20 - r) % 20) * kRowStride) + 5;
 #pragma unroll
           for (int a = 0; a < 5; ++a) {
@@ -600,73 +697,89 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           }
         }
         __syncthreads();  // exchange is dead: the region becomes power tile (bottom) + next audio tile (top)
-        nxt = sm_ctl[kCtlNext];
-        nxt_clip = sm_ctl[kCtlNext + 1];
-        nxt_t0 = sm_ctl[kCtlNext + 2];
-        nxt_kind = sm_ctl[kCtlNext + 3];
-
-        // prefetch the NEXT tile's PCM into the top of the region
-        prefetched = nxt_kind == kTileInterior;
-        if (prefetched) {
-          const long long off = (static_cast<long long>(sm_ctl[kCtlNext + 5]) << 32) |
-                                static_cast<unsigned int>(sm_ctl[kCtlNext + 4]);
+        // prefetch the NEXT tile's PCM into the top of the region (its descriptor stays in sm_ctl until the loop ends)
+        if (NDESC[3] == kTileInterior) {
+          const long long off = (static_cast<long long>(NDESC[5]) << 32) | static_cast<unsigned int>(NDESC[4]);
           if (tid == kTmaThread) prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
         }
-        if (warp == 0 && lane < n_ring) stat_seen = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
+        if (warp == 0 && lane < sm_ctl[kCtlNRing]) {
+          const uint4 st = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
+          seen_max = st.x;
+          seen_done = st.z;
+        }
 
-        // even frame 2q -> power row q, odd frame 2q+1 -> power row 16+q; row bases keep both the scattered
-        // writes here and the lane<->row reads of the mel phase free of bank conflicts
-        float* pe = sm_region + q * kPStride + r;
-        float* po = pe + kPOddBase;
+        // power tile [bin][frame]: the pair's two frames are neighbours, one 8-byte store per bin
+        const auto [q, r] = pair_coord();
+        float* pw = sm_region + r * kPStride + 2 * q;
 #pragma unroll
         for (int m = 0; m < 10; ++m) {
           // Z[k] = z[m], Z[400-k] = mz[9-m]
-          const cpx sa = cfma(mz[9 - m], make_float2(1.0f, -1.0f), z[m]);   // Z[k] + conj Z[400-k]
-          const cpx sb = cfma(mz[9 - m], make_float2(-1.0f, 1.0f), z[m]);   // Z[k] - conj Z[400-k]
-          pe[20 * m] = fmaf(sa.x, sa.x, sa.y * sa.y);
-          po[20 * m] = fmaf(sb.x, sb.x, sb.y * sb.y);
+          const cpx sa = cfma(mz[9 - m], make_float2(1.0f, -1.0f), z[m]);   // Z[k] + conj Z[400-k]  -> frame 2q
+          const cpx sb = cfma(mz[9 - m], make_float2(-1.0f, 1.0f), z[m]);   // Z[k] - conj Z[400-k]  -> frame 2q + 1
+          *reinterpret_cast<float2*>(pw + 20 * m * kPStride) =
+              make_float2(fmaf(sa.x, sa.x, sa.y * sa.y), fmaf(sb.x, sb.x, sb.y * sb.y));
         }
       }
       __syncthreads();
 
-      // mel phase: warp <-> row group, lane <-> frame ------------------------------------------------------------
+      // mel phase: thread <-> (mel row, 16 or 8 frames) -------------------------------------------------------------
       {
-        const int l16 = lane & 15;   // frame slot of the tile: even frames of the 8 pairs first, then the odd ones
-        const int frame = t0 + (l16 < 8 ? 2 * l16 : 2 * (l16 - 8) + 1);
-        const float* P = sm_region + (l16 < 8 ? l16 * kPStride : kPOddBase + (l16 - 8) * kPStride);
-        const int keep = kept_frames(p.n_valid, clip, p.n_frames);
-        const bool live = frame < p.n_frames;           // real frame of the clip: counts for the max
-        const bool kept = frame < keep;                 // survives the partial-segment cut: counts for the pad min
-        MelLane ln;
-        ln.store = (live && frame < p.n_frames_out) ? 1u : 0u;
-        ln.obase = reinterpret_cast<char*>(p.out + static_cast<size_t>(clip) * NM * p.n_frames_out + frame);
-        ln.tmask = false;
-        ln.row_lo = 0u;
-        ln.row_span = 0u;
-        ln.mask_value = p.mask_value;
-        if (p.masks != nullptr) {
-          const int4 mk = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
-          const uint32_t row_bytes = static_cast<uint32_t>(p.n_frames_out) * 4u;
-          ln.tmask = frame >= mk.x && frame < mk.y;
-          if (mk.w > mk.z) {
-            ln.row_lo = static_cast<uint32_t>(mk.z) * row_bytes;
-            ln.row_span = static_cast<uint32_t>(mk.w - mk.z) * row_bytes;
-          }
-        }
-        float mx = -INFINITY, mn = INFINITY;
-        mel_rows<2>(sm_prog + mel_idx[0].first, mel_idx[0].count, P, ln, mx, mn);
-        mel_rows<6>(sm_prog + mel_idx[1].first, mel_idx[1].count, P, ln, mx, mn);
-        mel_rows<10>(sm_prog + mel_idx[2].first, mel_idx[2].count, P, ln, mx, mn);
-        if constexpr (NM == 80) mel_rows<14>(sm_prog + mel_idx[3].first, mel_idx[3].count, P, ln, mx, mn);
-        if (!live) mx = -INFINITY;
-        float mn_kept = kept ? mn : INFINITY;   // pad value of pad_or_trim: minimum over the kept frames
-        float mn_live = live ? mn : INFINITY;   // does the max-8 floor bind anywhere in this tile?
+        const int4 d_mel = DESC4;
+        const int clip = d_mel.y, t0 = d_mel.z;
+        const int mel_row = static_cast<int>(mel_desc & 0xffu);
+        const int mel_q0 = static_cast<int>((mel_desc >> 16) & 3u);
+        const float* mel_p = sm_region + ((mel_desc >> 8) & 0xffu) * kPStride + 4 * mel_q0;
+        const float* mel_w = sm_melw + (mel_desc >> 18);
+        int mel_cls = 0;
+        bool mel_wide = false;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          mn_kept = fminf(mn_kept, __shfl_xor_sync(0xffffffffu, mn_kept, o));
-          mn_live = fminf(mn_live, __shfl_xor_sync(0xffffffffu, mn_live, o));
+        for (int w = 0; w < kWarps; ++w)
+          if (warp == w) {
+            mel_cls = mel_warp_class<NM>(w);
+            mel_wide = mel_class_quads<NM>(mel_warp_class<NM>(w)) == 4;
+          }
+        // 32-byte stores need an aligned `out` and a row pitch that is a multiple of 8 frames
+        const bool out_vec_ok = (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && (p.n_frames_out & 7) == 0;
+        const int keep = kept_frames(p.n_valid, clip, p.n_frames);
+        int4 mk = make_int4(0, 0, 0, 0);
+        if (p.masks != nullptr) mk = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
+        const bool rowmask = mel_row >= mk.z && mel_row < mk.w;
+        const float sc = rowmask ? 0.0f : 0.25f;            // masked row: 0 * L + mask_value
+        const float of = rowmask ? p.mask_value : 1.0f;
+        // fast tile (uniform over the CTA): all 16 frames live and stored, none inside the time mask, and either all of
+        // them kept or none (frames beyond the partial-segment cut still count for the max; the fix-up pads them later)
+        const bool all_kept = t0 + kTileFrames <= keep;
+        const bool fast = out_vec_ok && (all_kept || keep <= t0) && t0 + kTileFrames <= p.n_frames &&
+                          t0 + kTileFrames <= p.n_frames_out && (mk.y <= t0 || mk.x >= t0 + kTileFrames || mk.y <= mk.x);
+        float* dst = p.out + (static_cast<size_t>(clip) * NM + mel_row) * p.n_frames_out + t0 + 4 * mel_q0;
+
+        float mx = -INFINITY, mn_kept = INFINITY, mn_live = INFINITY;
+        MelEdge e;
+        if (!fast) {
+          const int sh = 4 * mel_q0;
+          e.live = frame_window(0, p.n_frames, t0) >> sh;
+          e.kept = frame_window(0, keep, t0) >> sh;
+          e.store = frame_window(0, p.n_frames < p.n_frames_out ? p.n_frames : p.n_frames_out, t0) >> sh;
+          e.tmask = frame_window(mk.x, mk.y, t0) >> sh;
         }
+        const int n_halves = (mel_any_wide<NM>() && mel_wide) ? 2 : 1;   // warp-uniform
+#pragma unroll 1
+        for (int half = 0; half < n_halves; ++half) {
+          cpx acc[4];
+          mel_dispatch<NM, 0>(mel_cls, mel_p, mel_w, acc);
+          if (fast) {
+            mel_post8<true>(acc, sc, of, p.mask_value, dst, e, mx, mn_kept, mn_live);
+          } else {
+            mel_post8<false>(acc, sc, of, p.mask_value, dst, e, mx, mn_kept, mn_live);
+            e.live >>= 8; e.kept >>= 8; e.store >>= 8; e.tmask >>= 8;
+          }
+          mel_p += 8;
+          dst += 8;
+        }
+        if (fast && all_kept) mn_kept = mn_live;
+        mx = warp_max(mx);
+        mn_kept = warp_min(mn_kept);
+        mn_live = warp_min(mn_live);
         if (lane == 0) {
           float* red = reinterpret_cast<float*>(sm_ctl + kCtlRed) + 3 * warp;
           red[0] = mx;
@@ -677,21 +790,22 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     } else {
       // nothing to compute: a pad-only tile (n_frames_out > n_frames) or a silent tile (all-zero PCM: every mel value is
       // the 1e-10 clamp, so only its statistics are recorded here and the fix-up later writes the constant rows)
-      __syncthreads();  // everyone has read the descriptor of THIS tile (matters when it is the CTA's first tile)
-      if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, sm_ctl + kCtlNext, sm_ctl + kCtlMemo);
+      __syncthreads();  // the previous tile's last readers of the other descriptor slot are done
+      if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, NDESC, sm_ctl + kCtlMemo);
       __syncthreads();
-      nxt = sm_ctl[kCtlNext];
-      nxt_clip = sm_ctl[kCtlNext + 1];
-      nxt_t0 = sm_ctl[kCtlNext + 2];
-      nxt_kind = sm_ctl[kCtlNext + 3];
-      prefetched = nxt_kind == kTileInterior;
-      if (prefetched && tid == kTmaThread) {
-        const long long off = (static_cast<long long>(sm_ctl[kCtlNext + 5]) << 32) |
-                              static_cast<unsigned int>(sm_ctl[kCtlNext + 4]);
+      if (NDESC[3] == kTileInterior && tid == kTmaThread) {
+        const long long off = (static_cast<long long>(NDESC[5]) << 32) | static_cast<unsigned int>(NDESC[4]);
         prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
       }
-      if (warp == 0 && lane < n_ring) stat_seen = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
+      if (warp == 0 && lane < sm_ctl[kCtlNRing]) {
+        const uint4 st = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
+        seen_max = st.x;
+        seen_done = st.z;
+      }
       if (lane == 0) {
+        const int clip = d_top.y, t0 = d_top.z, kind = d_top.w;   // (short path: the loop-top read is still in registers)
+        const bool silent = (kind == kTileSilent || kind == kTileSilentRest) && t0 < p.n_frames;
+        const bool silent_head = kind == kTileSilent;   // only the first silent tile of a clip touches the clip statistics
         float* red = reinterpret_cast<float*>(sm_ctl + kCtlRed) + 3 * warp;
         const float lc = silent_log_mel();
         red[0] = (silent && silent_head) ? lc : -INFINITY;                                                 // live frames
@@ -703,16 +817,16 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     // warp 0 looks at the pending ring: a tile whose clip is complete either needs the fix-up (floor binds or it
     // carries pad frames) or is already final and simply leaves the ring; everything else keeps waiting
     if (warp == 0) {
-      const bool pending = lane < n_ring;
+      const bool pending = lane < sm_ctl[kCtlNRing];
       const int mine = pending ? sm_ctl[kCtlRing + lane] : -1;
       const int mine_clip = pending ? sm_ctl[kCtlRingClip + lane] : 0;
       const float mine_min = pending ? __int_as_float(sm_ctl[kCtlRingMin + lane]) : 0.0f;
-      const bool complete = pending && stat_seen.z >= tiles_per_clip_u;
+      const bool complete = pending && seen_done >= tiles_per_clip_u;
       bool ready = false;
       if (complete) {
         const int mt0 = ((mine & kTileIdMask) - mine_clip * p.tiles_per_clip) * kTileFrames;
         ready = (mine & kSilentBit) != 0 ||
-                tile_needs_fixup(mine_min, stat_seen.x, mt0, kept_frames(p.n_valid, mine_clip, p.n_frames), p.n_frames_out);
+                tile_needs_fixup(mine_min, seen_max, mt0, kept_frames(p.n_valid, mine_clip, p.n_frames), p.n_frames_out);
       }
       const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
       const uint32_t wait_mask = __ballot_sync(0xffffffffu, pending && !complete);
@@ -726,8 +840,10 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         sm_ctl[kCtlRingClip + __popc(wait_mask & below)] = mine_clip;
         sm_ctl[kCtlRingMin + __popc(wait_mask & below)] = __float_as_int(mine_min);
       }
-      n_ring = __popc(wait_mask);
-      if (lane == 0) sm_ctl[kCtlReady] = __popc(ready_mask);
+      if (lane == 0) {
+        sm_ctl[kCtlNRing] = __popc(wait_mask);
+        sm_ctl[kCtlReady] = __popc(ready_mask);
+      }
     }
     __syncthreads();  // tile finished: power tile free, ready list and per-warp max/min visible
 
@@ -739,44 +855,49 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       float mx = lane < kWarps ? red[0] : -INFINITY;
       float mn_kept = lane < kWarps ? red[1] : INFINITY;
       float mn_live = lane < kWarps ? red[2] : INFINITY;
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn_kept = fminf(mn_kept, __shfl_xor_sync(0xffffffffu, mn_kept, o));
-        mn_live = fminf(mn_live, __shfl_xor_sync(0xffffffffu, mn_live, o));
-      }
+      mx = warp_max(mx);
+      mn_kept = warp_min(mn_kept);
+      mn_live = warp_min(mn_live);
       if (lane == 0) {
+        const int4 d_pub = DESC4;
+        const int cur = d_pub.x, clip = d_pub.y;
+        const bool silent = (d_pub.w == kTileSilent || d_pub.w == kTileSilentRest) && d_pub.z < p.n_frames;
         ClipStat* cs = p.stats + clip;
         uint32_t dep = 0;
         if (mx > -INFINITY) dep |= atomicMax(&cs->max_enc, enc_ordered(mx));
         if (mn_kept < INFINITY) dep |= atomicMax(&cs->min_inv, ~enc_ordered(mn_kept));
         const int tagged = cur | (silent ? kSilentBit : 0);
+        const int n_ring = sm_ctl[kCtlNRing];
         if (n_ring < kMaxPending) {
           sm_ctl[kCtlRing + n_ring] = tagged;
           sm_ctl[kCtlRingClip + n_ring] = clip;
           sm_ctl[kCtlRingMin + n_ring] = __float_as_int(mn_live);
+          sm_ctl[kCtlNRing] = n_ring + 1;
         } else {
-          p.next[cur] = chain;                       // parked tiles are re-examined (conservatively) in the drain
-          chain = tagged;
+          p.next[cur] = sm_ctl[kCtlChain];           // parked tiles are re-examined (conservatively) in the drain
+          sm_ctl[kCtlChain] = tagged;
         }
-        atomicAdd(&cs->done, 1u + (dep & p.zero));  // (paying this one stage later was measured 2 % slower)
+        // (deferring this count -- to the next tile's gather, or with the two results kept apart -- costs registers the
+        // gather does not have: measured slower every time)
+        atomicAdd(&cs->done, 1u + (dep & p.zero));
       }
-      if (n_ring < kMaxPending) ++n_ring;
       __syncwarp();
     }
     const int n_ready = sm_ctl[kCtlReady];
+#pragma unroll 1
     for (int k = 0; k < n_ready; ++k) fixup_tile<NM>(make_fixup_args(p), sm_ctl[kCtlList + k], sm_ctl[kCtlListClip + k], tid);
-    cur = nxt;
-    clip = nxt_clip;
-    t0 = nxt_t0;
-    kind = nxt_kind;
+    lstate ^= kCtlSlot;   // the next tile becomes current; its slot is rewritten only behind the tile-after-next's first barrier
   }
+#undef DESC
+#undef NDESC
+#undef DESC4
 
   // drain: every tile is claimed by a running CTA now, so waiting on a clip's counter is safe
   for (;;) {
     __syncthreads();  // previous readers of sm_ctl are done
     if (tid == 0) {
       int t = -1, c = 0;
+      int n_ring = sm_ctl[kCtlNRing], chain = sm_ctl[kCtlChain];
       for (;;) {
         float tmin = -INFINITY;  // parked tiles lost their minimum: treat them as needing the fix-up
         if (n_ring > 0) {
@@ -801,6 +922,8 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         if ((t & kSilentBit) != 0 ||
             tile_needs_fixup(tmin, st.x, tt0, kept_frames(p.n_valid, c, p.n_frames), p.n_frames_out)) break;
       }
+      sm_ctl[kCtlNRing] = n_ring;
+      sm_ctl[kCtlChain] = chain;
       sm_ctl[kCtlDrain] = t;
       sm_ctl[kCtlDrainClip] = c;
     }

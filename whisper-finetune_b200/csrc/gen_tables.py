@@ -28,7 +28,6 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-N_GROUPS = 10
 TWIDDLE_ROW = 44  # floats per n2 twiddle row: 20 complex + 4 pad
 
 
@@ -82,7 +81,10 @@ def twiddle_table() -> np.ndarray:
     return t
 
 
-MEL_CLASSES = (2, 6, 10, 14)
+N_THREADS = 160
+N_WARPS = 5
+TILE_FRAMES = 16
+P_STRIDE = 20  # floats per bin row of the power tile [bin][frame]; stride/4 odd -> consecutive bins hit distinct 16-byte bank groups
 
 
 def row_support(bank: np.ndarray):
@@ -95,69 +97,144 @@ def row_support(bank: np.ndarray):
     return supp
 
 
-def row_class(n_taps: int) -> int:
-    for c in MEL_CLASSES:
-        if n_taps <= c:
-            return c
-    raise AssertionError(f"mel row with {n_taps} taps")
+# Which mel rows every warp of a CTA owns: (first_row, n_rows, quads_per_thread).  A thread owns ONE mel row for
+# `quads` groups of 4 consecutive frames of the 16-frame tile; with 2 quads per thread a row is shared by two threads
+# (frames 0-7 and 8-15).  Rows are handed out in bands of similar tap count so a warp's unrolled tap loop has little
+# padding; warp 0 (which also runs the tile scheduler) gets the cheapest band.
+WARP_BANDS = {
+    128: [(0, 32, 4), (32, 32, 4), (64, 32, 4), (96, 32, 2), (96, 32, 2)],
+    80: [(0, 32, 2), (0, 32, 2), (32, 16, 2), (48, 16, 2), (64, 16, 2)],
+}
 
 
-def row_program(bank: np.ndarray, n_groups: int = N_GROUPS):
-    """-> (words: list of uint32 literals, index[g][class] = (first_uint4, n_rows), assignment[g] = rows)."""
-    supp = row_support(bank)
+def _conflict_cost(starts):
+    """LDS.128 phases are quarter-warps (8 lanes): distinct start bins that agree mod 8 collide for every tap."""
+    cost = 0
+    for g in range(0, len(starts), 8):
+        by_res = {}
+        for s in set(starts[g : g + 8]):
+            by_res[s % 8] = by_res.get(s % 8, 0) + 1
+        cost += max(by_res.values()) - 1
+    return cost
+
+
+def _order_rows(rows, start_range):
+    """Choose every row's first tap bin (anywhere its padded window still covers the support) and permute the band's
+    rows over the lanes so that the 8 lanes of a quarter-warp start on distinct 16-byte bank groups.
+
+    -> (lane order, {row: start bin}, residual conflicts)."""
+    import random
+
+    rng = random.Random(1234)
+    n = len(rows)
+    best = None
+    for _restart in range(8):
+        order = list(rows)
+        rng.shuffle(order) if _restart else None
+        start = {m: start_range[m][1] for m in rows}
+        cost = _conflict_cost([start[m] for m in order])
+        for _ in range(6000):
+            if cost == 0:
+                break
+            if rng.random() < 0.5:
+                i, j = rng.randrange(n), rng.randrange(n)
+                if i // 8 == j // 8:
+                    continue
+                order[i], order[j] = order[j], order[i]
+                c = _conflict_cost([start[m] for m in order])
+                if c <= cost:
+                    cost = c
+                else:
+                    order[i], order[j] = order[j], order[i]
+            else:
+                m = order[rng.randrange(n)]
+                lo, hi = start_range[m]
+                if lo == hi:
+                    continue
+                old = start[m]
+                start[m] = rng.randint(lo, hi)
+                c = _conflict_cost([start[x] for x in order])
+                if c <= cost:
+                    cost = c
+                else:
+                    start[m] = old
+        if best is None or cost < best[2]:
+            best = (list(order), dict(start), cost)
+        if cost == 0:
+            break
+    return best
+
+
+def mel_plan(bank: np.ndarray):
+    """Thread-level plan of the mel phase.
+
+    -> dict(weights=[float32...], thread=[(row, start_bin, q0, w_ofs)] * 160, classes=[(taps, quads, w_stride)],
+            warp_class=[class of warp w], conflicts=int)
+    """
     n_mels = bank.shape[0]
-    cost = {m: 10.0 + 2.25 * row_class(supp[m][1] - supp[m][0] + 1) for m in range(n_mels)}
-    load = [0.0] * n_groups
-    rows_of = [[] for _ in range(n_groups)]
-    for m in sorted(range(n_mels), key=lambda r: (-cost[r], r)):  # longest-processing-time first
-        g = min(range(n_groups), key=lambda j: (load[j], j))
-        rows_of[g].append(m)
-        load[g] += cost[m]
-    words, index = [], []
-    for g in range(n_groups):
-        idx_g = []
-        for c in MEL_CLASSES:
-            rows = sorted(m for m in rows_of[g] if row_class(supp[m][1] - supp[m][0] + 1) == c)
-            assert len(words) % 4 == 0
-            idx_g.append((len(words) // 4, len(rows)))
-            for m in rows:
-                k0, k1 = supp[m]
-                if k0 + c - 1 > 199:  # padded taps must stay on bins 1..199 (rewritten every tile, always finite)
-                    k0 = 199 - (c - 1)
-                assert k0 >= 1
-                entry = ["%du" % (4 * k0), "%du" % m]
-                for j in range(c):
-                    k = k0 + j
-                    w = np.float32(bank[m, k]) * np.float32(0.25)
-                    entry.append(fbits(w))
-                assert len(entry) == c + 2
-                words.extend(entry)
-        index.append(idx_g)
-    return words, index, rows_of
+    supp = row_support(bank)
+    bands = WARP_BANDS[n_mels]
+    blocks = {}  # (first, n) -> (w_base, taps, lane order, start bins)
+    weights = []
+    conflicts = 0
+    for first, n, _ in bands:
+        if (first, n) in blocks:
+            continue
+        rows = list(range(first, first + n))
+        taps = max(supp[m][1] - supp[m][0] + 1 for m in rows)
+        # the padded window [start, start + taps) must cover the support and stay on bins 1..199 (rewritten every
+        # tile, always finite); whatever freedom is left goes into avoiding bank conflicts
+        start_range = {m: (max(1, supp[m][1] - taps + 1), min(supp[m][0], 200 - taps)) for m in rows}
+        assert all(lo <= hi for lo, hi in start_range.values())
+        order, start_of, cost = _order_rows(rows, start_range)
+        conflicts += cost
+        base = len(weights)
+        for j in range(taps):
+            for m in order:
+                # 0.25 * bank weight: the packed two-frame FFT yields 4 |X|^2 (exact scaling)
+                weights.append(np.float32(bank[m, start_of[m] + j]) * np.float32(0.25))
+        blocks[(first, n)] = (base, taps, order, start_of)
+    classes, warp_class, thread = [], [], []
+    seen_band = {}
+    for first, n, quads in bands:
+        base, taps, order, start_of = blocks[(first, n)]
+        cls = (taps, quads, n)
+        if cls not in classes:
+            classes.append(cls)
+        warp_class.append(classes.index(cls))
+        if n == 32:
+            # one row per lane; with 2 quads per thread a second warp takes the other half of the tile
+            q0 = 0 if quads == 4 else 2 * seen_band.get((first, n), 0)
+            seen_band[(first, n)] = seen_band.get((first, n), 0) + 1
+            for lane in range(32):
+                m = order[lane]
+                thread.append((m, start_of[m], q0, base + lane))
+        else:
+            assert n == 16 and quads == 2
+            for lane in range(32):
+                m = order[lane % 16]
+                thread.append((m, start_of[m], 2 * (lane // 16), base + lane % 16))
+    assert len(thread) == N_THREADS and len(warp_class) == N_WARPS
+    return dict(weights=weights, thread=thread, classes=classes, warp_class=warp_class, conflicts=conflicts)
 
 
-def simulate(bank: np.ndarray, words, index):
-    """Replay the row program on a random power spectrum and compare with the dense product (float64)."""
+def simulate(bank: np.ndarray, plan):
+    """Replay the plan on a random power tile and compare with the dense product (float64); every cell exactly once."""
     rng = np.random.default_rng(0)
-    P = rng.random(202)
-    vals = []
-    for w in words:
-        w = w.rstrip("u")
-        vals.append(int(w, 16) if w.startswith("0x") else int(w))
-    out = np.full(bank.shape[0], np.nan)
-    for idx_g in index:
-        for c, (first, n) in zip(MEL_CLASSES, idx_g):
-            pos = first * 4
-            for _ in range(n):
-                k0, m = vals[pos] // 4, vals[pos + 1]
-                acc = 0.0
-                for j in range(c):
-                    wgt = struct.unpack("<f", struct.pack("<I", vals[pos + 2 + j]))[0]
-                    acc += wgt * P[k0 + j]
-                assert np.isnan(out[m])
-                out[m] = acc
-                pos += c + 2
-    ref = (bank.astype(np.float64) * 0.25) @ P[:201]
+    P = rng.random((201, TILE_FRAMES))
+    out = np.full((bank.shape[0], TILE_FRAMES), np.nan)
+    w = np.asarray(plan["weights"], dtype=np.float64)
+    for t, (row, start, q0, w_ofs) in enumerate(plan["thread"]):
+        taps, quads, stride = plan["classes"][plan["warp_class"][t // 32]]
+        f0, f1 = 4 * q0, 4 * q0 + 4 * quads
+        assert 1 <= start and start + taps - 1 <= 199 and f1 <= TILE_FRAMES
+        acc = np.zeros(f1 - f0)
+        for j in range(taps):
+            acc += w[w_ofs + j * stride] * P[start + j, f0:f1]
+        assert np.isnan(out[row, f0:f1]).all(), "cell computed twice"
+        out[row, f0:f1] = acc
+    assert not np.isnan(out).any(), "cell never computed"
+    ref = (bank.astype(np.float64) * 0.25) @ P
     assert np.allclose(out, ref, rtol=1e-12, atol=0), np.abs(out - ref).max()
 
 
@@ -183,22 +260,33 @@ def generate() -> str:
         lines.append("  " + ", ".join(flit(v) for v in tt[r : r + 8]) + ", \\")
     lines.append("}")
     lines.append("")
-    lines.append(f"#define WFT_MEL_GROUPS {N_GROUPS}")
-    lines.append(f"#define WFT_MEL_CLASSES {len(MEL_CLASSES)}")
+    lines.append(f"#define WFT_MEL_P_STRIDE {P_STRIDE}")
+    lines.append("#define WFT_MEL_MAX_CLASSES 4")
     for n_mels in (80, 128):
         bank = mb.slaney_mel_bank(n_mels)
         assert not bank[:, 0].any() and not bank[:, 200].any()
-        words, index, _ = row_program(bank)
-        simulate(bank, words, index)
-        lines.append(f"#define WFT_MEL{n_mels}_PROG_VEC {len(words) // 4}")
-        lines.append(f"#define WFT_MEL{n_mels}_PROG_INIT {{ \\")
-        for r in range(0, len(words), 4):
-            lines.append("  {" + ", ".join(words[r : r + 4]) + "}, \\")
+        plan = mel_plan(bank)
+        simulate(bank, plan)
+        w = plan["weights"]
+        pad = lambda xs: list(xs) + [0] * (4 - len(xs))
+        assert len(plan["classes"]) <= 4 and len(w) < 1024
+        lines.append(f"// n_mels={n_mels}: classes (taps, quads/thread, weight stride) = {plan['classes']}, "
+                     f"residual LDS.128 conflicts = {plan['conflicts']}")
+        lines.append(f"#define WFT_MEL{n_mels}_NCLASS {len(plan['classes'])}")
+        lines.append(f"#define WFT_MEL{n_mels}_CLASS_T {{" + ", ".join(str(v) for v in pad([c[0] for c in plan["classes"]])) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_CLASS_NQ {{" + ", ".join(str(v) for v in pad([c[1] for c in plan["classes"]])) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_CLASS_WS {{" + ", ".join(str(v) for v in pad([c[2] for c in plan["classes"]])) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_WARP_CLASS {{" + ", ".join(str(v) for v in plan["warp_class"]) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_W_LEN {len(w)}")
+        lines.append(f"#define WFT_MEL{n_mels}_W_INIT {{ \\")
+        for r in range(0, len(w), 8):
+            lines.append("  " + ", ".join(flit(v) for v in w[r : r + 8]) + ", \\")
         lines.append("}")
-        lines.append(f"// per warp: (first_uint4, n_rows) for tap classes {MEL_CLASSES}, n_mels={n_mels}")
-        lines.append(f"#define WFT_MEL{n_mels}_INDEX_INIT {{ \\")
-        for idx_g in index:
-            lines.append("  {" + ", ".join("{%d, %d}" % fc for fc in idx_g) + "}, \\")
+        lines.append(f"// per thread: row | start_bin << 8 | first_quad << 16 | weight_offset << 18")
+        lines.append(f"#define WFT_MEL{n_mels}_THREAD_INIT {{ \\")
+        words = ["0x%08xu" % (row | (start << 8) | (q0 << 16) | (w_ofs << 18)) for row, start, q0, w_ofs in plan["thread"]]
+        for r in range(0, len(words), 8):
+            lines.append("  " + ", ".join(words[r : r + 8]) + ", \\")
         lines.append("}")
         lines.append("")
     return "\n".join(lines) + "\n"
