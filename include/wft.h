@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WFT_ABI_VERSION 2
+#define WFT_ABI_VERSION 3
 
 /* Front-end constants (whisper.audio: SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES;
  * imported by the reference at data_loader.py:13 and data/utils.py:10). */
@@ -125,6 +125,15 @@ int wft_time_warp_f32(const float* in, float* out, int32_t batch, int32_t n_rows
  * data/utils.py:107-111), Philox keyed like wft_specaug_draw; (T/2, 0) = identity when the p gate rejects the clip. */
 int wft_time_warp_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t time_warp_w, float p,
                        int32_t* warp_params_out, void* stream);
+
+/* Deep SpecAugment on encoder activations (model/model_utils.py:382-437: permute -> TimeMasking -> FrequencyMasking ->
+ * permute on every hooked layer-norm output), without the permutes: x is [batch, seq, dim] contiguous with 16-bit (fp16 /
+ * bf16) or 32-bit elements, out[b, s, d] = (t0 <= s < t1 || f0 <= d < f1) ? fill : x[b, s, d].  ONE mask for the whole batch,
+ * like torchaudio's mask_along_axis on a 3-D input; the intervals are host integers because the reference draws them on
+ * the host (torch.rand).  fill_bits is the fill value's bit pattern in the element type (0 for the reference's 0.0).
+ * in == out is allowed.  The backward of this op is the same call on the gradient with fill 0. */
+int wft_mask_bsd(const void* in, void* out, int32_t elem_bytes, int64_t batch, int32_t seq, int32_t dim, int32_t t0,
+                 int32_t t1, int32_t f0, int32_t f1, uint32_t fill_bits, void* stream);
 
 /* Introspection used by bench.py / tests: number of kernel launches issued by this library on the calling
  * thread since the last reset, and the persistent grid the fused kernel would use on the current device. */

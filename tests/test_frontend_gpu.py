@@ -377,3 +377,185 @@ def test_front_end_with_time_warp_follows_reference_order(wft, cuda):
         ref = OS.apply_masks(OT.time_warp(O.log_mel_spectrogram(x[b], 80), int(warps[b, 0]), int(warps[b, 1])), *masks[b])
         assert (got[b] - ref).abs().max() <= 1e-3
         assert torch.equal(got[b] == 0, ref == 0)
+
+
+# ---- deep SpecAugment on activations (model/model_utils.py:382-437) ----------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(4, 1500, 1280), (2, 75, 384), (3, 33, 100), (1, 7, 5)])
+def test_mask_activations_matches_oracle_bit_exact(wft, cuda, dtype, shape):
+    from oracle.deep_specaug import deep_spec_augment
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(shape, generator=g).to(dtype)
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        want, t, f = deep_spec_augment(x, 100, 43)
+        torch.manual_seed(seed)
+        t2, f2 = wft.draw_deep_spans(shape[1], shape[2], 100, 43)
+        assert (t2, f2) == (t, f)
+        got = wft.mask_activations(x.to(cuda), t2, f2)
+        assert got.dtype == dtype and torch.equal(got.cpu(), want)
+
+
+@pytest.mark.gpu
+def test_mask_activations_backward_is_the_same_mask(wft, cuda):
+    x = torch.randn(2, 40, 64, device=cuda, dtype=torch.bfloat16, requires_grad=True)
+    y = wft.mask_activations(x, (5, 17), (60, 64))
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    want = gy.clone()
+    want[:, 5:17, :] = 0
+    want[:, :, 60:64] = 0
+    assert torch.equal(x.grad, want)
+    # unaligned views take the scalar path and give the same answer
+    base = torch.randn(2, 40, 65, device=cuda)
+    v = base[:, :, 1:]
+    out = wft.mask_activations(v, (0, 3), (10, 20))
+    ref = v.clone()
+    ref[:, 0:3, :] = 0
+    ref[:, :, 10:20] = 0
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.gpu
+def test_deep_spec_augment_hooks_match_reference_hook(wft, cuda):
+    """Same seed -> the hooked toy encoder produces what the reference hook body (torchaudio masks) produces."""
+    import torch.nn as nn
+    import torchaudio.transforms as T
+
+    class Block(nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.attn_ln = nn.LayerNorm(d)
+
+        def forward(self, x):
+            return x + self.attn_ln(x)
+
+    class Enc(nn.Module):
+        def __init__(self, d, n):
+            super().__init__()
+            self.blocks = nn.ModuleList([Block(d) for _ in range(n)])
+
+        def forward(self, x):
+            for b in self.blocks:
+                x = b(x)
+            return x
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = Enc(64, 3)
+
+    torch.manual_seed(0)
+    ours, ref = Model().to(cuda).train(), Model().to(cuda).train()
+    ref.load_state_dict(ours.state_dict())
+    wft.register_deep_spec_augment_hooks(ours, 20, 9, p=1.0)
+    tm, fm = T.TimeMasking(time_mask_param=20), T.FrequencyMasking(freq_mask_param=9)
+
+    def ref_hook(module, inp, out):   # body of the reference's _norm_hook (model_utils.py:412-421)
+        if module.training:
+            return fm(tm(out.permute(0, 2, 1))).permute(0, 2, 1)
+        return out
+
+    for i in range(2):  # the last block is skipped, like the reference
+        ref.encoder.blocks[i].attn_ln.register_forward_hook(ref_hook)
+    x = torch.randn(2, 50, 64, device=cuda)
+    torch.manual_seed(11)
+    a = ours.encoder(x)
+    torch.manual_seed(11)
+    b = ref.encoder(x)
+    assert torch.equal(a, b)
+    ours.eval()
+    assert torch.equal(ours.encoder(x), ref.eval().encoder(x))
+    with pytest.raises(ValueError):
+        wft.register_deep_spec_augment_hooks(ours, 20, 9, p=1.5)
+
+
+# ---- loader integration (SURVEY 8f row 4): PCM records -> pcm_collate_fn -> DeviceFrontEndLoader ---------------------------
+class _StandInDataset:
+    """The attribute surface ``deferred_calculate_mel`` uses of the reference's AudioDataset (data_loader.py:60-150)."""
+
+    def __init__(self, n_mels, p, extremes=None):
+        self.aud_augment = None
+        self.n_mels = n_mels
+        self.num_frames_per_second = 3000 / 30
+        self.spec_augment = p > 0
+        self.spec_augment_p = p
+        self.extreme_freq_masking = extremes
+
+    def _should_apply_spec_augment(self):  # data_loader.py:294-301
+        if not self.spec_augment:
+            return False
+        if self.spec_augment_p >= 1.0:
+            return True
+        if self.spec_augment_p <= 0.0:
+            return False
+        return torch.rand(1).item() < self.spec_augment_p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pcm_dtype", [torch.float32, torch.int16])
+def test_device_front_end_loader_matches_oracle(wft, cuda, pcm_dtype):
+    from types import SimpleNamespace
+
+    from whisper_finetune_b200 import loader as L
+
+    rng = np.random.default_rng(7)
+    B, n_mels = 6, 80
+    ds = _StandInDataset(n_mels, 0.5, extremes=SimpleNamespace(low_freq_range=10, high_freq_range=6))
+    L._PCM_DTYPE["dtype"] = pcm_dtype
+    clips, starts, items = [], [], []
+    torch.manual_seed(5)
+    for b in range(B):
+        n = int(rng.integers(16000, 480001)) if b else 480000
+        a = S.make("int16" if b % 2 else "white", n=n, seed=300 + b)
+        a = (a.float() / 32768.0 if a.dtype == torch.int16 else a).numpy()
+        if pcm_dtype == torch.int16:
+            a = np.round(a * 32768.0).clip(-32768, 32767).astype(np.float32) / 32768.0   # what a 16-bit source decodes to
+        start = None if b % 3 else float(rng.uniform(0.5, 29.0))
+        clips.append(a)
+        starts.append(start)
+        rec = wft.deferred_calculate_mel(ds, np.pad(a, (0, 480000 - n)), start, True)
+        items.append((rec, torch.arange(3 + b), torch.arange(2 + b)))
+    L._PCM_DTYPE["dtype"] = torch.float32
+    batch, y_in, y_out = wft.pcm_collate_fn(items)
+    assert batch.pcm.dtype == pcm_dtype and tuple(batch.pcm.shape) == (B, 480000)
+    assert y_in.shape == (B, 3 + B - 1) and y_out[0, -1] == -100
+    assert batch.lengths.tolist() == [int(np.flatnonzero(c)[-1]) + 1 for c in clips]
+    want_nv = [-1 if s is None else int(s * 100) for s in starts]
+    assert batch.n_valid_frames.tolist() == want_nv
+    assert 0 < int(batch.augment.sum()) < B, "p = 0.5 with this seed should gate some clips on and some off"
+
+    fe = wft.FrontEnd(n_mels=n_mels, spec_augment=True,
+                      spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "p": 1.0}, seed=9)
+    dl = wft.DeviceFrontEndLoader([(batch, y_in, y_out)], fe, clip_offset=40)
+    out = list(dl)
+    assert len(out) == 1 and out[0][1] is y_in and out[0][2] is y_out
+    x = out[0][0]
+    assert x.is_cuda and tuple(x.shape) == (B, n_mels, 3000) and dl.clip_offset == 40 + B
+    masks = OS.draw_mask_params(9, 40, B, n_mels, 3000, 100, 27, 1.0)
+    x = x.cpu()
+    for b in range(B):
+        nv = None if want_nv[b] < 0 else want_nv[b]
+        ref = OP.calculate_mel(torch.from_numpy(clips[b]), n_mels, nv, masks[b] if batch.augment[b] else None)
+        lo, hi = batch.extremes[b].tolist()
+        ref[:lo] = 0
+        if hi:
+            ref[n_mels - hi:] = 0
+        keep = 3000 if nv is None else nv
+        _check(x[b, :, :keep], ref[:, :keep], f"loader clip {b}")
+        assert (x[b] - ref).abs().max() <= S.MAX_ABS
+        assert torch.equal(x[b] == 0, ref == 0), "masked / extreme cells are exactly 0.0, nothing else is"
+
+
+@pytest.mark.gpu
+def test_pcm_record_errors(wft, cuda):
+    with pytest.raises(RuntimeError):
+        wft.encode_pcm_record(np.ones(100, np.float32), n_valid_frames=0)       # empty spectrogram: torch.min raises upstream
+    with pytest.raises(ValueError):
+        wft.encode_pcm_record(np.ones(480001, np.float32))
+    bad = wft.encode_pcm_record(np.ones(100, np.float32))
+    bad[480000] = 1
+    with pytest.raises(ValueError):
+        wft.decode_pcm_records([bad])

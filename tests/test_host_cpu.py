@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol(wft):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/wft.h but not exported"
     assert sorted(wft._lib.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert wft._lib.load().wft_abi_version() == wft._lib.ABI_VERSION == 2
+    assert wft._lib.load().wft_abi_version() == wft._lib.ABI_VERSION == 3
 
 
 def test_host_validation_without_gpu(wft):
@@ -194,3 +194,90 @@ def test_bench_reference_arm_prints_contract_line():
                 "cpu_baseline", "e2e"):
         assert key in line
     assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_pcm_record_round_trip(wft):
+    """encode_pcm_record / decode_pcm_records: samples, length, cut, gate and extremes survive, for both PCM types."""
+    rng = np.random.default_rng(0)
+    a = (rng.standard_normal(12345) * 0.1).astype(np.float32)
+    a[-20:] = 0                                           # trailing zeros are padding
+    for dt in (torch.float32, torch.int16):
+        recs = [wft.encode_pcm_record(a, 1234, True, dt, (3, 4)), wft.encode_pcm_record(np.zeros(7, np.float32), None, False, dt)]
+        assert all(r.dtype == dt and r.shape == (480008,) for r in recs)
+        b = wft.decode_pcm_records(recs)
+        assert b.pcm.dtype == dt and tuple(b.pcm.shape) == (2, 480000)
+        assert b.lengths.tolist() == [12325, 0] and b.n_valid_frames.tolist() == [1234, -1]
+        assert b.augment.tolist() == [1, 0] and b.extremes.tolist() == [[3, 4], [0, 0]]
+        if dt == torch.float32:
+            assert np.array_equal(b.pcm[0, :12345].numpy(), a)
+        else:
+            assert np.array_equal(b.pcm[0, :12345].numpy(), np.rint(a.astype(np.float64) * 32768).astype(np.int16))
+        assert not b.pcm[0, 12345:].any()
+    assert wft.encode_pcm_record(a, 5000)[480001] == 3001    # a cut beyond the clip keeps every frame
+
+
+_LOADER_DRIVER = r"""
+import sys, types
+root, ref = sys.argv[1], sys.argv[2]
+sys.path[:0] = [root, ref + "/src"]
+import numpy as np, torch
+import whisper_finetune_b200 as wft
+
+w = types.ModuleType("whisper"); wa = types.ModuleType("whisper.audio"); wt = types.ModuleType("whisper.tokenizer")
+wa.CHUNK_LENGTH, wa.HOP_LENGTH, wa.N_FFT, wa.N_FRAMES, wa.N_SAMPLES = 30, 160, 400, 3000, 480000
+wa.log_mel_spectrogram = lambda *a, **k: (_ for _ in ()).throw(AssertionError("features must not be computed on the host"))
+wt.LANGUAGES, wt.TO_LANGUAGE_CODE, wt.Tokenizer = {"de": "german"}, {"german": "de"}, object
+w.audio, w.tokenizer = wa, wt
+sys.modules.update({"whisper": w, "whisper.audio": wa, "whisper.tokenizer": wt})
+class _Any(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"): raise AttributeError(name)
+        return type(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, x, **k: x})
+sys.modules["audiomentations"] = _Any("audiomentations")
+from whisper_finetune.data import data_loader as dl
+
+ref_collate = dl.collate_fn
+ref_gate = dl.AudioDataset._should_apply_spec_augment
+wft.install_loader(dl, pcm_dtype=torch.int16)
+assert dl.collate_fn is wft.pcm_collate_fn and dl.AudioDataset._calculate_mel is wft.deferred_calculate_mel
+
+ds = dl.AudioDataset.__new__(dl.AudioDataset)          # the way the reference's own tests build one
+ds.aud_augment, ds.n_mels, ds.device = None, 128, None
+ds.num_frames_per_second = dl.N_FRAMES / dl.CHUNK_LENGTH
+ds.spec_augment, ds.spec_augment_p, ds.extreme_freq_masking = True, 0.5, dl.ExtremesFrequencyMasking(10, 10)
+audio = np.zeros(480000, np.float32); audio[:32000] = 0.25
+items = []
+for seed in range(8):
+    torch.manual_seed(seed)
+    want_gate = ref_gate(ds)                            # the reference's draw under this seed ...
+    r = torch.rand(1).item()                            # ... followed by the extremes ratio (data/utils.py:173)
+    torch.manual_seed(seed)
+    rec = ds._calculate_mel(audio, 12.34 if seed % 2 else None, True)
+    b = wft.decode_pcm_records([rec])
+    assert b.pcm.dtype == torch.int16 and int(b.pcm[0, 0]) == 8192 and b.lengths.tolist() == [32000]
+    assert b.augment.tolist() == [int(want_gate)], seed
+    assert b.n_valid_frames.tolist() == [1234 if seed % 2 else -1]
+    assert b.extremes.tolist() == [[int(round(r * 10)), int(round(r * 10))]]
+    items.append((rec, torch.arange(4 + seed), torch.full((3 + seed,), 7)))
+batch, y_in, y_out = dl.collate_fn(items)
+_, ry_in, ry_out = ref_collate([(torch.zeros(1, 3000), i, o) for _, i, o in items])
+assert torch.equal(y_in, ry_in) and torch.equal(y_out, ry_out) and len(batch) == 8
+try:
+    ds._calculate_mel(audio, 0.001, True)               # cut at frame 0: the reference dies in pad_or_trim (torch.min of nothing)
+    raise SystemExit("expected RuntimeError")
+except RuntimeError:
+    pass
+print("LOADER-OK")
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present (GPU box)")
+def test_install_loader_rewires_reference_dataset(tmp_path):
+    """install_loader on the REAL reference module: gate / cut / extremes decisions equal the reference's, no host features."""
+    import subprocess
+
+    script = tmp_path / "drive.py"
+    script.write_text(_LOADER_DRIVER)
+    res = subprocess.run([sys.executable, str(script), ROOT, "/root/reference"], capture_output=True, text=True, timeout=600,
+                         cwd=str(tmp_path))
+    assert res.returncode == 0 and "LOADER-OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

@@ -181,3 +181,19 @@ def test_timewarp_and_extremes_against_reference_goldens():
         assert np.array_equal((ext == 0).all(dim=1).numpy(), z[f"ext_zero_rows{k}"])
     ident = OT.time_warp(mel, 1500, 0)  # warp_d = 0: the spline is the identity map
     assert (ident - mel).abs().max() <= 2e-4
+
+
+def test_deep_spec_augment_oracle_matches_torchaudio():
+    """oracle.deep_specaug == the reference hook body (permute -> torchaudio masks -> permute), same seed."""
+    import torchaudio.transforms as T
+
+    from oracle.deep_specaug import deep_spec_augment
+
+    x = torch.randn(3, 150, 64)
+    for seed, (tp, fp) in enumerate([(100, 27), (40, 10), (1, 1), (0, 43), (400, 27), (400, 200), (149, 63)]):
+        torch.manual_seed(seed)
+        ref = T.FrequencyMasking(freq_mask_param=fp)(T.TimeMasking(time_mask_param=tp)(x.permute(0, 2, 1))).permute(0, 2, 1)
+        torch.manual_seed(seed)
+        got, t, f = deep_spec_augment(x, tp, fp)
+        assert torch.equal(got, ref.contiguous()), (seed, tp, fp, t, f)
+        assert t[1] - t[0] <= max(tp - 1, 0) and f[1] - f[0] <= max(fp - 1, 0)

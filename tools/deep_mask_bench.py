@@ -1,0 +1,67 @@
+"""Bandwidth of wft_mask_bsd (deep SpecAugment on activations) on large-v3 encoder shapes -> JSON on stdout.
+
+    python tools/deep_mask_bench.py            # [64, 1500, 1280] bf16 / fp16 / fp32, T=100, F=43 spans
+"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import whisper_finetune_b200 as wft  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    peak = 6551.7
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_copy_gbps"]
+    except Exception:
+        pass
+    res = []
+    B, S, D = 64, 1500, 1280
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for dtype in (torch.bfloat16, torch.float16, torch.float32):
+        x = torch.randn(B, S, D, device=dev).to(dtype)
+        t, f = (700, 790), (600, 640)
+        for _ in range(3):
+            y = wft.mask_activations(x, t, f)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = wft.mask_activations(x, t, f)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts.sort()
+        med = ts[len(ts) // 2]
+        eb = x.element_size()
+        kept = (S - (t[1] - t[0])) * (D - (f[1] - f[0]))
+        algo = B * (kept + S * D) * eb          # unmasked cells read once, every cell written once
+        # what the reference does per hooked layer: 2 masked_fill passes (read + write each) on the permuted view
+        ref = torch.empty_like(x)
+        import torchaudio.transforms as T
+        tm, fm = T.TimeMasking(time_mask_param=100), T.FrequencyMasking(freq_mask_param=43)
+        for _ in range(2):
+            r = fm(tm(x.permute(0, 2, 1))).permute(0, 2, 1)
+        rs = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fm(tm(x.permute(0, 2, 1))).permute(0, 2, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            rs.append(e0.elapsed_time(e1) * 1e-3)
+        rs.sort()
+        res.append({"dtype": str(dtype).replace("torch.", ""), "shape": [B, S, D], "ms": med * 1e3,
+                    "algorithmic_GB_per_s": algo / med / 1e9, "frac_of_measured_hbm_peak": algo / med / 1e9 / peak,
+                    "torchaudio_permute_path_ms": rs[len(rs) // 2] * 1e3})
+    print(json.dumps({"kernel": "wft_mask_bsd", "peak_GB_per_s": peak, "l2_flushed_between_runs": True, "results": res}, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -6,7 +6,7 @@ compute call raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwft_b200.so")
@@ -15,7 +15,7 @@ WFT_PCM_F32 = 0
 WFT_PCM_I16 = 1
 WFT_ERR_INVALID = -1
 WFT_ERR_CUDA = -2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class FrontendArgs(Structure):
@@ -52,6 +52,8 @@ SIGNATURES = {
                                  c_void_p, c_void_p]),
     "wft_time_warp_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "wft_time_warp_draw": (c_int, [c_uint64, c_uint64, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
+    "wft_mask_bsd": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                             c_uint32, c_void_p]),
     "wft_launch_count": (c_int64, [c_int]),
     "wft_frontend_grid": (c_int, [c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
 }

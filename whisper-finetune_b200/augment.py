@@ -20,7 +20,10 @@ from .audio import _stream_ptr, resolve_device
 
 
 def _interval_from_global_rng(mask_param: int, size: int) -> Tuple[int, int]:
-    """torchaudio's draw (functional.py: value = rand*param; min_value = rand*(size - value)), on the host RNG."""
+    """torchaudio's draw (functional.py: value = rand*param; min_value = rand*(size - value)), on the host RNG.
+    ``mask_param < 1`` masks nothing and consumes no random numbers, like torchaudio."""
+    if mask_param < 1:
+        return 0, 0
     value = torch.rand(1) * mask_param
     min_value = torch.rand(1) * (size - value)
     start = int(min_value.long())

@@ -125,6 +125,67 @@ __global__ void specaug_apply_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
+// Deep SpecAugment on encoder activations (model/model_utils.py:382-437): x is [batch, seq, dim], one (time, feature) mask
+// for the whole batch.  Works on 16-byte vectors of 16- or 32-bit elements; masked rows are written without being read,
+// a vector that straddles the feature mask's edge is patched element by element.  blockDim = (vectors, rows).
+template <typename ElemT>
+__device__ __forceinline__ uint4 patch_vector(uint4 v, int c0, int f0, int f1, ElemT fill) {
+  constexpr int kPer = 16 / sizeof(ElemT);
+  ElemT e[kPer];
+  memcpy(e, &v, 16);
+#pragma unroll
+  for (int i = 0; i < kPer; ++i)
+    if (c0 + i >= f0 && c0 + i < f1) e[i] = fill;
+  memcpy(&v, e, 16);
+  return v;
+}
+
+template <typename ElemT>
+__global__ void mask_bsd_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n_rows, int32_t seq,
+                                int32_t vec_per_row, int32_t t0, int32_t t1, int32_t f0, int32_t f1, uint32_t fill_bits) {
+  constexpr int kPer = 16 / sizeof(ElemT);
+  ElemT fill;
+  memcpy(&fill, &fill_bits, sizeof(ElemT));
+  const uint32_t f32 = sizeof(ElemT) == 2 ? (fill_bits & 0xffffu) * 0x10001u : fill_bits;
+  const uint4 fill4 = make_uint4(f32, f32, f32, f32);
+  const bool in_place = in == out;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.y + threadIdx.y; row < n_rows;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.y) {
+    const int s = static_cast<int>(row % seq);
+    const bool row_masked = s >= t0 && s < t1;
+    const uint4* src = in + row * vec_per_row;
+    uint4* dst = out + row * vec_per_row;
+    for (int v = threadIdx.x; v < vec_per_row; v += blockDim.x) {
+      const int c0 = v * kPer;
+      const bool all_in = row_masked || (c0 >= f0 && c0 + kPer <= f1);
+      const bool none_in = !row_masked && (c0 + kPer <= f0 || c0 >= f1);
+      if (all_in) {
+        dst[v] = fill4;
+      } else if (none_in) {
+        if (!in_place) dst[v] = __ldcs(src + v);
+      } else {
+        dst[v] = patch_vector<ElemT>(__ldcs(src + v), c0, f0, f1, fill);
+      }
+    }
+  }
+}
+
+// any shape / alignment: one element per thread
+template <typename ElemT>
+__global__ void mask_bsd_scalar_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, int64_t n_elems, int32_t seq,
+                                       int32_t dim, int32_t t0, int32_t t1, int32_t f0, int32_t f1, uint32_t fill_bits) {
+  ElemT fill;
+  memcpy(&fill, &fill_bits, sizeof(ElemT));
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n_elems;
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = k / dim;
+    const int d = static_cast<int>(k - row * dim);
+    const int s = static_cast<int>(row % seq);
+    if ((s >= t0 && s < t1) || (d >= f0 && d < f1)) out[k] = fill;
+    else if (in != out) out[k] = in[k];
+  }
+}
+
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t (&o)[4]) {
 #pragma unroll
@@ -388,6 +449,48 @@ int wft_specaug_apply_f32(const float* in, float* out, int32_t batch, int32_t n_
   if (batch > 65535) return fail(WFT_ERR_INVALID, "batch too large for one launch (max 65535)");
   dim3 grid(grid_1d(static_cast<int64_t>(n_rows) * n_frames, 256), batch);
   specaug_apply_kernel<<<grid, 256, 0, stream>>>(in, out, n_rows, n_frames, mask_params, mask_value);
+  ++g_launches;
+  WFT_CUDA(cudaGetLastError());
+  return WFT_OK;
+}
+
+int wft_mask_bsd(const void* in, void* out, int32_t elem_bytes, int64_t batch, int32_t seq, int32_t dim, int32_t t0,
+                 int32_t t1, int32_t f0, int32_t f1, uint32_t fill_bits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (elem_bytes != 2 && elem_bytes != 4) return fail(WFT_ERR_INVALID, "elem_bytes must be 2 (fp16 / bf16) or 4 (fp32)");
+  if (batch < 0 || seq < 0 || dim < 0) return fail(WFT_ERR_INVALID, "negative extent");
+  const int64_t n_rows = batch * seq;
+  if (n_rows == 0 || dim == 0) return WFT_OK;
+  if (in == nullptr || out == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
+  const int64_t row_bytes = static_cast<int64_t>(dim) * elem_bytes;
+  const bool vec_ok = row_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  int dev = 0, sms = 148;
+  WFT_CUDA(cudaGetDevice(&dev));
+  WFT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (vec_ok) {
+    const int vec_per_row = static_cast<int>(row_bytes / 16);
+    int bx = (vec_per_row + 31) / 32 * 32;
+    if (bx > 256) bx = 256;
+    const int by = 256 / bx > 0 ? 256 / bx : 1;
+    int64_t ctas = (n_rows + by - 1) / by;
+    if (ctas > static_cast<int64_t>(sms) * 8) ctas = static_cast<int64_t>(sms) * 8;
+    const dim3 block(bx, by), grid(static_cast<unsigned>(ctas));
+    if (elem_bytes == 2)
+      mask_bsd_kernel<uint16_t><<<grid, block, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), n_rows, seq,
+                                                           vec_per_row, t0, t1, f0, f1, fill_bits);
+    else
+      mask_bsd_kernel<uint32_t><<<grid, block, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), n_rows, seq,
+                                                           vec_per_row, t0, t1, f0, f1, fill_bits);
+  } else {
+    const int64_t n = n_rows * dim;
+    const int grid = grid_1d(n, 256);
+    if (elem_bytes == 2)
+      mask_bsd_scalar_kernel<uint16_t><<<grid, 256, 0, stream>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), n,
+                                                                seq, dim, t0, t1, f0, f1, fill_bits);
+    else
+      mask_bsd_scalar_kernel<uint32_t><<<grid, 256, 0, stream>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), n,
+                                                                seq, dim, t0, t1, f0, f1, fill_bits);
+  }
   ++g_launches;
   WFT_CUDA(cudaGetLastError());
   return WFT_OK;

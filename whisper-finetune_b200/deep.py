@@ -1,0 +1,102 @@
+"""Deep SpecAugment on encoder activations, on the GPU and without the permutes.
+
+Mirror of ``register_deep_spec_augment_hooks`` (``src/whisper_finetune/model/model_utils.py:382-437``): a forward hook
+on ``encoder.blocks[i].attn_ln`` that, while training, masks a time span and a feature span of the normalised
+activations ``[batch, seq, dim]``.  The reference does ``permute(0, 2, 1)`` -> ``T.TimeMasking`` ->
+``T.FrequencyMasking`` -> ``permute(0, 2, 1)``: two full ``masked_fill`` copies plus a non-contiguous result on every
+hooked layer.  Here it is ONE pass of ``wft_mask_bsd`` (include/wft.h) over the tensor in its own layout, in
+fp32 / fp16 / bf16, and the backward is the same pass over the gradient.
+
+The two intervals are drawn exactly like torchaudio does for a 3-D input (one mask for the whole batch, two
+``torch.rand(1)`` per mask from the global CPU generator, float32 interval arithmetic), time first, then frequency,
+so a seeded reference run and a seeded run of these hooks mask the same cells.
+"""
+from typing import Iterable, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .audio import _stream_ptr
+from .augment import _interval_from_global_rng
+
+_ELEM_BYTES = {torch.float32: 4, torch.float16: 2, torch.bfloat16: 2}
+
+
+def _mask_bsd(x: torch.Tensor, t0: int, t1: int, f0: int, f1: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    if not x.is_cuda:
+        raise RuntimeError("whisper-finetune_b200 computes on CUDA only; the activations must be a CUDA tensor")
+    if x.dtype not in _ELEM_BYTES:
+        raise TypeError(f"activations must be float32, float16 or bfloat16, got {x.dtype}")
+    if x.dim() != 3:
+        raise ValueError(f"activations must be [batch, seq, dim], got shape {tuple(x.shape)}")
+    x = x.contiguous()
+    B, S, D = x.shape
+    res = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _lib.check(lib.wft_mask_bsd(x.data_ptr(), res.data_ptr(), _ELEM_BYTES[x.dtype], B, S, D, int(t0), int(t1),
+                                    int(f0), int(f1), 0, _stream_ptr(x.device)))
+    return res
+
+
+class _MaskActivations(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, t0, t1, f0, f1):
+        ctx.spans = (t0, t1, f0, f1)
+        return _mask_bsd(x, t0, t1, f0, f1)
+
+    @staticmethod
+    def backward(ctx, grad):
+        # y = x * m with m in {0, 1}: the gradient is masked by the same spans
+        return _mask_bsd(grad, *ctx.spans), None, None, None, None
+
+
+def mask_activations(x: torch.Tensor, time_span: Tuple[int, int], feature_span: Tuple[int, int]) -> torch.Tensor:
+    """``x[b, s, d] := 0`` for ``s`` in ``time_span`` or ``d`` in ``feature_span``; ``x`` is ``[batch, seq, dim]``
+    (CUDA, fp32 / fp16 / bf16).  Returns a new tensor; differentiable."""
+    return _MaskActivations.apply(x, int(time_span[0]), int(time_span[1]), int(feature_span[0]), int(feature_span[1]))
+
+
+def draw_deep_spans(seq: int, dim: int, time_mask_param: int, freq_mask_param: int) -> Tuple[Tuple[int, int], Tuple[int, int]]:
+    """The reference's draws for one hooked layer: TimeMasking on the ``seq`` axis first, FrequencyMasking on ``dim``."""
+    t = _interval_from_global_rng(time_mask_param, seq)
+    f = _interval_from_global_rng(freq_mask_param, dim)
+    return t, f
+
+
+def register_deep_spec_augment_hooks(model, time_mask_param: int, freq_mask_param: int, p: float = 1.0,
+                                     layer_indices: Optional[Iterable[int]] = None) -> None:
+    """Same arguments, gate and layer selection as the reference function of this name."""
+    p = float(p)
+    if not 0.0 <= p <= 1.0:
+        raise ValueError(f"deep_spec_augment p must be between 0 and 1, got {p}")
+    state = {"apply": False}
+
+    def _should_apply() -> bool:
+        if p >= 1.0:
+            return True
+        if p <= 0.0:
+            return False
+        return torch.rand(1).item() < p
+
+    def _encoder_pre_hook(module, input):
+        # decided once per encoder forward so that checkpoint recomputation sees the same on/off state
+        state["apply"] = _should_apply()
+
+    def _norm_hook(module, input, output):
+        if module.training and state["apply"]:
+            _, seq, dim = output.shape
+            t, f = draw_deep_spans(seq, dim, time_mask_param, freq_mask_param)
+            return mask_activations(output, t, f)
+        return output
+
+    n_blocks = len(model.encoder.blocks)
+    if layer_indices is None:
+        layer_indices = range(n_blocks - 1)   # the last block is left alone so the model can recover
+    for idx in layer_indices:
+        if idx >= n_blocks:
+            raise ValueError(f"Layer index {idx} out of range")
+        if idx == n_blocks - 1:
+            continue
+        model.encoder.blocks[idx].attn_ln.register_forward_hook(_norm_hook)
+    model.encoder.register_forward_pre_hook(_encoder_pre_hook)

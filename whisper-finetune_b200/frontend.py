@@ -47,8 +47,12 @@ class FrontEnd:
             self.time_warp_w = 0
 
     def __call__(self, pcm: torch.Tensor, lengths=None, n_valid_frames=None, clip_offset: int = 0,
-                 mask_params: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """``pcm`` ``[B, N<=480000]`` float32 / int16 (host or device) -> ``[B, n_mels, 3000]`` on the device."""
+                 mask_params: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                 augment: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``pcm`` ``[B, N<=480000]`` float32 / int16 (host or device) -> ``[B, n_mels, 3000]`` on the device.
+
+        ``augment`` (optional int / bool ``[B]``): per-clip outcome of the reference's SpecAugment gate
+        (data_loader.py:294-301) when it was already decided upstream; clips with 0 get no warp and no masks."""
         if not torch.is_tensor(pcm):
             pcm = torch.as_tensor(pcm)
         if pcm.dim() != 2:
@@ -61,12 +65,20 @@ class FrontEnd:
             mask_params = draw_mask_params(self.seed, clip_offset, B, self.n_mels, self.n_frames,
                                            self.time_mask_param, self.freq_mask_param, self.spec_augment_p,
                                            self.device)
+        gate = None
+        if augment is not None:
+            gate = torch.as_tensor(augment).to(self.device, torch.int32, non_blocking=True).reshape(B, 1)
+            if mask_params is not None:
+                mask_params = (mask_params * gate).contiguous()   # [0, 0) spans mask nothing
         if self.time_warp_w > 0 and self.spec_augment_p > 0.0:
             # reference order (data_loader.py:285-287): warp -> time mask -> frequency mask
             plain = frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
                                      n_frames_out=self.n_frames, n_valid_frames=n_valid_frames)
             warps = draw_warp_params(self.seed, clip_offset, B, self.n_frames, self.time_warp_w, self.spec_augment_p,
                                      self.device)
+            if gate is not None:   # (T / 2, 0) is the identity warp
+                ident = torch.tensor([self.n_frames // 2, 0], dtype=torch.int32, device=self.device)
+                warps = torch.where(gate != 0, warps, ident).contiguous()
             warped = time_warp(plain, warps, out=out)
             return apply_masks(warped, mask_params, 0.0, out=warped) if mask_params is not None else warped
         return frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
