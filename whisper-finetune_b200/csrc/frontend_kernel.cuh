@@ -77,10 +77,12 @@ static_assert((kAudioBase & 3) == 0 && ((kSkewBlock + Skew<float>::value) * 4) %
               "every bulk copy (f32 or i16) must start and end on 16 bytes");
 static_assert(6 * (kSmemBytes + 1024) <= 228 * 1024, "6 CTAs per SM: 6 x (dynamic + 1 KB reserved) must fit 228 KB");
 
-__device__ const float g_window_table[kWinFloats] = WFT_WINDOW_TABLE_INIT;
-__device__ const float g_twiddle_table[kTwFloats] = WFT_TWIDDLE_TABLE_INIT;
-__device__ const float g_mel80_w[WFT_MEL80_W_LEN] = WFT_MEL80_W_INIT;
-__device__ const float g_mel128_w[WFT_MEL128_W_LEN] = WFT_MEL128_W_INIT;
+__device__ __align__(16) const float g_window_table[kWinFloats] = WFT_WINDOW_TABLE_INIT;
+__device__ __align__(16) const float g_twiddle_table[kTwFloats] = WFT_TWIDDLE_TABLE_INIT;
+__device__ __align__(16) const float g_mel80_w[WFT_MEL80_W_LEN] = WFT_MEL80_W_INIT;
+__device__ __align__(16) const float g_mel128_w[WFT_MEL128_W_LEN] = WFT_MEL128_W_INIT;
+static_assert(kWinFloats % 4 == 0 && kTwFloats % 4 == 0 && WFT_MEL80_W_LEN % 4 == 0 && WFT_MEL128_W_LEN % 4 == 0,
+              "the tables are copied to shared memory as 16-byte vectors");
 __device__ const uint32_t g_mel80_thread[kThreads] = WFT_MEL80_THREAD_INIT;
 __device__ const uint32_t g_mel128_thread[kThreads] = WFT_MEL128_THREAD_INIT;
 
@@ -552,11 +554,30 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   {
     // int16 PCM: the 1/32768 scale (whisper.audio.load_audio) is folded into the window, exactly (power of two)
     const float wscale = sizeof(PcmT) == 2 ? (1.0f / 32768.0f) : 1.0f;
-    for (int k = tid; k < kWinFloats; k += kThreads) sm_win[k] = g_window_table[k] * wscale;
-    for (int k = tid; k < kTwFloats; k += kThreads) sm_tw[k] = g_twiddle_table[k];
+    // 7.4 KB of tables as 16-byte vectors, every load of a thread in flight before its first store (this prologue is
+    // ~1/40 of a B = 64 launch when it is a chain of dependent 4-byte round trips)
     constexpr int kMelW = NM == 128 ? WFT_MEL128_W_LEN : WFT_MEL80_W_LEN;
-    const float* gw = NM == 128 ? g_mel128_w : g_mel80_w;
-    for (int k = tid; k < kMelW; k += kThreads) sm_melw[k] = gw[k];
+    constexpr int kVecWin = kWinFloats / 4, kVecTw = kTwFloats / 4, kVecMel = kMelW / 4;
+    constexpr int kVecAll = kVecWin + kVecTw + kVecMel;
+    constexpr int kPerThread = (kVecAll + kThreads - 1) / kThreads;
+    const float4* gwin = reinterpret_cast<const float4*>(g_window_table);
+    const float4* gtw = reinterpret_cast<const float4*>(g_twiddle_table);
+    const float4* gmel = reinterpret_cast<const float4*>(NM == 128 ? g_mel128_w : g_mel80_w);
+    float4 v[kPerThread];
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+      const int k = tid + i * kThreads;
+      if (k < kVecWin) v[i] = __ldg(gwin + k);
+      else if (k < kVecWin + kVecTw) v[i] = __ldg(gtw + (k - kVecWin));
+      else if (k < kVecAll) v[i] = __ldg(gmel + (k - kVecWin - kVecTw));
+    }
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+      const int k = tid + i * kThreads;
+      if (k < kVecWin) v[i] = make_float4(v[i].x * wscale, v[i].y * wscale, v[i].z * wscale, v[i].w * wscale);
+      // sm_win, sm_tw and sm_melw are contiguous in that order
+      if (k < kVecAll) reinterpret_cast<float4*>(sm_win)[k] = v[i];
+    }
   }
   uint64_t* audio_bar = reinterpret_cast<uint64_t*>(sm_ctl + kCtlMbar);  // completion of the audio tile's bulk copies
   constexpr int kTmaThread = kThreads - 32;                               // the thread that issues the bulk copies
