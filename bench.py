@@ -36,6 +36,7 @@ N_FRAMES = 3000
 TIME_MASK = 100
 FREQ_MASK = 43
 SEED = 42
+N_STREAMS = 2   # batches in flight in the throughput loop (the roofline loop stays strictly one launch after another)
 BYTES_PER_CLIP = 4 * N_SAMPLES + 4 * N_MELS * N_FRAMES  # 3 456 000 (algorithmic bytes, f32 in, 128 mel)
 METRIC = "30-s clips/sec log-mel+SpecAugment"
 UNIT = "clips/s"
@@ -49,7 +50,9 @@ def workload_config(n_gpus):
                     "time/freq masks (T=100, F=43, p=1.0), device-resident input",
         "n_mels": N_MELS, "clips_per_gpu_per_step": BATCH, "global_batch": BATCH * n_gpus, "pcm_dtype": "float32",
         "spec_augment": True, "sharding": "DistributedSampler-style batch shards, no data-path collective",
-        "cache": "3 rotating input/output buffer sets (664 MB per GPU) > 126 MB L2",
+        "cache": "4 rotating input/output buffer sets (885 MB per GPU) > 126 MB L2",
+        "streams": N_STREAMS,
+        "in_flight": "value: step i on stream i % 2 (two batches in flight); roofline: one launch after another on one stream",
     }
 
 
@@ -205,30 +208,49 @@ def run_ours(args):
     fe = wft.FrontEnd(n_mels=N_MELS, device=dev, spec_augment=True,
                       spec_augment_params={"time_mask_param": TIME_MASK, "freq_mask_param": FREQ_MASK, "p": 1.0},
                       seed=SEED)
-    n_sets = 3
+    n_sets = 4
     # every rank owns its shard of the synthetic "dataset": clip ids rank*B + step*world*B ... (weak scaling)
     pcm_sets = [synth_pcm(BATCH, SEED + 1000 * rank + s).to(dev) for s in range(n_sets)]
     out_sets = [torch.empty(BATCH, N_MELS, N_FRAMES, device=dev) for _ in range(n_sets)]
+    # two batches in flight (a loader with one batch of prefetch): step i runs on stream i % 2, so the ramp-down of one
+    # launch (CTAs running out of tiles) is filled by the next batch's CTAs.  Buffer set i % 4 is only ever used on
+    # stream i % 2, so launches that share buffers stay ordered.
+    streams = [torch.cuda.Stream(device=dev) for _ in range(N_STREAMS)]
 
     def step(i):
         s = i % n_sets
-        return fe(pcm_sets[s], clip_offset=(i * world + rank) * BATCH, out=out_sets[s])
+        with torch.cuda.stream(streams[i % N_STREAMS]):
+            return fe(pcm_sets[s], clip_offset=(i * world + rank) * BATCH, out=out_sets[s])
+
+    def fork():   # side streams start behind everything already queued on the current stream
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cur)
+
+    def join():
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            cur.wait_stream(st)
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    fork()
     for i in range(max(args.warmup, 3)):
         step(i)
+    join()
     barrier()
     lib.wft_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
         ev0.record()
+        fork()
         for i in range(args.steps):
             step(i)
+        join()
         ev1.record()
         barrier()
         launches = int(lib.wft_launch_count(0))
@@ -237,9 +259,11 @@ def run_ours(args):
         t_end = time.perf_counter() + 0.4
         i = args.steps
         while time.perf_counter() < t_end:
+            fork()
             for _ in range(20):
                 step(i)
                 i += 1
+            join()
             torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
