@@ -58,8 +58,8 @@ struct Skew {
 };
 constexpr int kAudioElems = kTileSamples + 20 * ((kTileSamples - 1) / kSkewBlock);     // 2960 float32 slots (int16 needs less)
 constexpr int kRowStride = 44;                                   // floats per exchange row (20 complex + pad)
-constexpr int kPairStride = 20 * kRowStride + 24;                // 904: pair stride == 8 (mod 32) banks
-constexpr int kRegionFloats = kPairs * kPairStride;              // 7232 floats = 28928 B
+constexpr int kPairStride = 20 * kRowStride + 20;                // 900: pair stride == 4 (mod 32) banks (pair_coord_a explains)
+constexpr int kRegionFloats = kPairs * kPairStride;              // 7200 floats = 28800 B
 constexpr int kPStride = WFT_MEL_P_STRIDE;                       // power tile [bin][frame]: 20 floats per bin (16 frames + pad)
 constexpr int kPFloats = 200 * kPStride;                         // bins 0..199 (bin 200 carries no mel weight)
 constexpr int kAudioBase = kRegionFloats - kAudioElems;          // float32 audio tile sits at the TOP of the region
@@ -270,17 +270,38 @@ __device__ __forceinline__ int launder(int x) {
   asm volatile("" : "+r"(x));
   return x;
 }
+//
+// Thread <-> (pair q, slot r) with the PAIR index fastest: a warp holds 8 pairs x 4 slots, so everything that depends on the
+// slot only -- the window column, the twiddle row -- is a quarter-warp-uniform 16-byte load (2 wavefronts instead of 4.8
+// when 20 consecutive lanes walked 20 different rows), and with a pair stride of 900 floats (== 4 banks mod 32) the eight
+// pairs of a quarter warp land on eight different 16-byte bank groups: exchange stores 2, row loads / mirror hand-off 4
+// wavefronts per instruction, i.e. their ideal (tools/micro/smem_wavefronts.cu measures every pattern used here).
+// Stages A and B need not agree on the slot a thread plays (nothing but shared memory crosses the stage boundary):
+//   stage A (slot = n2): slots in thread order;
+//   stage B / mirror / power (slot = k1 = j): the power store writes 16 consecutive floats of row j per quarter warp at a
+//   row stride of 20 floats, which is conflict free only when the two rows of a HALF warp are 4 (mod 8) rows apart, so
+//   the warps hold rows {0,4,1,5} {2,6,3,7} {8,12,9,13} {10,14,11,15} {16,17,18,19} (the last one cannot be paired).
 struct PairCoord {
   int q, r;
 };
-__device__ __forceinline__ PairCoord pair_coord() {
+__device__ __forceinline__ PairCoord pair_coord_a() {
   int t;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
   PairCoord c;
-  c.q = t / kPairThreads;
-  c.r = t - c.q * kPairThreads;
+  c.q = t & (kPairs - 1);
+  c.r = t >> 3;
   return c;
 }
+__device__ __forceinline__ PairCoord pair_coord_b() {
+  int t;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+  PairCoord c;
+  c.q = t & (kPairs - 1);
+  const int s = t >> 3;
+  c.r = s >= 16 ? s : ((s & 8) | ((s & 7) >> 1) | ((s & 1) << 2));
+  return c;
+}
+static_assert(kPairs == 8 && kThreads == 160, "pair_coord_a / pair_coord_b are written for 8 pairs x 20 slots");
 
 constexpr int kSilentBit = 1 << 30;   // flag carried by the tile id inside the pending ring / parked chain
 constexpr int kTileIdMask = kSilentBit - 1;
@@ -640,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         cpx x[20];
         {
           float u[28];
-          const auto [q, r] = pair_coord();
+          const auto [q, r] = pair_coord_a();
           const PcmT* a = sm_audio + (kSkewBlock + Skew<PcmT>::value) * q + r;
 #pragma unroll
           for (int j = 0; j < 28; ++j) u[j] = pcm_as_float(a[20 * j + (j >= 16 ? Skew<PcmT>::value : 0)]);
@@ -659,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         __syncthreads();  // audio is dead from here on: the region becomes the exchange buffer
         // (letting half 0 run ahead here with bar.arrive / bar.sync was measured 2-3 % slower)
         dft20(x);
-        const auto [q, r] = pair_coord();
+        const auto [q, r] = pair_coord_a();
         const float4* t4 = reinterpret_cast<const float4*>(sm_tw + r * kTwRow);
         float2* e2 = reinterpret_cast<float2*>(sm_region + q * kPairStride) + r;
 #pragma unroll
@@ -682,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         {
           cpx y[20];
           {
-            const auto [q, r] = pair_coord();
+            const auto [q, r] = pair_coord_b();
             const float4* row4 = reinterpret_cast<const float4*>(sm_region + q * kPairStride + r * kRowStride);
 #pragma unroll
             for (int a = 0; a < 10; ++a) {
@@ -692,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
             }
           }
           dft20(y);
-          const auto [q, r] = pair_coord();
+          const auto [q, r] = pair_coord_b();
           float4* row4 = reinterpret_cast<float4*>(sm_region + q * kPairStride + r * kRowStride);
           if (r != 0) {
 #pragma unroll
@@ -708,7 +729,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         }
         __syncthreads();
         {
-          const auto [q, r] = pair_coord();
+          const auto [q, r] = pair_coord_b();
           const float4* mir = reinterpret_cast<const float4*>(sm_region + q * kPairStride + ((20 - r) % 20) * kRowStride) + 5;
 #pragma unroll
           for (int a = 0; a < 5; ++a) {
@@ -730,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         }
 
         // power tile [bin][frame]: the pair's two frames are neighbours, one 8-byte store per bin
-        const auto [q, r] = pair_coord();
+        const auto [q, r] = pair_coord_b();
         float* pw = sm_region + r * kPStride + 2 * q;
 #pragma unroll
         for (int m = 0; m < 10; ++m) {
