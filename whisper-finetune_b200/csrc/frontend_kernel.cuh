@@ -278,9 +278,12 @@ __device__ __forceinline__ int launder(int x) {
 // wavefronts per instruction, i.e. their ideal (tools/micro/smem_wavefronts.cu measures every pattern used here).
 // Stages A and B need not agree on the slot a thread plays (nothing but shared memory crosses the stage boundary):
 //   stage A (slot = n2): slots in thread order;
-//   stage B / mirror / power (slot = k1 = j): the power store writes 16 consecutive floats of row j per quarter warp at a
-//   row stride of 20 floats, which is conflict free only when the two rows of a HALF warp are 4 (mod 8) rows apart, so
-//   the warps hold rows {0,4,1,5} {2,6,3,7} {8,12,9,13} {10,14,11,15} {16,17,18,19} (the last one cannot be paired).
+//   stage B / power (slot = k1 = j): two constraints pick the rows of a warp.  (1) Row j needs the upper half of row
+//   20 - j (the mirror bins): with both rows in one warp, 16 lanes apart, the hand-off is 20 SHFL per thread instead of a
+//   round trip through shared memory and two CTA barriers.  (2) The power store writes 16 consecutive floats of row j per
+//   quarter warp at a row stride of 20 floats, conflict free only when the two rows of a HALF warp are 4 (mod 8) apart.
+//   Warps 0..3 hold rows {a, a+4 | 20-a, 16-a}, a = 1..4; warp 4 holds what is left, {0, 10 | 9, 11}: rows 0 and 10 mirror
+//   themselves, 9 and 11 sit 8 lanes apart, and its power stores keep a 2-way conflict.
 struct PairCoord {
   int q, r;
 };
@@ -297,9 +300,18 @@ __device__ __forceinline__ PairCoord pair_coord_b() {
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
   PairCoord c;
   c.q = t & (kPairs - 1);
-  const int s = t >> 3;
-  c.r = s >= 16 ? s : ((s & 8) | ((s & 7) >> 1) | ((s & 1) << 2));
+  // rows of warp w = slots 4w .. 4w+3, one byte each
+  const uint32_t rows = (t >> 5) == 0 ? 0x0f130501u : (t >> 5) == 1 ? 0x0e120602u : (t >> 5) == 2 ? 0x0d110703u
+                      : (t >> 5) == 3 ? 0x0c100804u : 0x0b090a00u;
+  c.r = static_cast<int>((rows >> (((t >> 3) & 3) * 8)) & 0xffu);
   return c;
+}
+// lane that plays the mirror row (20 - r) % 20 of the same pair (see pair_coord_b)
+__device__ __forceinline__ int mirror_lane() {
+  int t;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+  const int lane = t & 31;
+  return t < 128 ? (lane ^ 16) : (lane < 16 ? lane : (lane ^ 8));
 }
 static_assert(kPairs == 8 && kThreads == 160, "pair_coord_a / pair_coord_b are written for 8 pairs x 20 slots");
 
@@ -695,9 +707,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       __syncthreads();
 
       // stage B: thread (q, k1 = r): Z[k1 + 20 k2] = DFT20 over n2.  The lower half (k2 < 10, bins k1 + 20 k2 <= 199)
-      // stays in registers; the upper half is what the mirror thread (q, 20 - k1) needs and goes back to the row.
+      // stays in registers; the upper half is what the mirror thread (q, 20 - k1) needs and travels by warp shuffle.
       // power: thread (q, j = r): bins j + 20 m (m = 0..9) against their mirrors Z[400 - j - 20 m] = row (20-j)%20,
-      // position 19 - m (row 0 mirrors itself one position further: 20 - m, so it publishes positions 11..20).
+      // position 19 - m (row 0 mirrors itself one position further: 20 - m, so it hands over positions 11..20).
       {
         cpx z[10], mz[10];
         {
@@ -713,30 +725,17 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
             }
           }
           dft20(y);
-          const auto [q, r] = pair_coord_b();
-          float4* row4 = reinterpret_cast<float4*>(sm_region + q * kPairStride + r * kRowStride);
-          if (r != 0) {
-#pragma unroll
-            for (int a = 0; a < 5; ++a)
-              row4[5 + a] = make_float4(y[10 + 2 * a].x, y[10 + 2 * a].y, y[11 + 2 * a].x, y[11 + 2 * a].y);
-          } else {
-#pragma unroll
-            for (int a = 0; a < 5; ++a)
-              row4[5 + a] = make_float4(y[11 + 2 * a].x, y[11 + 2 * a].y, y[(12 + 2 * a) % 20].x, y[(12 + 2 * a) % 20].y);
-          }
 #pragma unroll
           for (int m = 0; m < 10; ++m) z[m] = y[m];
-        }
-        __syncthreads();
-        {
-          const auto [q, r] = pair_coord_b();
-          const float4* mir = reinterpret_cast<const float4*>(sm_region + q * kPairStride + ((20 - r) % 20) * kRowStride) + 5;
+          if (tid < 8 * 16 + 8 && tid >= 8 * 16) {   // row 0 (slot 16, pair_coord_b): positions 11..20 instead of 10..19
 #pragma unroll
-          for (int a = 0; a < 5; ++a) {
-            const float4 v = mir[a];
-            mz[2 * a] = make_float2(v.x, v.y);
-            mz[2 * a + 1] = make_float2(v.z, v.w);
+            for (int m = 10; m < 19; ++m) y[m] = y[m + 1];
+            y[19] = y[0];
           }
+          const int src = mirror_lane();
+#pragma unroll
+          for (int m = 0; m < 10; ++m)
+            mz[m] = make_float2(__shfl_sync(0xffffffffu, y[10 + m].x, src), __shfl_sync(0xffffffffu, y[10 + m].y, src));
         }
         __syncthreads();  // exchange is dead: the region becomes power tile (bottom) + next audio tile (top)
         // prefetch the NEXT tile's PCM into the top of the region (its descriptor stays in sm_ctl until the loop ends)
