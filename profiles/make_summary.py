@@ -66,6 +66,8 @@ def main():
                      ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe"),
                      ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe"),
                      ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe"),
+                     ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared data pipe (LSU wavefronts), % of peak over the launch"),
+                     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
                      ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "shared-load bank conflicts"),
                      ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "shared-store bank conflicts"),
                      ("smsp__sass_inst_executed_op_local_ld.sum", "local loads (spills)")]:
@@ -116,8 +118,9 @@ def main():
     tot_e = sum(x["exec"] for x in regions)
     tot_s = sum(x["samp"] for x in regions) or 1.0
     out += ["", f"### Instructions per barrier-delimited region of the SASS ({len(data)} instructions = {len(data) * 16 / 1024:.0f} KB)",
-            "", "Regions in program order (stage 0/scheduling, stage A loads, stage A DFT+twiddle, stage B, power, mel, publish, "
-            "drain, fix-up function).", "", "| # | SASS instr | warp-instr / tile | share | stall-sample share | top opcodes (per tile) |", "|---|---|---|---|---|---|"]
+            "", "Regions in program order: 0-1 prologue / loop top / edge staging, 2 audio gather + window, 3 stage A DFT + twiddles + "
+            "exchange stores (+ describe_tile), 4 stage B row loads + DFT, 5 DFT tail + mirror shuffles + power tile, 6 mel phase, "
+            "8 ring check, 9 publication, 10-11 drain, 15-16 helper functions (bulk-copy issue, fix-up).", "", "| # | SASS instr | warp-instr / tile | share | stall-sample share | top opcodes (per tile) |", "|---|---|---|---|---|---|"]
     for i, x in enumerate(regions):
         if x["exec"] < 0.002 * tot_e:
             continue
