@@ -5,12 +5,13 @@
 //   (src/whisper_finetune/data/data_loader.py:346, :278, :279-282, :286-287, :362-367; data/utils.py:380-404).
 //
 // Work decomposition
-//   tile      = 16 consecutive frames of one clip = 8 frame PAIRS; 160 threads = 8 pairs x 20 threads; 6 CTAs per SM.
+//   tile      = 16 consecutive frames of one clip = 8 frame PAIRS; 160 threads = 8 pairs x 20 slots, pair index fastest
+//               (pair_coord_a / pair_coord_b); 6 CTAs per SM.
 //   pair      = frames (2q, 2q+1) packed as re/im of ONE 400-point complex FFT (two real frames per transform).
 //   400-point = 20 x 20 Cooley-Tukey, one register-resident 20-point DFT (dft20.cuh, packed f32x2) per thread per stage:
 //               stage A: thread (q, n2) transforms over n1, multiplies by W400^(n2 k1), scatters to the exchange;
-//               stage B: thread (q, k1) transforms over n2, keeps Z[k1 + 20 k2] for k2 < 10 in registers and hands the
-//                        upper half to the mirror thread (q, 20 - k1) through its exchange row;
+//               stage B: thread (q, k1) transforms over n2, keeps Z[k1 + 20 k2] for k2 < 10 in registers and receives the
+//                        upper half of the mirror row 20 - k1 by warp shuffle (both rows sit in one warp);
 //               power  : thread (q, j) pairs Z[j + 20 m] with its mirror Z[400 - j - 20 m] and separates the two real
 //                        spectra: 4|Xa|^2 = |Z[k] + conj Z[400-k]|^2, 4|Xb|^2 = |Z[k] - conj Z[400-k]|^2.
 //   mel phase = thread <-> one mel row x 16 (or 8) consecutive frames: the power tile is stored [bin][frame], so one tap of
@@ -27,10 +28,12 @@
 //               a CTA never waits while tiles are still unclaimed (pending tiles are ringed / parked), so the kernel is
 //               deadlock-free for any grid size.
 //
-// Shared memory per CTA: one 28.9 KB region time-multiplexed as
+// Shared memory per CTA: one 28.8 KB region time-multiplexed as
 //   [audio tile at the top] -> stage A->B exchange -> [power tile at the bottom | next audio tile at the top],
-// plus ~8.7 KB of window / twiddle / mel-program tables and control words.  The hot loop is one DFT20 copy per stage and
-// ~2.6 k SASS instructions so that it stays resident in the SM's instruction cache.
+// plus ~7.8 KB of window / twiddle / mel-weight tables and control words.  The thread order and every stride in here
+// were chosen against measured shared-memory wavefront costs (tools/micro/smem_wavefronts.cu,
+// profiles/r01_smem_wavefront_probe.md): the data pipe, not HBM, is what bounds this kernel.  The hot loop is one DFT20
+// copy per stage and ~2.4 k SASS instructions so that it stays resident in the SM's instruction cache.
 #pragma once
 
 #include <cuda_runtime.h>
