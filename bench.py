@@ -146,6 +146,18 @@ def cpu_reference_clips_per_s(min_seconds, max_clips=None, threads=None):
     return done / el, done, el, torch.get_num_threads()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (here: its restatement in oracle/, since
     whisper.audio is a third-party dependency that is not installable offline) on all host threads.  A step is a
@@ -183,7 +195,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "audio_hours_per_s": val * 30.0 / 3600.0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -351,7 +363,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
                                     "sample": f"{done} clips in {el:.1f} s, oracle/pipeline.py clip by clip, torch "
                                               f"intra-op threads={thr} of {os.cpu_count()} host cores"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
@@ -372,6 +384,12 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    # stdout carries exactly ONE JSON line: anything a library prints on file descriptor 1 while the run is going on (NCCL's
+    # version banner, for one) is sent to stderr instead, and the line is written to the real stdout at the end
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
