@@ -277,6 +277,17 @@ def test_host_pipeline_matches_direct_call(wft, cuda):
     pipe.synchronize()
     direct = fe(host.to(cuda), clip_offset=100).cpu()
     assert torch.equal(out, direct)
+    # two batches back to back without a synchronisation in between (they overlap on the side streams), then join():
+    # the current stream sees both results
+    host_b = torch.stack([S.make("white", n=480000, seed=60 + s) for s in range(6)]).pin_memory()
+    out_b = torch.empty(6, 128, 3000).pin_memory()
+    out.zero_()
+    pipe(host, out, clip_offset=100)
+    pipe(host_b, out_b, clip_offset=106)
+    pipe.join()
+    torch.cuda.current_stream().synchronize()
+    assert torch.equal(out, direct)
+    assert torch.equal(out_b, fe(host_b.to(cuda), clip_offset=106).cpu())
     host16 = (host * 32767).round().to(torch.int16).pin_memory()
     pipe16 = wft.HostPipeline(fe, 6, pcm_dtype=torch.int16, n_chunks=2, n_streams=2)
     pipe16(host16, out, clip_offset=100)

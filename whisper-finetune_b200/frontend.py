@@ -119,11 +119,17 @@ class HostPipeline:
     def __call__(self, pcm_host: torch.Tensor, out_host: torch.Tensor, lengths=None, n_valid_frames=None,
                  clip_offset: int = 0) -> torch.Tensor:
         """``pcm_host`` pinned ``[B, N]``, ``out_host`` pinned ``[B, n_mels, 3000]`` (``[B]`` for ``readback="probe"``);
-        returns ``out_host`` once every copy has been enqueued (call ``synchronize()`` before reading it)."""
+        returns ``out_host`` once every copy has been enqueued: call ``synchronize()`` before reading it on the host, or
+        ``join()`` to make the current stream wait for it.
+
+        Consecutive calls overlap: slice ``k`` always travels on stream ``k % n_streams`` and re-uses its own part of the
+        device buffers, so stream order alone keeps two batches apart and the H2D copies of batch ``i + 1`` start while the
+        D2H copies of batch ``i`` are still draining (the current stream is NOT made to wait here -- that would put a
+        full pipeline drain between any two batches)."""
         cur = torch.cuda.current_stream(self.fe.device)
         for k, (a, b) in enumerate(self.slices):
             st = self.streams[k % len(self.streams)]
-            st.wait_stream(cur)
+            st.wait_stream(cur)   # whatever the caller queued before this call (device-side lengths, ...)
             with torch.cuda.stream(st):
                 self.dev_pcm[a:b].copy_(pcm_host[a:b], non_blocking=True)
                 self.fe(self.dev_pcm[a:b],
@@ -134,9 +140,14 @@ class HostPipeline:
                     out_host[a:b].copy_(self.dev_out[a:b], non_blocking=True)
                 else:
                     out_host[a:b].copy_(self.dev_out[a:b, 0, 0], non_blocking=True)
-        for st in self.streams:
-            cur.wait_stream(st)
         return out_host
 
+    def join(self) -> None:
+        """Make the current stream wait for everything enqueued so far (for stream-ordered consumers and event timing)."""
+        cur = torch.cuda.current_stream(self.fe.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
     def synchronize(self) -> None:
-        torch.cuda.current_stream(self.fe.device).synchronize()
+        for st in self.streams:
+            st.synchronize()
