@@ -712,7 +712,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       // stage B: thread (q, k1 = r): Z[k1 + 20 k2] = DFT20 over n2.  The lower half (k2 < 10, bins k1 + 20 k2 <= 199)
       // stays in registers; the upper half is what the mirror thread (q, 20 - k1) needs and travels by warp shuffle.
       // power: thread (q, j = r): bins j + 20 m (m = 0..9) against their mirrors Z[400 - j - 20 m] = row (20-j)%20,
-      // position 19 - m (row 0 mirrors itself one position further: 20 - m, so it hands over positions 11..20).
+      // position 19 - m = mz[9 - m].  Row 0 mirrors ITSELF one position further (20 - m, with 20 == 0): it reads its own
+      // upper half back from the shuffle and picks mz[10 - m] (m > 0) or z[0]; only warp 4 holds row 0 and pays for the
+      // selection.
       {
         cpx z[10], mz[10];
         {
@@ -730,11 +732,6 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           dft20(y);
 #pragma unroll
           for (int m = 0; m < 10; ++m) z[m] = y[m];
-          if (tid < 8 * 16 + 8 && tid >= 8 * 16) {   // row 0 (slot 16, pair_coord_b): positions 11..20 instead of 10..19
-#pragma unroll
-            for (int m = 10; m < 19; ++m) y[m] = y[m + 1];
-            y[19] = y[0];
-          }
           const int src = mirror_lane();
 #pragma unroll
           for (int m = 0; m < 10; ++m)
@@ -755,13 +752,26 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         // power tile [bin][frame]: the pair's two frames are neighbours, one 8-byte store per bin
         const auto [q, r] = pair_coord_b();
         float* pw = sm_region + r * kPStride + 2 * q;
+        if (tid < 128) {
 #pragma unroll
-        for (int m = 0; m < 10; ++m) {
-          // Z[k] = z[m], Z[400-k] = mz[9-m]
-          const cpx sa = cfma(mz[9 - m], make_float2(1.0f, -1.0f), z[m]);   // Z[k] + conj Z[400-k]  -> frame 2q
-          const cpx sb = cfma(mz[9 - m], make_float2(-1.0f, 1.0f), z[m]);   // Z[k] - conj Z[400-k]  -> frame 2q + 1
-          *reinterpret_cast<float2*>(pw + 20 * m * kPStride) =
-              make_float2(fmaf(sa.x, sa.x, sa.y * sa.y), fmaf(sb.x, sb.x, sb.y * sb.y));
+          for (int m = 0; m < 10; ++m) {
+            // Z[k] = z[m], Z[400-k] = mz[9-m]
+            const cpx sa = cfma(mz[9 - m], make_float2(1.0f, -1.0f), z[m]);   // Z[k] + conj Z[400-k]  -> frame 2q
+            const cpx sb = cfma(mz[9 - m], make_float2(-1.0f, 1.0f), z[m]);   // Z[k] - conj Z[400-k]  -> frame 2q + 1
+            *reinterpret_cast<float2*>(pw + 20 * m * kPStride) =
+                make_float2(fmaf(sa.x, sa.x, sa.y * sa.y), fmaf(sb.x, sb.x, sb.y * sb.y));
+          }
+        } else {   // warp 4: rows 0, 10, 9, 11
+          const bool row0 = r == 0;
+#pragma unroll
+          for (int m = 0; m < 10; ++m) {
+            const cpx alt = m == 0 ? z[0] : mz[10 - m];
+            const cpx mir = make_float2(row0 ? alt.x : mz[9 - m].x, row0 ? alt.y : mz[9 - m].y);
+            const cpx sa = cfma(mir, make_float2(1.0f, -1.0f), z[m]);
+            const cpx sb = cfma(mir, make_float2(-1.0f, 1.0f), z[m]);
+            *reinterpret_cast<float2*>(pw + 20 * m * kPStride) =
+                make_float2(fmaf(sa.x, sa.x, sa.y * sa.y), fmaf(sb.x, sb.x, sb.y * sb.y));
+          }
         }
       }
       __syncthreads();
