@@ -140,6 +140,11 @@ int wft_mask_bsd(const void* in, void* out, int32_t elem_bytes, int64_t batch, i
 int64_t wft_launch_count(int reset);
 int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t* threads, int32_t* smem_bytes);
 
+/* Test hook: cap the persistent grid of wft_frontend_forward at `max_ctas` CTAs (0 = no cap, the default).  Results do not
+ * depend on the grid; a tiny grid forces the kernel's pending-tile FIFO to overflow into the parked chain and every
+ * fix-up into the drain loop, paths a full-size grid only takes for clips longer than ~19 minutes. */
+int wft_debug_set_max_ctas(int32_t max_ctas);
+
 #ifdef __cplusplus
 }
 #endif

@@ -188,8 +188,91 @@ def test_large_batch_roundtrip_properties(wft, cuda):
     perm = torch.randperm(64, generator=g)
     c = wft.log_mel_spectrogram(d[perm.to(cuda)], n_mels=128)
     assert torch.equal(c, a[perm.to(cuda)]), "clips are independent: permuting the batch permutes the output"
-    for bidx in (0, 5, 9, 63):
-        _check(a[bidx].cpu(), O.log_mel_spectrogram(pcm[bidx], 128), f"clip {bidx}")
+    ref = O.log_mel_batch(pcm, 128)          # every clip of the batch against the oracle (not a spot check)
+    host = a.cpu()
+    for bidx in range(64):
+        _check(host[bidx], ref[bidx], f"clip {bidx}")
+
+
+def _config3_batch(B, seed):
+    """config 3 of BASELINE.json: ragged U(1 s, 30 s) clips, 25 % partial-segment cuts, SpecAugment masks."""
+    rng = np.random.default_rng(seed)
+    lengths = rng.integers(16000, 480001, size=B).astype(np.int32)
+    lengths[0], lengths[1] = 480000, 16000
+    g = torch.Generator().manual_seed(seed)
+    pcm = (0.1 * torch.randn(B, 480000, generator=g)).clamp(-1, 1)
+    pcm *= torch.from_numpy(10.0 ** rng.uniform(-3, 0, size=(B, 1))).float()      # clips of very different loudness
+    pcm[torch.arange(480000)[None, :] >= torch.from_numpy(lengths)[:, None]] = 0.0
+    n_valid = np.full(B, -1, dtype=np.int32)
+    cut = rng.random(B) < 0.25
+    n_valid[cut] = (rng.uniform(0.02, 30.0, size=int(cut.sum())) * 100).astype(np.int32)
+    return pcm, lengths, n_valid
+
+
+def test_config3_batch_256_matches_oracle(wft, cuda):
+    """BASELINE config 3 at its full size (B = 256, 128 mel, ragged + cuts + masks), every clip against the oracle."""
+    B = 256
+    pcm, lengths, n_valid = _config3_batch(B, 2024)
+    masks = OS.draw_mask_params(11, 5000, B, 128, 3000, 100, 27, 1.0)
+    fe = wft.FrontEnd(n_mels=128, spec_augment=True,
+                      spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "p": 1.0}, seed=11)
+    got = fe(pcm.to(cuda), lengths=lengths, n_valid_frames=n_valid, clip_offset=5000).cpu()
+    ref = OP.front_end_batch(pcm, 128, lengths=lengths, n_valid_frames=n_valid, masks=masks)
+    for b in range(B):
+        keep = 3000 if n_valid[b] < 0 else int(n_valid[b])
+        if keep:
+            _check(got[b, :, :keep], ref[b, :, :keep], f"config 3 clip {b} (kept frames)")
+        assert (got[b] - ref[b]).abs().max() <= S.MAX_ABS
+        t0, t1, f0, f1 = masks[b]
+        m = torch.zeros(128, 3000, dtype=torch.bool)
+        m[:, t0:t1] = True
+        m[f0:f1, :] = True
+        assert torch.equal(got[b][m], torch.zeros(int(m.sum()))), "masked cells must be exactly 0.0"
+        assert int((got[b][~m] == 0).sum()) <= 2, "an unmasked feature is 0.0 only by coincidence"
+
+
+@pytest.mark.parametrize("max_ctas", [1, 3, 40])
+def test_tiny_grid_takes_the_parked_chain_and_drain(wft, cuda, max_ctas):
+    """The result must not depend on the persistent grid.  With 1-40 CTAs a CTA holds far more than 16 pending tiles of an
+    incomplete clip, so the pending FIFO overflows into the parked chain and the fix-ups (floor binds on the hdr clip,
+    min pad, silent tiles, masks) run from the drain loop -- the paths a full grid takes only for very long clips."""
+    lib = wft._lib.load()
+    pcm = torch.stack([S.make("hdr"), S.make("white", seed=3), S.make("int16").float() / 32768.0, S.make("chirp")])
+    lengths = np.asarray([480000, 300000, 480000, 123456], dtype=np.int32)
+    pcm[torch.arange(480000)[None, :] >= torch.from_numpy(lengths)[:, None]] = 0.0
+    n_valid = np.asarray([-1, 1000, 2999, -1], dtype=np.int32)
+    masks = OS.draw_mask_params(5, 77, 4, 128, 3000, 100, 27, 1.0)
+    fe = wft.FrontEnd(n_mels=128)
+    full = fe(pcm.to(cuda), lengths=lengths, n_valid_frames=n_valid, mask_params=masks)
+    try:
+        lib.wft_debug_set_max_ctas(max_ctas)
+        capped = fe(pcm.to(cuda), lengths=lengths, n_valid_frames=n_valid, mask_params=masks)
+        torch.cuda.synchronize()
+    finally:
+        lib.wft_debug_set_max_ctas(0)
+    assert torch.equal(capped, full)
+    ref = OP.front_end_batch(pcm, 128, lengths=lengths, n_valid_frames=n_valid, masks=masks)
+    for b in range(4):
+        keep = 3000 if n_valid[b] < 0 else int(n_valid[b])
+        _check(capped[b, :, :keep].cpu(), ref[b, :, :keep], f"capped grid clip {b}")
+        assert (capped[b].cpu() - ref[b]).abs().max() <= S.MAX_ABS
+
+
+def test_forty_minute_clip_overflows_the_pending_fifo(wft, cuda):
+    """One 40-minute clip = 15 000 tiles > 16 FIFO slots x 888 CTAs: on the FULL grid every CTA parks tiles, and the floor
+    binds on almost all of them (2 s of loud tone, then faint noise 14 decades down)."""
+    n = 40 * 60 * 16000
+    g = torch.Generator().manual_seed(40)
+    x = 1e-7 * torch.randn(n, generator=g)
+    t = torch.arange(32000, dtype=torch.float64) / 16000.0
+    x[:32000] += (0.5 * torch.sin(2 * np.pi * 440.0 * t)).float()
+    got = wft.log_mel_spectrogram(x.to(cuda), n_mels=128).cpu()
+    ref = O.log_mel_spectrogram(x, 128)
+    assert got.shape == (128, n // 160)
+    _check(got, ref, "40-minute clip")
+    floor = got.min().item()
+    assert (got == floor).float().mean().item() > 0.9, "the floor must bind on the quiet part"
+    assert abs((got.max().item() - floor) - 2.0) <= 1e-5
 
 
 def _gold(name):

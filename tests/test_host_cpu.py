@@ -101,8 +101,8 @@ def test_generated_tables_are_current(wft):
         plan = gen.mel_plan(bank)
         gen.simulate(bank, plan)
         assert len(plan["thread"]) == 160 and sorted({t[0] for t in plan["thread"]}) == list(range(n_mels))
-        assert all(1 <= t[1] and t[1] + plan["classes"][plan["warp_class"][i // 32]][0] - 1 <= 199
-                   for i, t in enumerate(plan["thread"]))
+        assert all(1 <= t[1] and t[1] + plan["warp_t"][i // 32] - 1 <= 199 for i, t in enumerate(plan["thread"]))
+        assert all(t[2] + plan["warp_nf"][i // 32] <= 16 for i, t in enumerate(plan["thread"]))
 
 
 @pytest.mark.parametrize("n,world,drop_last,shuffle", [(100, 4, False, True), (101, 4, True, True), (7, 8, False, True),

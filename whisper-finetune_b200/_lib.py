@@ -56,6 +56,7 @@ SIGNATURES = {
                              c_uint32, c_void_p]),
     "wft_launch_count": (c_int64, [c_int]),
     "wft_frontend_grid": (c_int, [c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    "wft_debug_set_max_ctas": (c_int, [c_int32]),
 }
 
 _lib = None

@@ -70,8 +70,8 @@ constexpr int kWinFloats = WFT_WINDOW_TABLE_LEN;                 // 400
 constexpr int kTwFloats = WFT_TWIDDLE_TABLE_LEN;                 // 880
 constexpr int kTwRow = WFT_TWIDDLE_ROW;                          // 44
 constexpr int kMelWFloats = ((WFT_MEL80_W_LEN > WFT_MEL128_W_LEN ? WFT_MEL80_W_LEN : WFT_MEL128_W_LEN) + 3) & ~3;
-constexpr int kMaxPending = 8;   // <= 8: ring slots in sm_ctl
-constexpr int kCtlInts = 84;
+constexpr int kRing = 16;         // pending-tile FIFO slots in sm_ctl (power of two)
+constexpr int kCtlInts = 116;
 constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats + kMelWFloats) * 4 + kCtlInts * 4;
 
 static_assert(kPFloats <= kAudioBase, "power tile and prefetched audio tile must not overlap");
@@ -89,34 +89,21 @@ static_assert(kWinFloats % 4 == 0 && kTwFloats % 4 == 0 && WFT_MEL80_W_LEN % 4 =
 __device__ const uint32_t g_mel80_thread[kThreads] = WFT_MEL80_THREAD_INIT;
 __device__ const uint32_t g_mel128_thread[kThreads] = WFT_MEL128_THREAD_INIT;
 
-// mel plan (gen_tables.py): warp w runs tap class mel_warp_class(w) = (taps, quads of 4 frames per thread, weight stride)
+// mel plan (gen_tables.py): warp w owns a group of rows of similar tap count; its threads run T(w) taps over NF(w) frames each
 template <int NM>
-__host__ __device__ constexpr int mel_n_classes() { return NM == 80 ? WFT_MEL80_NCLASS : WFT_MEL128_NCLASS; }
-template <int NM>
-__host__ __device__ constexpr int mel_class_taps(int c) {
-  constexpr int a[WFT_MEL_MAX_CLASSES] = WFT_MEL80_CLASS_T, b[WFT_MEL_MAX_CLASSES] = WFT_MEL128_CLASS_T;
-  return NM == 80 ? a[c] : b[c];
-}
-template <int NM>
-__host__ __device__ constexpr int mel_class_quads(int c) {
-  constexpr int a[WFT_MEL_MAX_CLASSES] = WFT_MEL80_CLASS_NQ, b[WFT_MEL_MAX_CLASSES] = WFT_MEL128_CLASS_NQ;
-  return NM == 80 ? a[c] : b[c];
-}
-template <int NM>
-__host__ __device__ constexpr int mel_class_wstride(int c) {
-  constexpr int a[WFT_MEL_MAX_CLASSES] = WFT_MEL80_CLASS_WS, b[WFT_MEL_MAX_CLASSES] = WFT_MEL128_CLASS_WS;
-  return NM == 80 ? a[c] : b[c];
-}
-template <int NM>
-__host__ __device__ constexpr int mel_warp_class(int w) {
-  constexpr int a[kWarps] = WFT_MEL80_WARP_CLASS, b[kWarps] = WFT_MEL128_WARP_CLASS;
+__host__ __device__ constexpr int mel_warp_taps(int w) {
+  constexpr int a[kWarps] = WFT_MEL80_WARP_T, b[kWarps] = WFT_MEL128_WARP_T;
   return NM == 80 ? a[w] : b[w];
 }
 template <int NM>
-__host__ __device__ constexpr bool mel_any_wide() {   // does any class hold 16 frames (4 quads) per thread?
-  for (int c = 0; c < mel_n_classes<NM>(); ++c)
-    if (mel_class_quads<NM>(c) == 4) return true;
-  return false;
+__host__ __device__ constexpr int mel_warp_frames(int w) {
+  constexpr int a[kWarps] = WFT_MEL80_WARP_NF, b[kWarps] = WFT_MEL128_WARP_NF;
+  return NM == 80 ? a[w] : b[w];
+}
+template <int NM>
+__host__ __device__ constexpr int mel_warp_wstride(int w) {
+  constexpr int a[kWarps] = WFT_MEL80_WARP_WS, b[kWarps] = WFT_MEL128_WARP_WS;
+  return NM == 80 ? a[w] : b[w];
 }
 
 struct ClipStat {
@@ -145,6 +132,8 @@ struct FrontendParams {
   int32_t total_tiles;
   float mask_value;
   uint32_t zero;        // always 0; gives the completion counter a data dependency the compiler cannot fold
+  uint32_t tpc_magic;   // floor(2^32 / tiles_per_clip): tile -> clip by multiply-high (+ one correction step)
+  int32_t vec_ok;       // `out` is 32-byte aligned and n_frames_out % 8 == 0: the mel phase may use 32-byte stores
 };
 
 __device__ __forceinline__ uint32_t enc_ordered(float f) {
@@ -240,13 +229,6 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* addr) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(addr) : "memory");
   return v;
 }
-// one 16-byte snapshot {max_enc, min_inv, done, -} of a clip's statistics (a single L2 sector access)
-__device__ __forceinline__ uint4 ld_stat(const ClipStat* st) {
-  uint4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(st) : "memory");
-  return v;
-}
 __device__ __forceinline__ float fast_log2(float x) {  // x is a normal float here: plain MUFU.LG2
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -321,91 +303,155 @@ static_assert(kPairs == 8 && kThreads == 160, "pair_coord_a / pair_coord_b are w
 constexpr int kSilentBit = 1 << 30;   // flag carried by the tile id inside the pending ring / parked chain
 constexpr int kTileIdMask = kSilentBit - 1;
 
-// log10 of the 1e-10 clamp exactly as the mel phase computes it for an all-zero frame
-__device__ __forceinline__ float silent_log_mel() { return fast_log2(1e-10f) * 0.301029995663981195f; }
+constexpr float kLog10Of2 = 0.301029995663981195f;
+constexpr float kFeatScale = 0.25f * kLog10Of2;   // (log10 x + 4) / 4 == log2 x * kFeatScale + 1 (0.25 * c is exact)
 
-// ---- mel projection ---------------------------------------------------------------------------------------------------
-// A thread owns ONE mel row for 16 or 8 consecutive frames and walks them 8 at a time.  pk = &P[start_bin][first frame]
-// in the [bin][frame] power tile, w = the thread's weight column (tap j at w[j * WS]).  Taps run in ascending bin order;
-// padded taps carry a zero weight on an always-finite bin, so the sum is exactly the dense row product.
-template <int T, int WS>
-__device__ __forceinline__ void mel_taps(const float* __restrict__ pk, const float* __restrict__ w, cpx (&acc)[4]) {
-#pragma unroll
-  for (int j = 0; j < T; ++j) {
-    const cpx ww = splat(w[j * WS]);
-#pragma unroll
-    for (int qd = 0; qd < 2; ++qd) {
-      const float4 v = *reinterpret_cast<const float4*>(pk + j * kPStride + 4 * qd);
-      if (j == 0) {
-        acc[2 * qd] = cmul(ww, make_float2(v.x, v.y));
-        acc[2 * qd + 1] = cmul(ww, make_float2(v.z, v.w));
-      } else {
-        acc[2 * qd] = cfma(ww, make_float2(v.x, v.y), acc[2 * qd]);
-        acc[2 * qd + 1] = cfma(ww, make_float2(v.z, v.w), acc[2 * qd + 1]);
-      }
-    }
-  }
+// Everything downstream of the mel sum works on L2 = MUFU.LG2(max(mel, 1e-10)): the clip statistics are max / min of L2,
+// the feature is ONE monotone FMA of it, and the floor / pad values are the same FMA applied to the statistics, so
+//   max(feature, floor)  and  pad = min over the kept, floored features
+// hold bit for bit whatever the rounding of the FMA is.
+__device__ __forceinline__ float feature_of_l2(float l2) { return fmaf(l2, kFeatScale, 1.0f); }
+// feature value of the clip's dynamic-range floor, (max log10 - 8 + 4) / 4 (whisper.audio: log_spec.max() - 8.0)
+__device__ __forceinline__ float floor_feature(float max_l2) {
+  return fmaf(__fsub_rn(__fmul_rn(max_l2, kLog10Of2), 8.0f), 0.25f, 1.0f);
 }
-// warp-uniform dispatch on the warp's tap class: one fully unrolled tap loop per class
-template <int NM, int C>
-__device__ __forceinline__ void mel_dispatch(int cls, const float* __restrict__ pk, const float* __restrict__ w, cpx (&acc)[4]) {
-  if constexpr (C < mel_n_classes<NM>()) {
-    if (C == mel_n_classes<NM>() - 1 || cls == C)
-      mel_taps<mel_class_taps<NM>(C), mel_class_wstride<NM>(C)>(pk, w, acc);
-    else
-      mel_dispatch<NM, C + 1>(cls, pk, w, acc);
-  }
+// L2 of the 1e-10 clamp exactly as the mel phase computes it for an all-zero frame
+__device__ __forceinline__ float silent_l2() { return fast_log2(1e-10f); }
+
+// three-input max / min (FMNMX3, sm_100+)
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 
-// frame windows of a tile as 16-bit masks (bit f = frame t0 + f); only edge tiles look at them
-struct MelEdge {
-  uint32_t live;    // real frame of the clip: counts for the max and for the floor test
-  uint32_t kept;    // survives the partial-segment cut: counts for the pad minimum
-  uint32_t store;   // has a cell in `out`
-  uint32_t tmask;   // inside the SpecAugment time mask
-};
-__device__ __forceinline__ uint32_t frame_window(int lo, int hi, int t0) {   // frames [lo, hi) as bits of the tile at t0
-  lo = min(max(lo - t0, 0), kTileFrames);
-  hi = min(max(hi - t0, 0), kTileFrames);
-  return hi > lo ? (1u << hi) - (1u << lo) : 0u;
-}
 __device__ __forceinline__ void st_global_256(float* dst, const float (&v)[8]) {   // one full 32-byte sector per thread
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 
-// 8 consecutive frames of one mel row: log10, statistics, final feature (L + 4) / 4 (row mask folded into sc / of), store.
-// kFast: every frame is live, kept, stored and outside the time mask, `dst` is 32-byte aligned.
-// Otherwise bit i of the (already shifted) windows in `e` describes frame i of these 8.
-template <bool kFast>
-__device__ __forceinline__ void mel_post8(const cpx* __restrict__ acc, float sc, float of, float mask_value,
-                                          float* __restrict__ dst, const MelEdge& e, float& mx, float& mn_kept, float& mn_live) {
-  float v[8];
+// ---- mel projection, fast tiles -------------------------------------------------------------------------------------------
+// A thread owns ONE mel row for NF consecutive frames (gen_tables.py deals the rows to the warps by tap count, so T, NF and
+// the weight stride WS are warp constants and this is fully unrolled, branch free code).  pk = &P[start_bin][first frame] in
+// the [bin][frame] power tile, wp = the thread's weight column (tap j at wp[j * WS]).  Taps run in ascending bin order;
+// padded taps carry a zero weight on an always-finite bin, so the sum is exactly the dense row product.
+// Fast tile: all 16 frames are real, stored, all kept or all cut, none (or all) inside the time mask; sc / of fold the
+// row / tile mask into the feature FMA (masked: 0 * L2 + mask_value).
+template <int T, int NF, int WS>
+__device__ __forceinline__ void mel_fast(const float* __restrict__ pk, const float* __restrict__ wp, float sc, float of,
+                                         float* __restrict__ dst, float& mx, float& mn) {
+  constexpr int CH = NF >= 8 ? 8 : 4;   // frames per pass: 8 (one 32-byte store) or 4 (16 bytes)
+  float w[T];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float a = (i & 1) ? acc[i >> 1].y : acc[i >> 1].x;
-    const float L = fast_log2(fmaxf(a, 1e-10f)) * 0.301029995663981195f;
-    v[i] = fmaf(L, sc, of);   // (L + 4) / 4, exactly
-    if (kFast) {
-      mx = fmaxf(mx, L);
-      mn_live = fminf(mn_live, L);
-    } else {
-      if ((e.live >> i) & 1u) {
-        mx = fmaxf(mx, L);
-        mn_live = fminf(mn_live, L);
+  for (int j = 0; j < T; ++j) w[j] = wp[j * WS];
+#pragma unroll
+  for (int c = 0; c < NF; c += CH) {
+    cpx acc[CH / 2];
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      const cpx ww = splat(w[j]);
+#pragma unroll
+      for (int qd = 0; qd < CH / 4; ++qd) {
+        const float4 v = *reinterpret_cast<const float4*>(pk + j * kPStride + c + 4 * qd);
+        if (j == 0) {
+          acc[2 * qd] = cmul(ww, make_float2(v.x, v.y));
+          acc[2 * qd + 1] = cmul(ww, make_float2(v.z, v.w));
+        } else {
+          acc[2 * qd] = cfma(ww, make_float2(v.x, v.y), acc[2 * qd]);
+          acc[2 * qd + 1] = cfma(ww, make_float2(v.z, v.w), acc[2 * qd + 1]);
+        }
       }
-      if ((e.kept >> i) & 1u) mn_kept = fminf(mn_kept, L);
-      if ((e.tmask >> i) & 1u) v[i] = mask_value;
-      if ((e.store >> i) & 1u) dst[i] = v[i];
+    }
+    float v[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i += 2) {
+      const float la = fast_log2(fmaxf(acc[i >> 1].x, 1e-10f));
+      const float lb = fast_log2(fmaxf(acc[i >> 1].y, 1e-10f));
+      mx = max3(mx, la, lb);
+      mn = min3(mn, la, lb);
+      v[i] = fmaf(la, sc, of);
+      v[i + 1] = fmaf(lb, sc, of);
+    }
+    if constexpr (CH == 8) {
+      st_global_256(dst + c, v);
+    } else {
+      *reinterpret_cast<float4*>(dst + c) = make_float4(v[0], v[1], v[2], v[3]);
     }
   }
-  if (kFast) st_global_256(dst, v);
+}
+
+// frames [lo, hi) as bits of the 16-frame tile starting at t0 (bit f = frame t0 + f)
+__device__ __forceinline__ uint32_t frame_window(int lo, int hi, int t0) {
+  lo = min(max(lo - t0, 0), kTileFrames);
+  hi = min(max(hi - t0, 0), kTileFrames);
+  return hi > lo ? (1u << hi) - (1u << lo) : 0u;
+}
+
+// tile descriptor (16 ints in sm_ctl, written by thread 0 in describe_tile, read by every phase that needs a field)
+enum { kDescId = 0, kDescClip = 1, kDescT0 = 2, kDescKind = 3, kDescPcmLo = 4, kDescPcmHi = 5, kDescFlags = 6, kDescKeep = 7,
+       kDescMask = 8 /* t0, t1, f0, f1 */, kDescOutLo = 12, kDescOutHi = 13 };
+enum { kFlagFast = 1,        // the mel phase may take the branch-free path
+       kFlagAllKept = 2,     // (fast tiles) every frame survives the partial-segment cut -> counts for the pad minimum
+       kFlagAllMasked = 4 }; // (fast tiles) every frame lies inside the SpecAugment time mask
+
+// ---- mel projection, edge tiles (generic, one frame at a time): the clip's last tile, the two tiles a time mask or the
+// partial-segment cut passes through, unaligned outputs.  Same thread <-> (row, frames) map and the same summation order as
+// mel_fast, so a cell's value does not depend on the path that produced it. ------------------------------------------------
+template <int NM>
+__device__ __noinline__ void mel_edge(const float* __restrict__ sm_region, const float* __restrict__ sm_melw,
+                                      const int* __restrict__ desc, uint32_t mel_desc, float* __restrict__ out, int n_frames,
+                                      int n_frames_out, float mask_value, float* __restrict__ red) {
+  const int warp = static_cast<int>(threadIdx.x) >> 5;
+  int T = 0, NF = 0, WS = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w)
+    if (warp == w) {
+      T = mel_warp_taps<NM>(w);
+      NF = mel_warp_frames<NM>(w);
+      WS = mel_warp_wstride<NM>(w);
+    }
+  const int row = static_cast<int>(mel_desc & 0xffu), f0 = static_cast<int>((mel_desc >> 16) & 0xfu);
+  const float* wp = sm_melw + (mel_desc >> 20);
+  const float* pk = sm_region + ((mel_desc >> 8) & 0xffu) * kPStride;
+  const int clip = desc[kDescClip], t0 = desc[kDescT0], keep = desc[kDescKeep];
+  const bool rowmask = row >= desc[kDescMask + 2] && row < desc[kDescMask + 3];
+  const uint32_t live = frame_window(0, n_frames, t0), kept = frame_window(0, keep, t0),
+                 store = frame_window(0, n_frames < n_frames_out ? n_frames : n_frames_out, t0),
+                 tmask = frame_window(desc[kDescMask], desc[kDescMask + 1], t0);
+  float* dst = out + (static_cast<size_t>(clip) * NM + row) * n_frames_out + t0;
+  float mx = -INFINITY, mn_kept = INFINITY, mn_live = INFINITY;
+#pragma unroll 1
+  for (int f = f0; f < f0 + NF; ++f) {
+    float a = 0.0f;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) a = fmaf(wp[j * WS], pk[j * kPStride + f], a);
+    const float l2 = fast_log2(fmaxf(a, 1e-10f));
+    if ((live >> f) & 1u) {
+      mx = fmaxf(mx, l2);
+      mn_live = fminf(mn_live, l2);
+    }
+    if ((kept >> f) & 1u) mn_kept = fminf(mn_kept, l2);
+    if ((store >> f) & 1u) dst[f] = (rowmask || ((tmask >> f) & 1u)) ? mask_value : feature_of_l2(l2);
+  }
+  mx = warp_max(mx);
+  mn_kept = warp_min(mn_kept);
+  mn_live = warp_min(mn_live);
+  if ((threadIdx.x & 31) == 0) {
+    red[3 * warp] = mx;
+    red[3 * warp + 1] = mn_kept;
+    red[3 * warp + 2] = mn_live;
+  }
 }
 
 // ---- deferred fix-up of one tile (only tiles that need it, see `tile_needs_fixup`) -----------------------------------
-// The mel phase wrote v = (L + 4) / 4 with masks applied.  What may still be missing once the clip's max / min are
-// known: the floor max(L, max - 8)  ==  max(v, (max - 8 + 4) / 4)  (monotone map, exact), and the min-value pad of
-// the frames beyond the kept part (data/utils.py:380-404).  Masked cells keep the mask value.
+// The mel phase wrote the feature with masks applied.  What may still be missing once the clip's max / min are known: the
+// floor max(feature, floor_feature(max)) and the min-value pad of the frames beyond the kept part (data/utils.py:380-404).
+// Masked cells keep the mask value.
 struct FixupArgs {
   float* out;
   const ClipStat* stats;
@@ -424,9 +470,9 @@ __device__ __forceinline__ int kept_frames(const int32_t* n_valid, int clip, int
   return keep;
 }
 
-// does tile (clip, t0) still differ from its final value?  tile_min = min log10(mel) over the tile's live cells
+// does tile (clip, t0) still differ from its final value?  tile_min = min L2 over the tile's live cells
 __device__ __forceinline__ bool tile_needs_fixup(float tile_min, uint32_t max_enc, int t0, int keep, int n_frames_out) {
-  const bool floor_binds = tile_min < dec_ordered(max_enc) - 8.0f;
+  const bool floor_binds = feature_of_l2(tile_min) < floor_feature(dec_ordered(max_enc));
   const int hi = t0 + kTileFrames < n_frames_out ? t0 + kTileFrames : n_frames_out;
   const bool has_pad = (t0 > keep ? t0 : keep) < hi;
   return floor_binds || has_pad;
@@ -436,13 +482,10 @@ template <int NM>
 __device__ __noinline__ void fixup_tile(const FixupArgs p, int tagged_tile, int clip, int tid) {
   const bool silent = (tagged_tile & kSilentBit) != 0;   // nothing was written yet: every cell is the clamp constant
   const int tile = tagged_tile & kTileIdMask;
-  const float vsilent = fmaf(silent_log_mel(), 0.25f, 1.0f);
+  const float vsilent = feature_of_l2(silent_l2());
   const ClipStat* st = p.stats + clip;
-  const float lmax = dec_ordered(__ldcg(&st->max_enc));
-  const float lmin = dec_ordered(~__ldcg(&st->min_inv));
-  const float floorv = lmax - 8.0f;
-  const float floorn = fmaf(floorv, 0.25f, 1.0f);
-  const float padv = fmaf(fmaxf(lmin, floorv), 0.25f, 1.0f);
+  const float floorn = floor_feature(dec_ordered(__ldcg(&st->max_enc)));
+  const float padv = fmaxf(feature_of_l2(dec_ordered(~__ldcg(&st->min_inv))), floorn);
   const int keep = kept_frames(p.n_valid, clip, p.n_frames);
   int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
   if (p.masks != nullptr) {
@@ -453,48 +496,46 @@ __device__ __noinline__ void fixup_tile(const FixupArgs p, int tagged_tile, int 
   const int pitch = p.n_frames_out;
   float* base = p.out + static_cast<size_t>(clip) * NM * pitch;
   const int t0 = (tile - clip * p.tiles_per_clip) * kTileFrames;
-  {
-    if ((pitch & 3) == 0) {
-      constexpr int kGroups = kTileFrames / 4;                      // float4 groups per row (4)
-      constexpr int kVec = NM * kGroups;                            // float4 groups per tile
-      constexpr int kIters = (kVec + kThreads - 1) / kThreads;      // 4 (128 mel) / 2 (80 mel)
-      const int f = t0 + ((tid & (kGroups - 1)) << 2);              // kThreads % kGroups == 0: same column group every iter
-      if (f >= pitch) return;
-      float4 v[kIters];
+  if ((pitch & 3) == 0) {
+    constexpr int kGroups = kTileFrames / 4;                      // float4 groups per row (4)
+    constexpr int kVec = NM * kGroups;                            // float4 groups per tile
+    constexpr int kIters = (kVec + kThreads - 1) / kThreads;      // 4 (128 mel) / 2 (80 mel)
+    const int f = t0 + ((tid & (kGroups - 1)) << 2);              // kThreads % kGroups == 0: same column group every iter
+    if (f >= pitch) return;
+    float4 v[kIters];
 #pragma unroll
-      for (int it = 0; it < kIters; ++it) {
-        const int row = (tid + kThreads * it) / kGroups;
-        v[it] = make_float4(vsilent, vsilent, vsilent, vsilent);
-        if (!silent && row < NM && f < keep)
-          v[it] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * pitch + f));
-      }
+    for (int it = 0; it < kIters; ++it) {
+      const int row = (tid + kThreads * it) / kGroups;
+      v[it] = make_float4(vsilent, vsilent, vsilent, vsilent);
+      if (!silent && row < NM && f < keep)
+        v[it] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * pitch + f));
+    }
 #pragma unroll
-      for (int it = 0; it < kIters; ++it) {
-        const int row = (tid + kThreads * it) / kGroups;
-        if (row < NM) {
-          const bool rowmask = row >= mf0 && row < mf1;
-          float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+    for (int it = 0; it < kIters; ++it) {
+      const int row = (tid + kThreads * it) / kGroups;
+      if (row < NM) {
+        const bool rowmask = row >= mf0 && row < mf1;
+        float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int fc = f + c;
-            float r = (fc < keep) ? fmaxf(e[c], floorn) : padv;
-            if (rowmask || (fc >= mt0 && fc < mt1)) r = mv;
-            e[c] = r;
-          }
-          *reinterpret_cast<float4*>(base + static_cast<size_t>(row) * pitch + f) = make_float4(e[0], e[1], e[2], e[3]);
+        for (int c = 0; c < 4; ++c) {
+          const int fc = f + c;
+          float r = (fc < keep) ? fmaxf(e[c], floorn) : padv;
+          if (rowmask || (fc >= mt0 && fc < mt1)) r = mv;
+          e[c] = r;
         }
+        *reinterpret_cast<float4*>(base + static_cast<size_t>(row) * pitch + f) = make_float4(e[0], e[1], e[2], e[3]);
       }
-    } else {
-      for (int idx = tid; idx < NM * kTileFrames; idx += kThreads) {
-        const int row = idx / kTileFrames;
-        const int f = t0 + (idx % kTileFrames);
-        if (f >= pitch) continue;
-        float* ptr = base + static_cast<size_t>(row) * pitch + f;
-        float r = padv;
-        if (f < keep) r = fmaxf(silent ? vsilent : __ldcg(ptr), floorn);
-        if ((row >= mf0 && row < mf1) || (f >= mt0 && f < mt1)) r = mv;
-        *ptr = r;
-      }
+    }
+  } else {
+    for (int idx = tid; idx < NM * kTileFrames; idx += kThreads) {
+      const int row = idx / kTileFrames;
+      const int f = t0 + (idx % kTileFrames);
+      if (f >= pitch) continue;
+      float* ptr = base + static_cast<size_t>(row) * pitch + f;
+      float r = padv;
+      if (f < keep) r = fmaxf(silent ? vsilent : __ldcg(ptr), floorn);
+      if ((row >= mf0 && row < mf1) || (f >= mt0 && f < mt1)) r = mv;
+      *ptr = r;
     }
   }
 }
@@ -508,11 +549,16 @@ __device__ __forceinline__ FixupArgs make_fixup_args(const FrontendParams& p) {
 }
 
 // sm_ctl slots
-// [kCtlDesc .. +5] and [kCtlDesc + kCtlSlot .. +5] = two tile descriptors {id, clip, first frame, kind, PCM element offset
-// (lo, hi)}: the tile being worked on and the one after it, swapping roles every iteration.  Every phase re-reads the few
-// fields it needs from here instead of carrying them in registers across the FFT stages.
-enum { kCtlDesc = 0, kCtlSlot = 8, kCtlReady = 76, kCtlDrain = 77, kCtlDrainClip = 78, kCtlNRing = 79, kCtlChain = 80, kCtlList = 16, kCtlListClip = 24, kCtlRing = 32,
-       kCtlRingClip = 40, kCtlRingMin = 48, kCtlRed = 56, kCtlMbar = 72, kCtlMemo = 74 };   // kCtlRed: 3 floats per warp (max, kept min, live min)
+// [kCtlDesc .. +15] and [kCtlDesc + kCtlSlot .. +15] = two tile descriptors (kDesc*): the tile being worked on and the one
+// after it, swapping roles every iteration.  Every phase re-reads the few fields it needs from here instead of carrying
+// them in registers across the FFT stages.  The pending-tile FIFO (kCtlRing*, kCtlHead, kCtlCount, kCtlChain) belongs to
+// thread 0 alone.
+enum { kCtlDesc = 0, kCtlSlot = 16, kCtlRing = 32, kCtlRingClip = 48, kCtlRingMin = 64,
+       kCtlRed = 80,    // 3 floats per warp (max, kept min, live min)
+       kCtlMbar = 96,   // 8 bytes
+       kCtlMemo = 100,  // describe_tile's per-clip memo: clip, len, keep, -, mask[4]
+       kCtlHead = 108, kCtlCount = 109, kCtlChain = 110, kCtlReady = 111, kCtlReadyClip = 112, kCtlDrain = 113, kCtlDrainClip = 114 };
+static_assert(kCtlDrainClip < kCtlInts && kCtlRed + 3 * kWarps <= kCtlMbar && kRing == 16, "sm_ctl layout");
 
 // how a tile's PCM reaches shared memory
 enum { kTileEdge = 0,      // reflection / zero extension / unaligned source: scalar staging
@@ -520,60 +566,108 @@ enum { kTileEdge = 0,      // reflection / zero extension / unaligned source: sc
        kTileSilent = 2,    // every sample it touches is zero padding: no FFT, the fix-up later writes the constant rows;
                            // this is the FIRST such tile of its clip and records the clamp value in the clip statistics
        kTileSilentRest = 3 };  // a later tile of the same silent tail: the statistics are already in, only counted
-// thread 0: describe tile `t` for everybody (one division and one lengths[] load per tile instead of 160)
 __device__ __forceinline__ bool tile_is_silent(int t0, int len, int n_total) {
   const int g0 = t0 * kHop - kNfft / 2;
   const int last = g0 + kTileSamples - 1;  // beyond n_total the samples are mirrored around n_total - 1
   return len == 0 || (g0 >= len && (last < n_total || 2 * (n_total - 1) - last >= len));
 }
 
-struct TileGeom {   // the few launch constants describe_tile needs (passed by value: it is a real call, thread 0 only)
+struct TileGeom {   // the few launch constants describe_tile needs
   const void* pcm;
   const int32_t* lengths;
+  const int32_t* n_valid;
+  const int32_t* masks;
   int64_t clip_stride;
-  int32_t n_samples, n_total, n_frames, tiles_per_clip, total_tiles;
+  int32_t n_samples, n_total, n_frames, n_frames_out, tiles_per_clip, total_tiles;
+  uint32_t tpc_magic;   // floor(2^32 / tiles_per_clip)
+  int32_t vec_ok;
 };
 __device__ __forceinline__ TileGeom tile_geom(const FrontendParams& q) {
   TileGeom g;
-  g.pcm = q.pcm; g.lengths = q.lengths; g.clip_stride = q.clip_stride; g.n_samples = q.n_samples; g.n_total = q.n_total;
-  g.n_frames = q.n_frames; g.tiles_per_clip = q.tiles_per_clip; g.total_tiles = q.total_tiles;
+  g.pcm = q.pcm; g.lengths = q.lengths; g.n_valid = q.n_valid; g.masks = q.masks; g.clip_stride = q.clip_stride;
+  g.n_samples = q.n_samples; g.n_total = q.n_total; g.n_frames = q.n_frames; g.n_frames_out = q.n_frames_out;
+  g.tiles_per_clip = q.tiles_per_clip; g.total_tiles = q.total_tiles; g.tpc_magic = q.tpc_magic; g.vec_ok = q.vec_ok;
   return g;
 }
 
+// thread 0: describe tile `t` for everybody (one multiply-high instead of 160 divisions; lengths[], n_valid[] and the
+// mask intervals are loaded once per clip and memoised in shared memory -- consecutive tiles mostly share the clip)
 // (forced inline: as a real call this sat on thread 0's critical path before a CTA barrier and cost 2.5 % overall)
-template <typename PcmT>
+template <int NM, typename PcmT>
 __device__ __forceinline__ void describe_tile(const TileGeom p, int t, int* __restrict__ slot, int* __restrict__ memo) {
-  int& memo_clip = memo[0];   // lengths[] of the last clip described (kept in shared memory, not in registers)
-  int& memo_len = memo[1];
-  int clip = 0, t0 = 0, interior = kTileEdge;
-  long long off = 0;
+  int clip = 0, t0 = 0, kind = kTileEdge, flags = 0, keep = 0;
+  long long off = 0, out_off = 0;
+  int4 mk = make_int4(0, 0, 0, 0);
   if (t < p.total_tiles) {
-    clip = t / p.tiles_per_clip;
+    clip = static_cast<int>(__umulhi(static_cast<uint32_t>(t), p.tpc_magic));
+    if (t - clip * p.tiles_per_clip >= p.tiles_per_clip) ++clip;   // the magic number undershoots by at most one
     t0 = (t - clip * p.tiles_per_clip) * kTileFrames;
-    if (t0 < p.n_frames) {
-      if (clip != memo_clip) {  // consecutive tiles mostly belong to the same clip: one lengths[] load per clip
-        int len = p.n_samples;
-        if (p.lengths != nullptr) {
-          const int l = __ldg(p.lengths + clip);
-          len = l < 0 ? 0 : (l < len ? l : len);
-        }
-        memo_clip = clip;
-        memo_len = len;
+    if (clip != memo[0]) {
+      int len = p.n_samples;
+      if (p.lengths != nullptr) {
+        const int l = __ldg(p.lengths + clip);
+        len = l < 0 ? 0 : (l < len ? l : len);
       }
-      const int len = memo_len;
+      int kp = p.n_frames;
+      if (p.n_valid != nullptr) {
+        const int nv = __ldg(p.n_valid + clip);
+        if (nv >= 0 && nv < kp) kp = nv;
+      }
+      int4 m = make_int4(0, 0, 0, 0);
+      if (p.masks != nullptr) m = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
+      memo[0] = clip; memo[1] = len; memo[2] = kp;
+      *reinterpret_cast<int4*>(memo + 4) = m;
+    }
+    keep = memo[2];
+    mk = *reinterpret_cast<const int4*>(memo + 4);
+    out_off = static_cast<long long>(clip) * NM * p.n_frames_out + t0;
+    if (t0 < p.n_frames) {
+      const int len = memo[1];
       const int g0 = t0 * kHop - kNfft / 2;
       off = static_cast<long long>(clip) * p.clip_stride + g0;
       if (tile_is_silent(t0, len, p.n_total)) {
         // silence is a suffix of the clip: only its first tile does any bookkeeping
-        interior = (t0 == 0 || !tile_is_silent(t0 - kTileFrames, len, p.n_total)) ? kTileSilent : kTileSilentRest;
+        kind = (t0 == 0 || !tile_is_silent(t0 - kTileFrames, len, p.n_total)) ? kTileSilent : kTileSilentRest;
       } else if (tile_is_interior(reinterpret_cast<const PcmT*>(p.pcm) + off - g0, g0, len)) {
-        interior = kTileInterior;
+        kind = kTileInterior;
       }
+      const int t1 = t0 + kTileFrames;
+      const bool all_kept = t1 <= keep;
+      const bool no_tmask = mk.y <= mk.x || mk.y <= t0 || mk.x >= t1;
+      const bool all_tmask = mk.x <= t0 && mk.y >= t1;
+      if (p.vec_ok && (all_kept || keep <= t0) && t1 <= p.n_frames && t1 <= p.n_frames_out && (no_tmask || all_tmask))
+        flags = kFlagFast | (all_kept ? kFlagAllKept : 0) | (all_tmask ? kFlagAllMasked : 0);
     }
   }
-  slot[0] = t; slot[1] = clip; slot[2] = t0; slot[3] = interior;
-  slot[4] = static_cast<int>(off & 0xffffffffll); slot[5] = static_cast<int>(off >> 32);
+  *reinterpret_cast<int4*>(slot) = make_int4(t, clip, t0, kind);
+  *reinterpret_cast<int4*>(slot + 4) = make_int4(static_cast<int>(off & 0xffffffffll), static_cast<int>(off >> 32), flags, keep);
+  *reinterpret_cast<int4*>(slot + 8) = mk;
+  *reinterpret_cast<int2*>(slot + 12) = make_int2(static_cast<int>(out_off & 0xffffffffll), static_cast<int>(out_off >> 32));
 }
+
+// acquire read of a clip's completion counter, then its maximum: pairs with the publisher's dependent atomics
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+
+// development build only (-DWFT_TIMELINE): lane 0 of every warp stamps %clock at 13 points of its first kTlIters tile
+// iterations; tools/timeline.cu turns the stamps into per-phase work / barrier-wait times
+#ifdef WFT_TIMELINE
+constexpr int kTlIters = 32, kTlPoints = 16, kTlMaxCtas = 148 * 6;
+__device__ uint32_t g_timeline[kTlMaxCtas * kTlIters * kWarps * kTlPoints];
+#define WFT_TL(k)                                                                                                      \
+  do {                                                                                                                 \
+    if (lane == 0 && tl_iter < kTlIters && blockIdx.x < kTlMaxCtas) {                                                  \
+      uint32_t c_;                                                                                                     \
+      asm volatile("mov.u32 %0, %%clock;" : "=r"(c_));                                                                 \
+      g_timeline[((blockIdx.x * kTlIters + tl_iter) * kWarps + warp) * kTlPoints + (k)] = c_;                          \
+    }                                                                                                                  \
+  } while (0)
+#else
+#define WFT_TL(k) do {} while (0)
+#endif
 
 template <int NM, typename PcmT>
 __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendParams p) {
@@ -619,40 +713,45 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   constexpr int kTmaThread = kThreads - 32;                               // the thread that issues the bulk copies
   if (tid == 0) {
     sm_ctl[kCtlMemo] = -1;
-    sm_ctl[kCtlNRing] = 0;
+    sm_ctl[kCtlHead] = 0;
+    sm_ctl[kCtlCount] = 0;
     sm_ctl[kCtlChain] = -1;
     mbar_init(audio_bar, 1);
-    describe_tile<PcmT>(tile_geom(p), static_cast<int>(atomicAdd(p.tile_counter, 1u)), sm_ctl + kCtlDesc, sm_ctl + kCtlMemo);
+    describe_tile<NM, PcmT>(tile_geom(p), static_cast<int>(atomicAdd(p.tile_counter, 1u)), sm_ctl + kCtlDesc, sm_ctl + kCtlMemo);
   }
   __syncthreads();
   // a tile of kind kTileInterior always arrives by TMA: the first one is sent here, every later one under the tile before it
-  if (tid == kTmaThread && sm_ctl[kCtlDesc + 3] == kTileInterior) {
-    const long long off = (static_cast<long long>(sm_ctl[kCtlDesc + 5]) << 32) | static_cast<unsigned int>(sm_ctl[kCtlDesc + 4]);
+  if (tid == kTmaThread && sm_ctl[kCtlDesc + kDescKind] == kTileInterior) {
+    const long long off = (static_cast<long long>(sm_ctl[kCtlDesc + kDescPcmHi]) << 32) | static_cast<unsigned int>(sm_ctl[kCtlDesc + kDescPcmLo]);
     prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
   }
-  // loop state in ONE register: bit 3 (kCtlSlot) = descriptor slot of the CURRENT tile, bit 0 = parity of the audio mbarrier
+  // loop state in ONE register: bit 4 (kCtlSlot) = descriptor slot of the CURRENT tile, bit 0 = parity of the audio mbarrier
   int lstate = 0;
 
-  // mel phase role of this thread (fixed for the whole launch): row | start_bin << 8 | first_quad << 16 | weight_offset << 18
+  // mel phase role of this thread (fixed for the whole launch): row | start_bin << 8 | first_frame << 16 | weight_offset << 20
   // (kept packed in ONE register across the FFT stages; unpacked again in every mel phase)
   const uint32_t mel_desc = (NM == 128 ? g_mel128_thread : g_mel80_thread)[tid];
   const uint32_t tiles_per_clip_u = static_cast<uint32_t>(p.tiles_per_clip);
 
-  // warp-0 scheduler state lives in sm_ctl (not in registers): ring of tiles whose fix-up is pending, its fill count
-  // kCtlNRing and the head kCtlChain of the parked chain
-
+#ifdef WFT_TIMELINE
+  int tl_iter = -1;
+#endif
   for (;;) {
-    // current tile: {id, clip, t0, kind} at DESC; thread 0 describes the next tile at NDESC (behind this tile's first barrier)
-    // (one 16-byte read {id, clip, t0, kind} per phase that needs them)
+#ifdef WFT_TIMELINE
+    ++tl_iter;
+#endif
+    // current tile at DESC; thread 0 describes the next tile at NDESC (behind this tile's first barrier)
 #define DESC (sm_ctl + (launder(lstate) & kCtlSlot))
 #define NDESC (sm_ctl + ((launder(lstate) & kCtlSlot) ^ kCtlSlot))
 #define DESC4 (*reinterpret_cast<const int4*>(DESC))
     const int4 d_top = DESC4;
     if (d_top.x >= p.total_tiles) break;
+    WFT_TL(0);
     // claim the tile AFTER this one now; the answer is consumed two barriers later (latency hidden by stage A)
     int nxt_claim = 0;
     if (tid == 0) nxt_claim = static_cast<int>(atomicAdd(p.tile_counter, 1u));
-    uint32_t seen_max = 0u, seen_done = 0u;  // warp 0: snapshot of the clip of ring[lane] (max_enc, done), sampled early
+    // thread 0: (max, done) of the clips of the two oldest pending tiles, sampled early, looked at after the mel phase
+    uint32_t seen_max0 = 0u, seen_done0 = 0u, seen_max1 = 0u, seen_done1 = 0u;
 
     if (d_top.z < p.n_frames && d_top.w != kTileSilent && d_top.w != kTileSilentRest) {
       // stage 0 ---------------------------------------------------------------------------------------------
@@ -670,6 +769,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         mbar_wait(audio_bar, static_cast<uint32_t>(lstate) & 1u);
         lstate ^= 1;
       }
+      WFT_TL(1);
 
       // stage A: thread (q, n2 = r): x[n1] = w[20 n1 + n2] * (pa + i pb)[20 n1 + n2] ------------------------------
       {
@@ -692,8 +792,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
             }
           }
         }
+        WFT_TL(2);
         __syncthreads();  // audio is dead from here on: the region becomes the exchange buffer
-        // (letting half 0 run ahead here with bar.arrive / bar.sync was measured 2-3 % slower)
+        WFT_TL(3);
         dft20(x);
         const auto [q, r] = pair_coord_a();
         const float4* t4 = reinterpret_cast<const float4*>(sm_tw + r * kTwRow);
@@ -706,8 +807,10 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           e2[k1 * (kRowStride / 2)] = make_float2(x[k1].x * t.z - x[k1].y * t.w, fmaf(x[k1].x, t.w, x[k1].y * t.z));
         }
       }
-      if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, NDESC, sm_ctl + kCtlMemo);
+      if (tid == 0) describe_tile<NM, PcmT>(tile_geom(p), nxt_claim, NDESC, sm_ctl + kCtlMemo);
+      WFT_TL(4);
       __syncthreads();
+      WFT_TL(5);
 
       // stage B: thread (q, k1 = r): Z[k1 + 20 k2] = DFT20 over n2.  The lower half (k2 < 10, bins k1 + 20 k2 <= 199)
       // stays in registers; the upper half is what the mirror thread (q, 20 - k1) needs and travels by warp shuffle.
@@ -737,16 +840,26 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           for (int m = 0; m < 10; ++m)
             mz[m] = make_float2(__shfl_sync(0xffffffffu, y[10 + m].x, src), __shfl_sync(0xffffffffu, y[10 + m].y, src));
         }
+        WFT_TL(6);
         __syncthreads();  // exchange is dead: the region becomes power tile (bottom) + next audio tile (top)
+        WFT_TL(7);
         // prefetch the NEXT tile's PCM into the top of the region (its descriptor stays in sm_ctl until the loop ends)
-        if (NDESC[3] == kTileInterior) {
-          const long long off = (static_cast<long long>(NDESC[5]) << 32) | static_cast<unsigned int>(NDESC[4]);
-          if (tid == kTmaThread) prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
+        if (tid == kTmaThread && NDESC[kDescKind] == kTileInterior) {
+          const long long off = (static_cast<long long>(NDESC[kDescPcmHi]) << 32) | static_cast<unsigned int>(NDESC[kDescPcmLo]);
+          prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
         }
-        if (warp == 0 && lane < sm_ctl[kCtlNRing]) {
-          const uint4 st = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
-          seen_max = st.x;
-          seen_done = st.z;
+        if (tid == 0) {
+          const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
+          if (n > 0) {
+            const ClipStat* st = p.stats + sm_ctl[kCtlRingClip + head];
+            seen_done0 = ld_acquire(&st->done);
+            seen_max0 = ld_relaxed(&st->max_enc);
+          }
+          if (n > 1) {
+            const ClipStat* st = p.stats + sm_ctl[kCtlRingClip + ((head + 1) & (kRing - 1))];
+            seen_done1 = ld_acquire(&st->done);
+            seen_max1 = ld_relaxed(&st->max_enc);
+          }
         }
 
         // power tile [bin][frame]: the pair's two frames are neighbours, one 8-byte store per bin
@@ -774,136 +887,117 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           }
         }
       }
+      WFT_TL(8);
       __syncthreads();
+      WFT_TL(9);
 
-      // mel phase: thread <-> (mel row, 16 or 8 frames) -------------------------------------------------------------
+      // mel phase: thread <-> (mel row, NF frames) -------------------------------------------------------------
       {
-        const int4 d_mel = DESC4;
-        const int clip = d_mel.y, t0 = d_mel.z;
-        const int mel_row = static_cast<int>(mel_desc & 0xffu);
-        const int mel_q0 = static_cast<int>((mel_desc >> 16) & 3u);
-        const float* mel_p = sm_region + ((mel_desc >> 8) & 0xffu) * kPStride + 4 * mel_q0;
-        const float* mel_w = sm_melw + (mel_desc >> 18);
-        int mel_cls = 0;
-        bool mel_wide = false;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w)
-          if (warp == w) {
-            mel_cls = mel_warp_class<NM>(w);
-            mel_wide = mel_class_quads<NM>(mel_warp_class<NM>(w)) == 4;
+        const int* desc = DESC;
+        const int flags = desc[kDescFlags];
+        float* red = reinterpret_cast<float*>(sm_ctl + kCtlRed);
+        if (flags & kFlagFast) {
+          const int4 mk = *reinterpret_cast<const int4*>(desc + kDescMask);
+          const int2 oo = *reinterpret_cast<const int2*>(desc + kDescOutLo);
+          const int mel_row = static_cast<int>(mel_desc & 0xffu);
+          const int mel_f0 = static_cast<int>((mel_desc >> 16) & 0xfu);
+          const float* mel_p = sm_region + ((mel_desc >> 8) & 0xffu) * kPStride + mel_f0;
+          const float* mel_w = sm_melw + (mel_desc >> 20);
+          const bool masked = (mel_row >= mk.z && mel_row < mk.w) || (flags & kFlagAllMasked) != 0;
+          const float sc = masked ? 0.0f : kFeatScale;            // masked cell: 0 * L2 + mask_value
+          const float of = masked ? p.mask_value : 1.0f;
+          const long long out_off = (static_cast<long long>(oo.y) << 32) | static_cast<unsigned int>(oo.x);
+          float* dst = p.out + out_off + (mel_row * p.n_frames_out + mel_f0);
+          float mx = -INFINITY, mn = INFINITY;
+          // warp-uniform dispatch: one fully unrolled body per warp of the plan
+          if (warp == 0) mel_fast<mel_warp_taps<NM>(0), mel_warp_frames<NM>(0), mel_warp_wstride<NM>(0)>(mel_p, mel_w, sc, of, dst, mx, mn);
+          else if (warp == 1) mel_fast<mel_warp_taps<NM>(1), mel_warp_frames<NM>(1), mel_warp_wstride<NM>(1)>(mel_p, mel_w, sc, of, dst, mx, mn);
+          else if (warp == 2) mel_fast<mel_warp_taps<NM>(2), mel_warp_frames<NM>(2), mel_warp_wstride<NM>(2)>(mel_p, mel_w, sc, of, dst, mx, mn);
+          else if (warp == 3) mel_fast<mel_warp_taps<NM>(3), mel_warp_frames<NM>(3), mel_warp_wstride<NM>(3)>(mel_p, mel_w, sc, of, dst, mx, mn);
+          else mel_fast<mel_warp_taps<NM>(4), mel_warp_frames<NM>(4), mel_warp_wstride<NM>(4)>(mel_p, mel_w, sc, of, dst, mx, mn);
+          mx = warp_max(mx);
+          mn = warp_min(mn);
+          if (lane == 0) {
+            red[3 * warp] = mx;
+            red[3 * warp + 1] = (flags & kFlagAllKept) ? mn : INFINITY;
+            red[3 * warp + 2] = mn;
           }
-        // 32-byte stores need an aligned `out` and a row pitch that is a multiple of 8 frames
-        const bool out_vec_ok = (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && (p.n_frames_out & 7) == 0;
-        const int keep = kept_frames(p.n_valid, clip, p.n_frames);
-        int4 mk = make_int4(0, 0, 0, 0);
-        if (p.masks != nullptr) mk = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
-        const bool rowmask = mel_row >= mk.z && mel_row < mk.w;
-        const float sc = rowmask ? 0.0f : 0.25f;            // masked row: 0 * L + mask_value
-        const float of = rowmask ? p.mask_value : 1.0f;
-        // fast tile (uniform over the CTA): all 16 frames live and stored, none inside the time mask, and either all of
-        // them kept or none (frames beyond the partial-segment cut still count for the max; the fix-up pads them later)
-        const bool all_kept = t0 + kTileFrames <= keep;
-        const bool fast = out_vec_ok && (all_kept || keep <= t0) && t0 + kTileFrames <= p.n_frames &&
-                          t0 + kTileFrames <= p.n_frames_out && (mk.y <= t0 || mk.x >= t0 + kTileFrames || mk.y <= mk.x);
-        float* dst = p.out + (static_cast<size_t>(clip) * NM + mel_row) * p.n_frames_out + t0 + 4 * mel_q0;
-
-        float mx = -INFINITY, mn_kept = INFINITY, mn_live = INFINITY;
-        MelEdge e;
-        if (!fast) {
-          const int sh = 4 * mel_q0;
-          e.live = frame_window(0, p.n_frames, t0) >> sh;
-          e.kept = frame_window(0, keep, t0) >> sh;
-          e.store = frame_window(0, p.n_frames < p.n_frames_out ? p.n_frames : p.n_frames_out, t0) >> sh;
-          e.tmask = frame_window(mk.x, mk.y, t0) >> sh;
-        }
-        const int n_halves = (mel_any_wide<NM>() && mel_wide) ? 2 : 1;   // warp-uniform
-#pragma unroll 1
-        for (int half = 0; half < n_halves; ++half) {
-          cpx acc[4];
-          mel_dispatch<NM, 0>(mel_cls, mel_p, mel_w, acc);
-          if (fast) {
-            mel_post8<true>(acc, sc, of, p.mask_value, dst, e, mx, mn_kept, mn_live);
-          } else {
-            mel_post8<false>(acc, sc, of, p.mask_value, dst, e, mx, mn_kept, mn_live);
-            e.live >>= 8; e.kept >>= 8; e.store >>= 8; e.tmask >>= 8;
-          }
-          mel_p += 8;
-          dst += 8;
-        }
-        if (fast && all_kept) mn_kept = mn_live;
-        mx = warp_max(mx);
-        mn_kept = warp_min(mn_kept);
-        mn_live = warp_min(mn_live);
-        if (lane == 0) {
-          float* red = reinterpret_cast<float*>(sm_ctl + kCtlRed) + 3 * warp;
-          red[0] = mx;
-          red[1] = mn_kept;
-          red[2] = mn_live;
+        } else {
+          mel_edge<NM>(sm_region, sm_melw, desc, mel_desc, p.out, p.n_frames, p.n_frames_out, p.mask_value, red);
         }
       }
     } else {
       // nothing to compute: a pad-only tile (n_frames_out > n_frames) or a silent tile (all-zero PCM: every mel value is
       // the 1e-10 clamp, so only its statistics are recorded here and the fix-up later writes the constant rows)
       __syncthreads();  // the previous tile's last readers of the other descriptor slot are done
-      if (tid == 0) describe_tile<PcmT>(tile_geom(p), nxt_claim, NDESC, sm_ctl + kCtlMemo);
+      if (tid == 0) describe_tile<NM, PcmT>(tile_geom(p), nxt_claim, NDESC, sm_ctl + kCtlMemo);
       __syncthreads();
-      if (NDESC[3] == kTileInterior && tid == kTmaThread) {
-        const long long off = (static_cast<long long>(NDESC[5]) << 32) | static_cast<unsigned int>(NDESC[4]);
+      if (tid == kTmaThread && NDESC[kDescKind] == kTileInterior) {
+        const long long off = (static_cast<long long>(NDESC[kDescPcmHi]) << 32) | static_cast<unsigned int>(NDESC[kDescPcmLo]);
         prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
       }
-      if (warp == 0 && lane < sm_ctl[kCtlNRing]) {
-        const uint4 st = ld_stat(p.stats + sm_ctl[kCtlRingClip + lane]);
-        seen_max = st.x;
-        seen_done = st.z;
+      if (tid == 0) {
+        const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
+        if (n > 0) {
+          const ClipStat* st = p.stats + sm_ctl[kCtlRingClip + head];
+          seen_done0 = ld_acquire(&st->done);
+          seen_max0 = ld_relaxed(&st->max_enc);
+        }
+        if (n > 1) {
+          const ClipStat* st = p.stats + sm_ctl[kCtlRingClip + ((head + 1) & (kRing - 1))];
+          seen_done1 = ld_acquire(&st->done);
+          seen_max1 = ld_relaxed(&st->max_enc);
+        }
       }
       if (lane == 0) {
         const int clip = d_top.y, t0 = d_top.z, kind = d_top.w;   // (short path: the loop-top read is still in registers)
         const bool silent = (kind == kTileSilent || kind == kTileSilentRest) && t0 < p.n_frames;
         const bool silent_head = kind == kTileSilent;   // only the first silent tile of a clip touches the clip statistics
         float* red = reinterpret_cast<float*>(sm_ctl + kCtlRed) + 3 * warp;
-        const float lc = silent_log_mel();
+        const float lc = silent_l2();
         red[0] = (silent && silent_head) ? lc : -INFINITY;                                                 // live frames
         red[1] = (silent && silent_head && t0 < kept_frames(p.n_valid, clip, p.n_frames)) ? lc : INFINITY;  // kept frames
         red[2] = silent ? lc : INFINITY;
       }
     }
 
-    // warp 0 looks at the pending ring: a tile whose clip is complete either needs the fix-up (floor binds or it
-    // carries pad frames) or is already final and simply leaves the ring; everything else keeps waiting
-    if (warp == 0) {
-      const bool pending = lane < sm_ctl[kCtlNRing];
-      const int mine = pending ? sm_ctl[kCtlRing + lane] : -1;
-      const int mine_clip = pending ? sm_ctl[kCtlRingClip + lane] : 0;
-      const float mine_min = pending ? __int_as_float(sm_ctl[kCtlRingMin + lane]) : 0.0f;
-      const bool complete = pending && seen_done >= tiles_per_clip_u;
-      bool ready = false;
-      if (complete) {
-        const int mt0 = ((mine & kTileIdMask) - mine_clip * p.tiles_per_clip) * kTileFrames;
-        ready = (mine & kSilentBit) != 0 ||
-                tile_needs_fixup(mine_min, seen_max, mt0, kept_frames(p.n_valid, mine_clip, p.n_frames), p.n_frames_out);
+    // thread 0 looks at the (up to) two oldest pending tiles: a tile whose clip is complete either needs the fix-up (the
+    // floor binds or it carries pad frames) or is already final and simply leaves the FIFO; one fix-up per iteration
+    if (tid == 0) {
+      const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
+      int ready = -1, ready_clip = 0, pops = 0;
+      if (n > 0 && seen_done0 >= tiles_per_clip_u) {
+        const int e = sm_ctl[kCtlRing + head], ec = sm_ctl[kCtlRingClip + head];
+        pops = 1;
+        if ((e & kSilentBit) != 0 ||
+            tile_needs_fixup(__int_as_float(sm_ctl[kCtlRingMin + head]), seen_max0, ((e & kTileIdMask) - ec * p.tiles_per_clip) * kTileFrames,
+                             kept_frames(p.n_valid, ec, p.n_frames), p.n_frames_out)) {
+          ready = e;
+          ready_clip = ec;
+        } else if (n > 1 && seen_done1 >= tiles_per_clip_u) {
+          const int h1 = (head + 1) & (kRing - 1);
+          const int e1 = sm_ctl[kCtlRing + h1], ec1 = sm_ctl[kCtlRingClip + h1];
+          pops = 2;
+          if ((e1 & kSilentBit) != 0 ||
+              tile_needs_fixup(__int_as_float(sm_ctl[kCtlRingMin + h1]), seen_max1, ((e1 & kTileIdMask) - ec1 * p.tiles_per_clip) * kTileFrames,
+                               kept_frames(p.n_valid, ec1, p.n_frames), p.n_frames_out)) {
+            ready = e1;
+            ready_clip = ec1;
+          }
+        }
       }
-      const uint32_t ready_mask = __ballot_sync(0xffffffffu, ready);
-      const uint32_t wait_mask = __ballot_sync(0xffffffffu, pending && !complete);
-      const uint32_t below = (1u << lane) - 1u;
-      __syncwarp();
-      if (ready) {
-        sm_ctl[kCtlList + __popc(ready_mask & below)] = mine;
-        sm_ctl[kCtlListClip + __popc(ready_mask & below)] = mine_clip;
-      } else if (pending && !complete) {
-        sm_ctl[kCtlRing + __popc(wait_mask & below)] = mine;
-        sm_ctl[kCtlRingClip + __popc(wait_mask & below)] = mine_clip;
-        sm_ctl[kCtlRingMin + __popc(wait_mask & below)] = __float_as_int(mine_min);
-      }
-      if (lane == 0) {
-        sm_ctl[kCtlNRing] = __popc(wait_mask);
-        sm_ctl[kCtlReady] = __popc(ready_mask);
-      }
+      sm_ctl[kCtlHead] = (head + pops) & (kRing - 1);
+      sm_ctl[kCtlCount] = n - pops;
+      sm_ctl[kCtlReady] = ready;
+      sm_ctl[kCtlReadyClip] = ready_clip;
     }
-    __syncthreads();  // tile finished: power tile free, ready list and per-warp max/min visible
+    WFT_TL(10);
+    __syncthreads();  // tile finished: power tile free, ready tile and per-warp max/min visible
+    WFT_TL(11);
 
     // publish the tile's statistics: two returning atomics, then the completion count with a true data dependency on
     // their results (through p.zero) -- no fence, so nobody waits for the tile's stores to drain.  The tile itself
-    // joins the pending ring (or is parked: a CTA never waits while tiles are unclaimed).
+    // joins the pending FIFO (or is parked: a CTA never waits while tiles are unclaimed).
     if (warp == 0) {
       const float* red = reinterpret_cast<const float*>(sm_ctl + kCtlRed) + 3 * (lane < kWarps ? lane : 0);
       float mx = lane < kWarps ? red[0] : -INFINITY;
@@ -921,25 +1015,24 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         if (mx > -INFINITY) dep |= atomicMax(&cs->max_enc, enc_ordered(mx));
         if (mn_kept < INFINITY) dep |= atomicMax(&cs->min_inv, ~enc_ordered(mn_kept));
         const int tagged = cur | (silent ? kSilentBit : 0);
-        const int n_ring = sm_ctl[kCtlNRing];
-        if (n_ring < kMaxPending) {
-          sm_ctl[kCtlRing + n_ring] = tagged;
-          sm_ctl[kCtlRingClip + n_ring] = clip;
-          sm_ctl[kCtlRingMin + n_ring] = __float_as_int(mn_live);
-          sm_ctl[kCtlNRing] = n_ring + 1;
+        const int n = sm_ctl[kCtlCount];
+        if (n < kRing) {
+          const int slot = (sm_ctl[kCtlHead] + n) & (kRing - 1);
+          sm_ctl[kCtlRing + slot] = tagged;
+          sm_ctl[kCtlRingClip + slot] = clip;
+          sm_ctl[kCtlRingMin + slot] = __float_as_int(mn_live);
+          sm_ctl[kCtlCount] = n + 1;
         } else {
           p.next[cur] = sm_ctl[kCtlChain];           // parked tiles are re-examined (conservatively) in the drain
           sm_ctl[kCtlChain] = tagged;
         }
-        // (deferring this count -- to the next tile's gather, or with the two results kept apart -- costs registers the
-        // gather does not have: measured slower every time)
         atomicAdd(&cs->done, 1u + (dep & p.zero));
       }
       __syncwarp();
     }
-    const int n_ready = sm_ctl[kCtlReady];
-#pragma unroll 1
-    for (int k = 0; k < n_ready; ++k) fixup_tile<NM>(make_fixup_args(p), sm_ctl[kCtlList + k], sm_ctl[kCtlListClip + k], tid);
+    const int ready = sm_ctl[kCtlReady];
+    if (ready >= 0) fixup_tile<NM>(make_fixup_args(p), ready, sm_ctl[kCtlReadyClip], tid);
+    WFT_TL(12);
     lstate ^= kCtlSlot;   // the next tile becomes current; its slot is rewritten only behind the tile-after-next's first barrier
   }
 #undef DESC
@@ -951,14 +1044,15 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     __syncthreads();  // previous readers of sm_ctl are done
     if (tid == 0) {
       int t = -1, c = 0;
-      int n_ring = sm_ctl[kCtlNRing], chain = sm_ctl[kCtlChain];
+      int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead], chain = sm_ctl[kCtlChain];
       for (;;) {
         float tmin = -INFINITY;  // parked tiles lost their minimum: treat them as needing the fix-up
-        if (n_ring > 0) {
-          --n_ring;
-          t = sm_ctl[kCtlRing + n_ring];
-          c = sm_ctl[kCtlRingClip + n_ring];
-          tmin = __int_as_float(sm_ctl[kCtlRingMin + n_ring]);
+        if (n > 0) {
+          t = sm_ctl[kCtlRing + head];
+          c = sm_ctl[kCtlRingClip + head];
+          tmin = __int_as_float(sm_ctl[kCtlRingMin + head]);
+          head = (head + 1) & (kRing - 1);
+          --n;
         } else if (chain >= 0) {
           t = chain;
           c = (t & kTileIdMask) / p.tiles_per_clip;
@@ -967,16 +1061,14 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           t = -1;
           break;
         }
-        uint4 st = ld_stat(p.stats + c);
-        while (st.z < tiles_per_clip_u) {
-          __nanosleep(100);
-          st = ld_stat(p.stats + c);
-        }
+        const ClipStat* st = p.stats + c;
+        while (ld_acquire(&st->done) < tiles_per_clip_u) __nanosleep(100);
         const int tt0 = ((t & kTileIdMask) - c * p.tiles_per_clip) * kTileFrames;
         if ((t & kSilentBit) != 0 ||
-            tile_needs_fixup(tmin, st.x, tt0, kept_frames(p.n_valid, c, p.n_frames), p.n_frames_out)) break;
+            tile_needs_fixup(tmin, ld_relaxed(&st->max_enc), tt0, kept_frames(p.n_valid, c, p.n_frames), p.n_frames_out)) break;
       }
-      sm_ctl[kCtlNRing] = n_ring;
+      sm_ctl[kCtlCount] = n;
+      sm_ctl[kCtlHead] = head;
       sm_ctl[kCtlChain] = chain;
       sm_ctl[kCtlDrain] = t;
       sm_ctl[kCtlDrainClip] = c;

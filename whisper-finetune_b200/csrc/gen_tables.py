@@ -97,51 +97,65 @@ def row_support(bank: np.ndarray):
     return supp
 
 
-# Which mel rows every warp of a CTA owns: (first_row, n_rows, quads_per_thread).  A thread owns ONE mel row for
-# `quads` groups of 4 consecutive frames of the 16-frame tile; with 2 quads per thread a row is shared by two threads
-# (frames 0-7 and 8-15).  Rows are handed out in bands of similar tap count so a warp's unrolled tap loop has little
-# padding; warp 0 (which also runs the tile scheduler) gets the cheapest band.
-WARP_BANDS = {
-    128: [(0, 32, 4), (32, 32, 4), (64, 32, 4), (96, 32, 2), (96, 32, 2)],
-    80: [(0, 32, 2), (0, 32, 2), (32, 16, 2), (48, 16, 2), (64, 16, 2)],
-}
+# ---- mel phase plan -------------------------------------------------------------------------------------------------
+# A thread owns ONE mel row for NF consecutive frames of the 16-frame tile, NF in {16, 8, 4} uniform over its warp (a row is
+# then shared by 16 / NF threads of that warp).  Rows are sorted by tap count and dealt to the five warps in consecutive
+# groups, so a warp's fully unrolled tap loop runs T = (largest tap count in the group) taps; the (NF per warp) assignment
+# is the one that minimises the slowest warp (every phase ends on a CTA barrier), found by enumeration.
+def _warp_cost(taps, nf):
+    """Issue-slot estimate of one thread: per tap NF/4 LDS.128 + NF/2 FFMA2 + 1 weight load; per frame clamp, lg2, fma and
+    its share of the running max / min; two stores and fixed overhead."""
+    return taps * (0.75 * nf + 1) + 4.0 * nf + 24
 
 
-def _conflict_cost(starts):
-    """LDS.128 phases are quarter-warps (8 lanes): distinct start bins that agree mod 8 collide for every tap."""
+def _conflict_cost(lanes):
+    """lanes = [(start_bin, f0)] of one warp in lane order.  An LDS.128 is served a quarter-warp (8 lanes) at a time;
+    two lanes of a quarter collide when they touch different addresses in the same 16-byte bank group.  The power tile is
+    [bin][frame] with a row stride of 20 floats, so the bank group of (bin, frame f) is (5 * bin + f / 4) mod 8."""
     cost = 0
-    for g in range(0, len(starts), 8):
-        by_res = {}
-        for s in set(starts[g : g + 8]):
-            by_res[s % 8] = by_res.get(s % 8, 0) + 1
-        cost += max(by_res.values()) - 1
+    for g in range(0, len(lanes), 8):
+        by_group = {}
+        for s, f0 in set(lanes[g : g + 8]):
+            key = (5 * s + f0 // 4) % 8
+            by_group[key] = by_group.get(key, 0) + 1
+        cost += max(by_group.values()) - 1
     return cost
 
 
-def _order_rows(rows, start_range):
-    """Choose every row's first tap bin (anywhere its padded window still covers the support) and permute the band's
-    rows over the lanes so that the 8 lanes of a quarter-warp start on distinct 16-byte bank groups.
+def _lanes_of(order, start, nf):
+    """lane -> (row, f0) for a warp whose rows are `order` (32 * nf / 16 of them)."""
+    n = len(order)
+    return [(order[lane % n], nf * (lane // n)) for lane in range(32)]
+
+
+def _order_rows(rows, start_range, nf):
+    """Choose every row's first tap bin (anywhere its padded window still covers the support) and permute the rows over
+    the lanes so that the 8 lanes of a quarter-warp start on distinct 16-byte bank groups.
 
     -> (lane order, {row: start bin}, residual conflicts)."""
     import random
 
     rng = random.Random(1234)
     n = len(rows)
+
+    def cost_of(order, start):
+        return _conflict_cost([(start[m], f0) for m, f0 in _lanes_of(order, start, nf)])
+
     best = None
     for _restart in range(8):
         order = list(rows)
         rng.shuffle(order) if _restart else None
         start = {m: start_range[m][1] for m in rows}
-        cost = _conflict_cost([start[m] for m in order])
+        cost = cost_of(order, start)
         for _ in range(6000):
             if cost == 0:
                 break
-            if rng.random() < 0.5:
+            if rng.random() < 0.5 and n > 1:
                 i, j = rng.randrange(n), rng.randrange(n)
-                if i // 8 == j // 8:
+                if i == j:
                     continue
                 order[i], order[j] = order[j], order[i]
-                c = _conflict_cost([start[m] for m in order])
+                c = cost_of(order, start)
                 if c <= cost:
                     cost = c
                 else:
@@ -153,7 +167,7 @@ def _order_rows(rows, start_range):
                     continue
                 old = start[m]
                 start[m] = rng.randint(lo, hi)
-                c = _conflict_cost([start[x] for x in order])
+                c = cost_of(order, start)
                 if c <= cost:
                     cost = c
                 else:
@@ -168,54 +182,56 @@ def _order_rows(rows, start_range):
 def mel_plan(bank: np.ndarray):
     """Thread-level plan of the mel phase.
 
-    -> dict(weights=[float32...], thread=[(row, start_bin, q0, w_ofs)] * 160, classes=[(taps, quads, w_stride)],
-            warp_class=[class of warp w], conflicts=int)
+    -> dict(weights=[float32...], thread=[(row, start_bin, f0, w_ofs)] * 160, warp_t=[taps of warp w],
+            warp_nf=[frames per thread of warp w], warp_ws=[weight stride of warp w], conflicts=int)
     """
+    import itertools
+
     n_mels = bank.shape[0]
     supp = row_support(bank)
-    bands = WARP_BANDS[n_mels]
-    blocks = {}  # (first, n) -> (w_base, taps, lane order, start bins)
-    weights = []
-    conflicts = 0
-    for first, n, _ in bands:
-        if (first, n) in blocks:
+    ntaps = [supp[m][1] - supp[m][0] + 1 for m in range(n_mels)]
+    by_taps = sorted(range(n_mels), key=lambda m: (ntaps[m], m))
+    best = None
+    for nfs in itertools.product((16, 8, 4), repeat=N_WARPS):
+        if list(nfs) != sorted(nfs, reverse=True):   # cheap rows first: they take the wide (16-frame) slots
             continue
-        rows = list(range(first, first + n))
-        taps = max(supp[m][1] - supp[m][0] + 1 for m in rows)
+        counts = [32 * nf // 16 for nf in nfs]
+        if sum(counts) != n_mels:
+            continue
+        pos, costs, groups = 0, [], []
+        for nf, c in zip(nfs, counts):
+            rows = by_taps[pos : pos + c]
+            pos += c
+            groups.append(rows)
+            costs.append(_warp_cost(max(ntaps[m] for m in rows), nf))
+        key = (max(costs), sum(costs))
+        if best is None or key < best[0]:
+            best = (key, nfs, groups)
+    assert best is not None, "no (frames per thread) assignment covers all rows"
+    _, nfs, groups = best
+    weights, thread, warp_t, warp_ws = [], [], [], []
+    conflicts = 0
+    for nf, rows in zip(nfs, groups):
+        taps = max(ntaps[m] for m in rows)
         # the padded window [start, start + taps) must cover the support and stay on bins 1..199 (rewritten every
         # tile, always finite); whatever freedom is left goes into avoiding bank conflicts
         start_range = {m: (max(1, supp[m][1] - taps + 1), min(supp[m][0], 200 - taps)) for m in rows}
         assert all(lo <= hi for lo, hi in start_range.values())
-        order, start_of, cost = _order_rows(rows, start_range)
+        order, start_of, cost = _order_rows(rows, start_range, nf)
         conflicts += cost
         base = len(weights)
+        n = len(order)
         for j in range(taps):
             for m in order:
                 # 0.25 * bank weight: the packed two-frame FFT yields 4 |X|^2 (exact scaling)
                 weights.append(np.float32(bank[m, start_of[m] + j]) * np.float32(0.25))
-        blocks[(first, n)] = (base, taps, order, start_of)
-    classes, warp_class, thread = [], [], []
-    seen_band = {}
-    for first, n, quads in bands:
-        base, taps, order, start_of = blocks[(first, n)]
-        cls = (taps, quads, n)
-        if cls not in classes:
-            classes.append(cls)
-        warp_class.append(classes.index(cls))
-        if n == 32:
-            # one row per lane; with 2 quads per thread a second warp takes the other half of the tile
-            q0 = 0 if quads == 4 else 2 * seen_band.get((first, n), 0)
-            seen_band[(first, n)] = seen_band.get((first, n), 0) + 1
-            for lane in range(32):
-                m = order[lane]
-                thread.append((m, start_of[m], q0, base + lane))
-        else:
-            assert n == 16 and quads == 2
-            for lane in range(32):
-                m = order[lane % 16]
-                thread.append((m, start_of[m], 2 * (lane // 16), base + lane % 16))
-    assert len(thread) == N_THREADS and len(warp_class) == N_WARPS
-    return dict(weights=weights, thread=thread, classes=classes, warp_class=warp_class, conflicts=conflicts)
+        for lane in range(32):
+            m = order[lane % n]
+            thread.append((m, start_of[m], nf * (lane // n), base + lane % n))
+        warp_t.append(taps)
+        warp_ws.append(n)
+    assert len(thread) == N_THREADS
+    return dict(weights=weights, thread=thread, warp_t=warp_t, warp_nf=list(nfs), warp_ws=warp_ws, conflicts=conflicts)
 
 
 def simulate(bank: np.ndarray, plan):
@@ -224,11 +240,12 @@ def simulate(bank: np.ndarray, plan):
     P = rng.random((201, TILE_FRAMES))
     out = np.full((bank.shape[0], TILE_FRAMES), np.nan)
     w = np.asarray(plan["weights"], dtype=np.float64)
-    for t, (row, start, q0, w_ofs) in enumerate(plan["thread"]):
-        taps, quads, stride = plan["classes"][plan["warp_class"][t // 32]]
-        f0, f1 = 4 * q0, 4 * q0 + 4 * quads
+    for t, (row, start, f0, w_ofs) in enumerate(plan["thread"]):
+        wi = t // 32
+        taps, nf, stride = plan["warp_t"][wi], plan["warp_nf"][wi], plan["warp_ws"][wi]
+        f1 = f0 + nf
         assert 1 <= start and start + taps - 1 <= 199 and f1 <= TILE_FRAMES
-        acc = np.zeros(f1 - f0)
+        acc = np.zeros(nf)
         for j in range(taps):
             acc += w[w_ofs + j * stride] * P[start + j, f0:f1]
         assert np.isnan(out[row, f0:f1]).all(), "cell computed twice"
@@ -261,30 +278,28 @@ def generate() -> str:
     lines.append("}")
     lines.append("")
     lines.append(f"#define WFT_MEL_P_STRIDE {P_STRIDE}")
-    lines.append("#define WFT_MEL_MAX_CLASSES 4")
     for n_mels in (80, 128):
         bank = mb.slaney_mel_bank(n_mels)
         assert not bank[:, 0].any() and not bank[:, 200].any()
         plan = mel_plan(bank)
         simulate(bank, plan)
-        w = plan["weights"]
-        pad = lambda xs: list(xs) + [0] * (4 - len(xs))
-        assert len(plan["classes"]) <= 4 and len(w) < 1024
-        lines.append(f"// n_mels={n_mels}: classes (taps, quads/thread, weight stride) = {plan['classes']}, "
-                     f"residual LDS.128 conflicts = {plan['conflicts']}")
-        lines.append(f"#define WFT_MEL{n_mels}_NCLASS {len(plan['classes'])}")
-        lines.append(f"#define WFT_MEL{n_mels}_CLASS_T {{" + ", ".join(str(v) for v in pad([c[0] for c in plan["classes"]])) + "}")
-        lines.append(f"#define WFT_MEL{n_mels}_CLASS_NQ {{" + ", ".join(str(v) for v in pad([c[1] for c in plan["classes"]])) + "}")
-        lines.append(f"#define WFT_MEL{n_mels}_CLASS_WS {{" + ", ".join(str(v) for v in pad([c[2] for c in plan["classes"]])) + "}")
-        lines.append(f"#define WFT_MEL{n_mels}_WARP_CLASS {{" + ", ".join(str(v) for v in plan["warp_class"]) + "}")
+        w = list(plan["weights"])
+        while len(w) % 4:
+            w.append(np.float32(0.0))
+        assert len(w) < 4096
+        lines.append(f"// n_mels={n_mels}: per warp taps = {plan['warp_t']}, frames per thread = {plan['warp_nf']}, "
+                     f"weight stride = {plan['warp_ws']}, residual LDS.128 conflicts = {plan['conflicts']}")
+        lines.append(f"#define WFT_MEL{n_mels}_WARP_T {{" + ", ".join(str(v) for v in plan["warp_t"]) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_WARP_NF {{" + ", ".join(str(v) for v in plan["warp_nf"]) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_WARP_WS {{" + ", ".join(str(v) for v in plan["warp_ws"]) + "}")
         lines.append(f"#define WFT_MEL{n_mels}_W_LEN {len(w)}")
         lines.append(f"#define WFT_MEL{n_mels}_W_INIT {{ \\")
         for r in range(0, len(w), 8):
             lines.append("  " + ", ".join(flit(v) for v in w[r : r + 8]) + ", \\")
         lines.append("}")
-        lines.append(f"// per thread: row | start_bin << 8 | first_quad << 16 | weight_offset << 18")
+        lines.append(f"// per thread: row | start_bin << 8 | first_frame << 16 | weight_offset << 20")
         lines.append(f"#define WFT_MEL{n_mels}_THREAD_INIT {{ \\")
-        words = ["0x%08xu" % (row | (start << 8) | (q0 << 16) | (w_ofs << 18)) for row, start, q0, w_ofs in plan["thread"]]
+        words = ["0x%08xu" % (row | (start << 8) | (f0 << 16) | (w_ofs << 20)) for row, start, f0, w_ofs in plan["thread"]]
         for r in range(0, len(words), 8):
             lines.append("  " + ", ".join(words[r : r + 8]) + ", \\")
         lines.append("}")

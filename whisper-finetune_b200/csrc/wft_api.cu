@@ -14,6 +14,7 @@ namespace {
 
 thread_local std::string g_last_error;
 thread_local int64_t g_launches = 0;
+int g_debug_max_ctas = 0;   // wft_debug_set_max_ctas: caps the persistent grid (tests of the parked-tile / drain paths)
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -63,6 +64,7 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream) {
   int rc = grid_for(wft::frontend_kernel<NM, PcmT>, cache, &ctas);
   if (rc != WFT_OK) return rc;
   if (ctas > p.total_tiles) ctas = p.total_tiles;
+  if (g_debug_max_ctas > 0 && ctas > g_debug_max_ctas) ctas = g_debug_max_ctas;
   wft::frontend_kernel<NM, PcmT><<<ctas, wft::kThreads, wft::kSmemBytes, stream>>>(p);
   ++g_launches;
   WFT_CUDA(cudaGetLastError());
@@ -326,6 +328,21 @@ int wft_abi_version(void) { return WFT_ABI_VERSION; }
 
 const char* wft_last_error(void) { return g_last_error.c_str(); }
 
+#ifdef WFT_TIMELINE
+// development build only: copy the kernel's clock stamps to the host (kTlMaxCtas x kTlIters x kWarps x kTlPoints words)
+int wft_debug_timeline(uint32_t* host_out, int32_t* dims) {
+  dims[0] = wft::kTlMaxCtas; dims[1] = wft::kTlIters; dims[2] = wft::kWarps; dims[3] = wft::kTlPoints;
+  if (host_out == nullptr) return WFT_OK;
+  WFT_CUDA(cudaMemcpyFromSymbol(host_out, wft::g_timeline, sizeof(wft::g_timeline)));
+  return WFT_OK;
+}
+#endif
+
+int wft_debug_set_max_ctas(int32_t max_ctas) {
+  g_debug_max_ctas = max_ctas > 0 ? max_ctas : 0;
+  return WFT_OK;
+}
+
 int64_t wft_launch_count(int reset) {
   const int64_t v = g_launches;
   if (reset) g_launches = 0;
@@ -396,6 +413,9 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
   p.total_tiles = p.tiles_per_clip * a->batch;
   p.mask_value = a->mask_value;
   p.zero = 0u;
+  const uint64_t magic = (uint64_t(1) << 32) / static_cast<uint64_t>(p.tiles_per_clip);
+  p.tpc_magic = magic > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(magic);
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(a->out) & 31) == 0 && (n_frames_out & 7) == 0) ? 1 : 0;
 
   WFT_CUDA(cudaMemsetAsync(ws, 0, ws_header_bytes(a->batch), stream));
   if (a->n_mels == 128) {
