@@ -40,8 +40,19 @@ N_STREAMS = 2   # batches in flight in the throughput loop (the roofline loop st
 BYTES_PER_CLIP = 4 * N_SAMPLES + 4 * N_MELS * N_FRAMES  # 3 456 000 (algorithmic bytes, f32 in, 128 mel)
 METRIC = "30-s clips/sec log-mel+SpecAugment"
 UNIT = "clips/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one B=64 launch, from profiles/r01_ncu_summary.md
-NCU_DRAM_BYTES_PER_LAUNCH = 182.6e6
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one B=64 launch of the fused kernel, from the committed summary of
+    the latest `ncu --set full` capture (profiles/ncu_traffic.json, written by profiles/make_summary.py); (None, why) if
+    there is none.  ncu cannot run inside the timed bench, so this is a recorded measurement, not a live one."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_launch"]), f"profiles/ncu_traffic.json ({d.get('source', '?')})"
+    except Exception as e:  # noqa: BLE001
+        return None, f"no committed ncu capture ({type(e).__name__})"
 
 
 def workload_config(n_gpus):
@@ -123,27 +134,95 @@ class ClockSampler:
                 "sampler": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
-def cpu_reference_clips_per_s(min_seconds, max_clips=None, threads=None):
-    """The reference's CPU path on this box's host cores: oracle log-mel + masks, clip by clip."""
+# ---- the reference's CPU path (oracle port) in the shapes the reference can run it in -------------------------------------
+# The reference computes features inside DataLoader workers: min(cpu_count, 8) worker PROCESSES, each single-clip,
+# (src/whisper_finetune/scripts/finetune.py:631, 641-664), so process-level parallelism is its real deployment shape;
+# torch intra-op threading of one process is the other way a user could run it.  Every shape runs the SAME work: the
+# 64-clip batch of the CUDA arm, log-mel + masks clip by clip like data_loader.py:273-292 (oracle/pipeline.py).
+
+def _ref_worker(w, n_workers, steps, warmup, barrier, queue):
+    """One DataLoader-style worker process: 1 torch thread, clips w::n_workers of every 64-clip batch."""
     import torch
 
     from oracle import pipeline as OP
     from oracle import specaug as OS
 
-    if threads:
-        torch.set_num_threads(threads)
-    n = BATCH  # the same 64-clip batch the CUDA arm runs per step
-    pcm = synth_pcm(n, SEED)
-    masks = OS.draw_mask_params(SEED, 0, n, N_MELS, N_FRAMES, TIME_MASK, FREQ_MASK, 1.0)
-    OP.front_end_batch(pcm[:2], N_MELS, masks=masks[:2])  # warm-up (FFT plans, filter cache)
-    done, t0 = 0, time.perf_counter()
-    while True:
+    torch.set_num_threads(1)
+    pcm = synth_pcm(BATCH, SEED)[w::n_workers].contiguous()
+    masks = OS.draw_mask_params(SEED, 0, BATCH, N_MELS, N_FRAMES, TIME_MASK, FREQ_MASK, 1.0)[w::n_workers]
+    if pcm.shape[0]:
+        OP.front_end_batch(pcm[:1], N_MELS, masks=masks[:1])
+        for _ in range(warmup):
+            OP.front_end_batch(pcm, N_MELS, masks=masks)
+    barrier.wait()
+    t0 = time.perf_counter()      # CLOCK_MONOTONIC: comparable across processes of one host
+    for _ in range(steps):
+        if pcm.shape[0]:
+            OP.front_end_batch(pcm, N_MELS, masks=masks)
+    queue.put((w, t0, time.perf_counter()))
+
+
+def _time_worker_processes(n_workers, steps, warmup):
+    """-> seconds for `steps` 64-clip batches split over `n_workers` single-threaded processes."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    barrier, queue = ctx.Barrier(n_workers), ctx.Queue()
+    procs = [ctx.Process(target=_ref_worker, args=(w, n_workers, steps, warmup, barrier, queue), daemon=True)
+             for w in range(n_workers)]
+    for p in procs:
+        p.start()
+    spans = [queue.get(timeout=1800) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    return max(s[2] for s in spans) - min(s[1] for s in spans)
+
+
+def _time_one_process(threads, steps, warmup):
+    import torch
+
+    from oracle import pipeline as OP
+    from oracle import specaug as OS
+
+    torch.set_num_threads(threads)
+    pcm = synth_pcm(BATCH, SEED)
+    masks = OS.draw_mask_params(SEED, 0, BATCH, N_MELS, N_FRAMES, TIME_MASK, FREQ_MASK, 1.0)
+    OP.front_end_batch(pcm[:2], N_MELS, masks=masks[:2])  # FFT plans, filter cache
+    for _ in range(warmup):
         OP.front_end_batch(pcm, N_MELS, masks=masks)
-        done += n
-        el = time.perf_counter() - t0
-        if el >= min_seconds or (max_clips and done >= max_clips):
-            break
-    return done / el, done, el, torch.get_num_threads()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        OP.front_end_batch(pcm, N_MELS, masks=masks)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_shapes(steps, warmup, budget_s=None):
+    """Time the CPU path in every shape -> (best shape name, {shape: {...}}).  `budget_s` bounds each shape's sample."""
+    cores = os.cpu_count() or 1
+    shapes = {}
+
+    def record(name, threads, procs, k, el):
+        shapes[name] = {"value": BATCH * k / el, "unit": UNIT, "processes": procs, "threads_per_process": threads,
+                        "cores": procs * threads, "clips": BATCH * k, "seconds": el}
+
+    def bounded(k, per_step_guess):
+        if budget_s is None:
+            return k
+        return max(1, min(k, int(budget_s / max(per_step_guess, 1e-3))))
+
+    k1 = bounded(steps, 1.0)                       # ~110 clips/s on one thread
+    record("1_process_x_1_thread", 1, 1, k1, _time_one_process(1, k1, min(warmup, 1)))
+    per_step_1t = shapes["1_process_x_1_thread"]["seconds"] / k1
+    k = bounded(steps, per_step_1t / min(cores, 4))
+    record(f"1_process_x_{cores}_threads_intra_op", cores, 1, k, _time_one_process(cores, k, warmup))
+    w8 = min(cores, 8)                             # finetune.py:631
+    k = bounded(steps, per_step_1t / w8)
+    record(f"{w8}_worker_processes_x_1_thread", 1, w8, k, _time_worker_processes(w8, k, warmup))
+    if cores > w8:
+        k = bounded(steps, per_step_1t / cores)
+        record(f"{cores}_worker_processes_x_1_thread", 1, cores, k, _time_worker_processes(cores, k, warmup))
+    best = max(shapes, key=lambda n: shapes[n]["value"])
+    return best, shapes
 
 
 _RESULT_FD = None
@@ -160,38 +239,26 @@ def emit(line):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (here: its restatement in oracle/, since
-    whisper.audio is a third-party dependency that is not installable offline) on all host threads.  A step is a
-    bounded sample of the workload: one 64-clip batch (the same batch size the CUDA arm runs per step)."""
-    import torch
-
-    from oracle import pipeline as OP
-    from oracle import specaug as OS
-
+    whisper.audio is a third-party dependency that is not installable offline), timed in every shape the reference can
+    run it in; `value` is the BEST of them (the process-parallel DataLoader shape on any multi-core host).  A step is a
+    bounded sample of the workload: one 64-clip batch (the same batch the CUDA arm runs per GPU per step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n = BATCH
-    pcm = synth_pcm(n, SEED)
-    masks = OS.draw_mask_params(SEED, 0, n, N_MELS, N_FRAMES, TIME_MASK, FREQ_MASK, 1.0)
-    OP.front_end_batch(pcm[:2], N_MELS, masks=masks[:2])
-    for _ in range(args.warmup):
-        OP.front_end_batch(pcm, N_MELS, masks=masks)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        OP.front_end_batch(pcm, N_MELS, masks=masks)
-    el = time.perf_counter() - t0
-    val = n * args.steps / el
-    thr = torch.get_num_threads()
+    best, shapes = cpu_reference_shapes(args.steps, args.warmup)
+    b = shapes[best]
+    val = b["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * BATCH / val, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": thr, "kind": "port",
-                         "sample": f"{n} clips per step ({n * args.steps} clips in {el:.1f} s), torch intra-op threads={thr} "
-                                   f"of {cores} host cores, oracle/pipeline.py (torch.stft recipe + masks, clip by clip)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": b["cores"], "kind": "port", "shape": best,
+                         "sample": f"{b['clips']} clips in {b['seconds']:.1f} s ({BATCH} clips per step), {b['processes']} "
+                                   f"process(es) x {b['threads_per_process']} torch thread(s) on {cores} host cores, "
+                                   "oracle/pipeline.py (torch.stft recipe + masks, clip by clip); best of `shapes`",
+                         "shapes": shapes},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "audio_hours_per_s": val * 30.0 / 3600.0,
     }
@@ -255,47 +322,54 @@ def run_ours(args):
     join()
     barrier()
     lib.wft_launch_count(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+
+    def timed_block(first_step, body):
+        """EXACTLY args.steps steps between two events on the current stream, barrier + synchronize on both sides;
+        -> milliseconds, max over ranks."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        fork()
-        for i in range(args.steps):
-            step(i)
-        join()
+        body(first_step)
         ev1.record()
         barrier()
-        launches = int(lib.wft_launch_count(0))
-        # the timed region lasts only milliseconds: keep the very same steps running for another ~0.4 s so that the
-        # clock / throttle-reason samples describe the GPU under this load (not part of the timing)
-        t_end = time.perf_counter() + 0.4
-        i = args.steps
-        while time.perf_counter() < t_end:
-            fork()
-            for _ in range(20):
-                step(i)
-                i += 1
-            join()
-            torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def repeat_blocks(body, min_gpu_seconds=0.5, max_blocks=400):
+        """One K-step block lasts only milliseconds: repeat it until >= 0.5 s of GPU time has been timed and report the
+        MEDIAN block (every rank runs the same number of blocks: the count comes from the max-over-ranks first block)."""
+        first = timed_block(0, body)
+        n_blocks = int(min(max_blocks, max(3, min_gpu_seconds * 1e3 / max(first, 1e-3))))
+        times = [first] + [timed_block((k + 1) * args.steps, body) for k in range(n_blocks)]
+        return statistics.median(times), times
+
+    def value_body(first_step):
+        fork()
+        for i in range(first_step, first_step + args.steps):
+            step(i)
+        join()
+
+    with ClockSampler(local_rank) as clocks:
+        block_ms, block_times = repeat_blocks(value_body)
+        launches_total = int(lib.wft_launch_count(0))
+    launches = launches_total // len(block_times)      # launches of ONE timed K-step block
+    ms_max = block_ms
     value = world * BATCH * args.steps / (ms_max * 1e-3)
 
-    # fused kernel alone (no mask draw), for the roofline: K back-to-back launches on the current stream
+    # fused kernel alone (no mask draw), for the roofline: K back-to-back launches on the current stream per block
     masks = wft.draw_mask_params(SEED, 0, BATCH, N_MELS, N_FRAMES, TIME_MASK, FREQ_MASK, 1.0, dev)
     for i in range(3):
         wft.frontend_forward(pcm_sets[i % n_sets], N_MELS, mask_params=masks, out=out_sets[i % n_sets])
     torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for i in range(args.steps):
-        wft.frontend_forward(pcm_sets[i % n_sets], N_MELS, mask_params=masks, out=out_sets[i % n_sets])
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / args.steps
+
+    def kernel_body(first_step):
+        for i in range(first_step, first_step + args.steps):
+            wft.frontend_forward(pcm_sets[i % n_sets], N_MELS, mask_params=masks, out=out_sets[i % n_sets])
+
+    kernel_block_ms, kernel_times = repeat_blocks(kernel_body, min_gpu_seconds=0.3)
+    kernel_ms = kernel_block_ms / args.steps
 
     # end to end through the public API with host buffers (pinned): H2D + kernels + D2H every step
     def run_e2e(pcm_dtype, readback):
@@ -310,30 +384,66 @@ def run_ours(args):
         for i in range(2):
             pipe(host_pcm[i % 2], host_out[i % 2], clip_offset=i * BATCH)
         pipe.synchronize()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            pipe(host_pcm[i % 2], host_out[i % 2], clip_offset=(i * world + rank) * BATCH)
-        pipe.join()   # the current stream (and so e1) waits for the last D2H copy
-        e1.record()
-        pipe.synchronize()
-        barrier()
-        probe = float(host_out[(steps - 1) % 2].reshape(BATCH, -1)[0, :8].sum())  # the result really is on the host
-        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        return world * BATCH * steps / (float(te.item()) * 1e-3), pipe.h2d_bytes, pipe.d2h_bytes, steps, probe
 
-    e2e_value, e2e_h2d, e2e_d2h, e2e_steps, checksum = run_e2e(torch.float32, "features")
-    # informational variants (not the headline): int16 PCM halves the H2D bytes; a training step consumes the features
-    # on the device, so only a per-clip probe has to return
+        def body(first_step):
+            for i in range(first_step, first_step + steps):
+                pipe(host_pcm[i % 2], host_out[i % 2], clip_offset=(i * world + rank) * BATCH)
+            pipe.join()   # the current stream (and so the closing event) waits for the last D2H copy
+
+        # a block is `steps` batches; repeated until >= 0.3 s are timed, median block (same helper as `value`)
+        saved, args.steps = args.steps, steps
+        try:
+            ms, times = repeat_blocks(body, min_gpu_seconds=0.3, max_blocks=20)
+        finally:
+            args.steps = saved
+        pipe.synchronize()
+        probe = float(host_out[(steps - 1) % 2].reshape(BATCH, -1)[0, :8].sum())  # the result really is on the host
+        return world * BATCH * steps / (ms * 1e-3), pipe.h2d_bytes, pipe.d2h_bytes, steps, probe
+
+    # Declared end-to-end shape (the only one a trainer uses): DataLoader workers hand over int16 PCM in
+    # pinned host memory, the features stay in HBM for the model (train_step moves x to the device anyway,
+    # model/model_utils.py:59-62) and one float32 per clip comes back as the step's read-back.  The other three
+    # combinations (float32 PCM, full features back to the host = what the reference's CPU path yields) are variants.
+    e2e_value, e2e_h2d, e2e_d2h, e2e_steps, checksum = run_e2e(torch.int16, "probe")
     e2e_variants = {}
-    for name, dt, rb in (("int16_pcm_features_to_host", torch.int16, "features"),
-                         ("f32_pcm_features_stay_on_device", torch.float32, "probe"),
-                         ("int16_pcm_features_stay_on_device", torch.int16, "probe")):
+    for name, dt, rb in (("f32_pcm_features_to_host", torch.float32, "features"),
+                         ("int16_pcm_features_to_host", torch.int16, "features"),
+                         ("f32_pcm_features_stay_on_device", torch.float32, "probe")):
         v, h2d, d2h, _, _ = run_e2e(dt, rb)
         e2e_variants[name] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    # multi-GPU correctness on the hardware (outside every timed region): each rank computes ITS DistributedSampler shard of
+    # a fixed set of 8 * world clips (masks keyed by the global clip index), the shards are all-gathered over NCCL, and
+    # rank 0 recomputes the whole set alone: the union of the shards must equal the single-GPU result bit for bit.
+    multi = None
+    if world > 1:
+        per = 8
+        total = per * world
+        idx = wft.shard_indices(total, world, rank, epoch=0, seed=SEED, shuffle=True)
+        all_pcm = synth_pcm(total, SEED + 77)
+        gmasks = wft.draw_mask_params(SEED, 0, total, N_MELS, N_FRAMES, TIME_MASK, FREQ_MASK, 1.0, dev)
+        mine = wft.frontend_forward(all_pcm[idx].to(dev), N_MELS, mask_params=gmasks[torch.as_tensor(idx, device=dev)].contiguous())
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gathered = wft.all_gather_features(mine)          # warm-up (NCCL channel setup)
+        barrier()
+        g0.record()
+        gathered = wft.all_gather_features(mine)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        order = torch.tensor([i for r in range(world) for i in wft.shard_indices(total, world, r, epoch=0, seed=SEED, shuffle=True)])
+        equal = torch.tensor([1], device=dev)
+        if rank == 0:
+            alone = wft.frontend_forward(all_pcm.to(dev), N_MELS, mask_params=gmasks)
+            equal = torch.tensor([int(torch.equal(gathered, alone[order.to(dev)]))], device=dev)
+        dist.broadcast(equal, 0)
+        nbytes = gathered.numel() * 4
+        multi = {"shard_union_equal": bool(equal.item()), "clips": total,
+                 "all_gather": {"backend": dist.get_backend(), "bytes_out_per_rank": nbytes, "ms": float(tg.item()),
+                                "algbw_gbs": nbytes / (float(tg.item()) * 1e-3) / 1e9,
+                                "busbw_gbs": nbytes * (world - 1) / world / (float(tg.item()) * 1e-3) / 1e9}}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -342,28 +452,40 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         achieved = BATCH * BYTES_PER_CLIP / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "audio_hours_per_s": value * 30.0 / 3600.0,
+            "timing": {"what": "median of repeated K-step blocks, each bracketed by barrier + synchronize, CUDA events, max over ranks",
+                       "blocks": len(block_times), "block_ms_median": block_ms, "block_ms_min": min(block_times),
+                       "block_ms_max": max(block_times), "gpu_seconds_timed": sum(block_times) * 1e-3,
+                       "kernel_blocks": len(kernel_times), "kernel_gpu_seconds_timed": sum(kernel_times) * 1e-3},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
-                    "steps": e2e_steps, "pipeline": "4 chunks on 2 streams, consecutive batches overlap, pinned host buffers, float32 PCM in, full "
-                    "float32 features back to the host", "checksum": checksum},
+                    "steps": e2e_steps, "pipeline": "4 chunks on 2 streams, consecutive batches overlap, pinned host buffers, int16 PCM in "
+                    "(what a DataLoader worker hands over), features stay in HBM for the model, one float32 per clip read back",
+                    "checksum": checksum},
             "e2e_variants": e2e_variants,
             "gpu_launches": launches,
             "gpu_launches_per_step": launches / max(args.steps, 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "wft::frontend_kernel<128,float>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": BATCH * BYTES_PER_CLIP},
         }
+        if multi is not None:
+            line["multi_gpu"] = multi
+            line["shard_union_equal"] = multi["shard_union_equal"]
         if world == 1 and not args.no_cpu_baseline:
-            v, done, el, thr = cpu_reference_clips_per_s(12.0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
-                                    "sample": f"{done} clips in {el:.1f} s, oracle/pipeline.py clip by clip, torch "
-                                              f"intra-op threads={thr} of {os.cpu_count()} host cores"}
+            best, shapes = cpu_reference_shapes(20, 1, budget_s=6.0)   # bounded: ~6 s per shape
+            b = shapes[best]
+            line["cpu_baseline"] = {"value": b["value"], "unit": UNIT, "cores": b["cores"], "kind": "port", "shape": best,
+                                    "sample": f"{b['clips']} clips in {b['seconds']:.1f} s, oracle/pipeline.py clip by clip, "
+                                              f"{b['processes']} process(es) x {b['threads_per_process']} thread(s) of "
+                                              f"{os.cpu_count()} host cores; best of `shapes`",
+                                    "shapes": shapes}
         emit(line)
     if world > 1:
         dist.barrier(device_ids=[local_rank])

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WFT_ABI_VERSION 3
+#define WFT_ABI_VERSION 4
 
 /* Front-end constants (whisper.audio: SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES;
  * imported by the reference at data_loader.py:13 and data/utils.py:10). */
@@ -122,9 +122,26 @@ int wft_time_warp_f32(const float* in, float* out, int32_t batch, int32_t n_rows
                       const int32_t* warp_params, void* stream);
 
 /* Counter-based draw of (warp_p in [W, T-W), warp_d in [-W, W)) per clip (the reference's torch.randint ranges,
- * data/utils.py:107-111), Philox keyed like wft_specaug_draw; (T/2, 0) = identity when the p gate rejects the clip. */
+ * data/utils.py:107-111), Philox keyed like wft_specaug_draw; (-1, 0) = "no warp" when the p gate rejects the clip (both
+ * wft_time_warp_f32 and wft_augment_f32 copy such a clip unchanged). */
 int wft_time_warp_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t time_warp_w, float p,
                        int32_t* warp_params_out, void* stream);
+
+/* Fused augmentation epilogue: everything AudioDataset._calculate_mel does to the finished features when the SpecAugment
+ * gate passes (data_loader.py:284-290: time_warping -> time_masking -> freq_masking -> extreme_freq_masking), in ONE read and
+ * ONE write of the features instead of one pass per transform:
+ *   out[b, r, t] = (t0 <= t < t1 || f0 <= r < f1 || r < lo || r >= n_rows - hi) ? mask_value : warp_b(in[b])[r, t]
+ * warp_params  device int32 [B,2] = (warp_p, warp_d) as in wft_time_warp_f32, or NULL = no warp; a clip whose warp_p is
+ *              outside (0, n_frames - 1) -- wft_time_warp_draw writes (-1, 0) when the p gate rejects it -- is copied.
+ * mask_params  device int32 [B,4] = (t0, t1, f0, f1) or NULL.
+ * extremes     device int32 [B,2] = (lo, hi): rows masked from the bottom / top (ExtremesFrequencyMasking,
+ *              data/utils.py:146-190) or NULL.
+ * spline_f32   0: the warp's cubic Hermite source map is evaluated in float64 and rounded once; 1: the reference's own
+ *              float32 evaluation order (data/utils.py:65-93) is restated, which lands on the reference's coordinate
+ *              wherever torch.pow returned the correctly rounded power.
+ * in == out is allowed only without a warp. */
+int wft_augment_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
+                    const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream);
 
 /* Deep SpecAugment on encoder activations (model/model_utils.py:382-437: permute -> TimeMasking -> FrequencyMasking ->
  * permute on every hooked layer-norm output), without the permutes: x is [batch, seq, dim] contiguous with 16-bit (fp16 /

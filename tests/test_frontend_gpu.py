@@ -426,6 +426,12 @@ def test_time_warp_matches_oracle_and_reference_golden(wft, cuda):
         ref = OT.time_warp(mel, wp, wd)
         assert (got - ref).abs().max() <= 2e-5, "CUDA vs oracle (same float64 spline)"
         assert np.abs(got[::8].numpy() - z[f"warp{k}"]).max() <= 1e-3, "CUDA vs the reference class (float32 spline)"
+        # the float32 restatement of the reference's own spline arithmetic (data/utils.py:65-93): the source coordinate
+        # lands on the reference's value wherever torch.pow is correctly rounded, so all but a few frames agree to float32
+        # rounding of the bilinear blend; a frame whose coordinate differs by one ulp moves by ~1e-4 of a frame
+        got32 = wft.augment_epilogue(mel.unsqueeze(0).to(cuda), torch.tensor([[wp, wd]], dtype=torch.int32), spline="f32")[0].cpu()
+        d32 = np.abs(got32[::8].numpy() - z[f"warp{k}"])
+        assert d32.max() <= 1e-3 and np.mean(d32 > 2e-6) <= 0.02, (d32.max(), np.mean(d32 > 2e-6))
         # drop-in class: same torch seed -> same (warp_p, warp_d) as the reference
         torch.manual_seed(seed)
         via_class = wft.TimeWarpAugmenter(W=W)(mel.to(cuda)).cpu()
@@ -438,7 +444,11 @@ def test_time_warp_matches_oracle_and_reference_golden(wft, cuda):
     draws = wft.draw_warp_params(42, 0, 4096, 3000, 80).cpu()
     assert (draws[:, 0] >= 80).all() and (draws[:, 0] < 2920).all() and (draws[:, 1] >= -80).all() and (draws[:, 1] < 80).all()
     assert torch.equal(draws[100:200], wft.draw_warp_params(42, 100, 100, 3000, 80).cpu())
-    assert (wft.draw_warp_params(42, 0, 16, 3000, 80, p=0.0).cpu() == torch.tensor([1500, 0])).all()
+    assert (wft.draw_warp_params(42, 0, 16, 3000, 80, p=0.0).cpu() == torch.tensor([-1, 0])).all(), "(-1, 0) = no warp"
+    same = wft.time_warp(batch, torch.tensor([[-1, 0], [2500, -41]], dtype=torch.int32))
+    assert torch.equal(same[0], batch[0]) and torch.equal(same[1].cpu(), out[1]), "warp_p = -1 copies the clip"
+    with pytest.raises(ValueError):
+        wft.time_warp(batch, wps, out=torch.empty(2, 80, 2999, device=cuda))
 
 
 def test_extremes_mask_matches_reference_golden(wft, cuda):
@@ -462,8 +472,8 @@ def test_front_end_with_time_warp_follows_reference_order(wft, cuda):
 
     x = torch.stack([S.make("white", seed=61), S.make("chirp", seed=62)])
     fe = wft.FrontEnd(n_mels=80, spec_augment=True, seed=5,
-                      spec_augment_params={"time_mask_param": 100, "freq_mask_param": 43, "time_warp_w": 80,
-                                           "fuse_time_warp": True, "p": 1.0})
+                      spec_augment_params={"time_mask_param": 100, "freq_mask_param": 43, "time_warp_w": 80, "p": 1.0})
+    assert fe.time_warp_w == 80, "a positive time_warp_w turns the warp on, like the reference (data_loader.py:117)"
     got = fe(x.to(cuda), clip_offset=10).cpu()
     warps = wft.draw_warp_params(5, 10, 2, 3000, 80).cpu().numpy()
     masks = OS.draw_mask_params(5, 10, 2, 80, 3000, 100, 43, 1.0)
@@ -471,6 +481,80 @@ def test_front_end_with_time_warp_follows_reference_order(wft, cuda):
         ref = OS.apply_masks(OT.time_warp(O.log_mel_spectrogram(x[b], 80), int(warps[b, 0]), int(warps[b, 1])), *masks[b])
         assert (got[b] - ref).abs().max() <= 1e-3
         assert torch.equal(got[b] == 0, ref == 0)
+
+
+def test_augment_epilogue_is_warp_then_masks_then_extremes(wft, cuda):
+    """One pass == the reference's sequence time_warping -> time_masking -> freq_masking -> extreme_freq_masking
+    (data_loader.py:284-290), and a front end built from the reference's config block runs exactly that."""
+    from oracle import timewarp as OT
+
+    x = torch.stack([S.make("white", seed=71), S.make("hdr", seed=72), S.make("chirp", seed=73)])
+    mel = O.log_mel_batch(x, 128)
+    warps = torch.tensor([[700, 33], [-1, 0], [2500, -41]], dtype=torch.int32)
+    masks = OS.draw_mask_params(3, 0, 3, 128, 3000, 100, 27, 1.0)
+    ext = torch.tensor([[4, 9], [0, 0], [10, 0]], dtype=torch.int32)
+    got = wft.augment_epilogue(mel.to(cuda), warps, masks, ext).cpu()
+    for b in range(3):
+        ref = mel[b] if warps[b, 0] < 0 else OT.time_warp(mel[b], int(warps[b, 0]), int(warps[b, 1]))
+        ref = OT.extremes_mask(OS.apply_masks(ref, *masks[b]), int(ext[b, 0]), int(ext[b, 1]))
+        assert (got[b] - ref).abs().max() <= 2e-5
+        assert torch.equal(got[b] == 0, ref == 0)
+    # masks + extremes only: in place, bit exact
+    buf = mel.to(cuda).clone()
+    res = wft.augment_epilogue(buf, None, masks, ext, out=buf)
+    assert res.data_ptr() == buf.data_ptr()
+    for b in range(3):
+        assert torch.equal(res[b].cpu(), OT.extremes_mask(OS.apply_masks(mel[b], *masks[b]), int(ext[b, 0]), int(ext[b, 1])))
+    with pytest.raises(ValueError):
+        wft.augment_epilogue(buf, warps, out=buf)      # a warp cannot run in place
+    # ragged frame count (scalar stores) and a tiny tensor
+    small = torch.randn(2, 5, 37)
+    got = wft.augment_epilogue(small.to(cuda), torch.tensor([[10, 3], [20, -4]], dtype=torch.int32),
+                               torch.tensor([[3, 9, 1, 2], [0, 0, 0, 5]], dtype=torch.int32)).cpu()
+    for b, (wp, wd, mk) in enumerate([(10, 3, (3, 9, 1, 2)), (20, -4, (0, 0, 0, 5))]):
+        assert (got[b] - OS.apply_masks(OT.time_warp(small[b], wp, wd), *mk)).abs().max() <= 2e-5
+
+
+def test_upstream_gate_is_not_rolled_twice(wft, cuda):
+    """with the gate decided upstream (`augment`), p = 0.5 must not thin the augmented clips a second time."""
+    B = 64
+    x = torch.stack([S.make("white", n=16000, seed=900 + b) for b in range(B)])
+    fe = wft.FrontEnd(n_mels=80, spec_augment=True, seed=9,
+                      spec_augment_params={"time_mask_param": 100, "freq_mask_param": 43, "time_warp_w": 80, "p": 0.5})
+    flags = (torch.arange(B) % 3 != 0).to(torch.int32)
+    got = fe(x.to(cuda), clip_offset=0, augment=flags).cpu()
+    plain = wft.FrontEnd(n_mels=80)(x.to(cuda)).cpu()
+    masks = OS.draw_mask_params(9, 0, B, 80, 3000, 100, 43, 1.0)
+    for b in range(B):
+        if flags[b]:
+            t0, t1, f0, f1 = masks[b]
+            assert (got[b][f0:f1] == 0).all() and (got[b][:, t0:t1] == 0).all(), "every gated-in clip carries its masks"
+            assert not torch.equal(got[b], plain[b])
+        else:
+            assert torch.equal(got[b], plain[b]), "a gated-out clip gets neither warp nor masks"
+    # without an upstream gate the device rolls p itself: about half of the clips, the same ones for warp and masks
+    own = fe(x.to(cuda), clip_offset=0).cpu()
+    changed = torch.tensor([not torch.equal(own[b], plain[b]) for b in range(B)])
+    assert 16 <= int(changed.sum()) <= 48
+    gate_ref = OS.draw_mask_params(9, 0, B, 80, 3000, 100, 43, 0.5).any(axis=1)
+    assert np.array_equal(changed.numpy(), gate_ref)
+
+
+def test_axis_masks_keep_dtype_and_gradients(wft, cuda):
+    """the drop-in mask classes may meet bf16 activations that require grad (model_utils.py:404-405)."""
+    for dtype in (torch.bfloat16, torch.float16, torch.float32):
+        x = torch.randn(2, 64, 50, device=cuda, dtype=dtype, requires_grad=True)
+        torch.manual_seed(4)
+        y = wft.FrequencyMasking(9)(wft.TimeMasking(11)(x))
+        assert y.dtype == dtype and y.requires_grad
+        y.float().sum().backward()
+        assert x.grad is not None and x.grad.dtype == dtype
+        torch.manual_seed(4)
+        import torchaudio.transforms as T
+
+        ref = T.FrequencyMasking(9)(T.TimeMasking(11)(x.detach()))
+        assert torch.equal(y.detach(), ref)
+        assert torch.equal(x.grad == 0, ref == 0) or (x.detach() == 0).any()
 
 
 # ---- deep SpecAugment on activations (SURVEY 8f row 3; model/model_utils.py:382-437) ----------------------------------

@@ -46,6 +46,19 @@ int main(int argc, char** argv) {
     for (int w = 0; w < W; ++w) printf(" %8.0f", sum[w] / cnt);
     printf("   %8.0f\n", summax / cnt);
   }
+  {
+    const int extra[][2] = {{7, 13}, {13, 14}, {14, 8}, {3, 15}, {15, 4}};
+    const char* en[] = {"past BAR d -> before TMA issue", "TMA issue (fence + expect_tx + copies)", "after TMA issue -> power stored",
+                        "past BAR b -> DFT A + exchange stores done", "publish-finish + describe (thread 0)"};
+    printf("intervals of lane 0 (mean cycles)\n");
+    for (int k = 0; k < 5; ++k) {
+      double sum[8] = {0}; long cnt2 = 0;
+      for (int c = 0; c < C; ++c) for (int i = 8; i < I; ++i) { for (int w = 0; w < W; ++w) sum[w] += (double)(int32_t)(at(c, i, w, extra[k][1]) - at(c, i, w, extra[k][0])); ++cnt2; }
+      printf("%-52s", en[k]);
+      for (int w = 0; w < W; ++w) printf(" %8.0f", sum[w] / cnt2);
+      printf("\n");
+    }
+  }
   double iter = 0; long cnt = 0;
   for (int c = 0; c < C; ++c) for (int i = 8; i < I - 1; ++i) { iter += (double)(uint32_t)(at(c, i + 1, 1, 0) - at(c, i, 1, 0)); ++cnt; }
   printf("tile-to-tile period of one CTA: %.0f cycles\n", iter / cnt);

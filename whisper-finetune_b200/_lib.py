@@ -15,7 +15,7 @@ WFT_PCM_F32 = 0
 WFT_PCM_I16 = 1
 WFT_ERR_INVALID = -1
 WFT_ERR_CUDA = -2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class FrontendArgs(Structure):
@@ -52,6 +52,8 @@ SIGNATURES = {
                                  c_void_p, c_void_p]),
     "wft_time_warp_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "wft_time_warp_draw": (c_int, [c_uint64, c_uint64, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
+    "wft_augment_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_int32,
+                                c_void_p]),
     "wft_mask_bsd": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                              c_uint32, c_void_p]),
     "wft_launch_count": (c_int64, [c_int]),

@@ -30,6 +30,14 @@ def _interval_from_global_rng(mask_param: int, size: int) -> Tuple[int, int]:
     return start, start + int(value.long())
 
 
+def _checked_out(out: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """An ``out=`` buffer goes to the C ABI as a bare pointer: it has to be exactly what the kernel will write."""
+    if (not torch.is_tensor(out) or out.device != like.device or out.dtype != like.dtype
+            or tuple(out.shape) != tuple(like.shape) or not out.is_contiguous()):
+        raise ValueError(f"out must be a contiguous {like.dtype} tensor of shape {tuple(like.shape)} on {like.device}")
+    return out
+
+
 def apply_masks(mel: torch.Tensor, mask_params: torch.Tensor, mask_value: float = 0.0,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``mel`` CUDA float32 ``[B, R, T]`` (or ``[R, T]``), ``mask_params`` int32 ``[B, 4]`` = (t0, t1, f0, f1)."""
@@ -45,7 +53,7 @@ def apply_masks(mel: torch.Tensor, mask_params: torch.Tensor, mask_value: float 
     mp = torch.as_tensor(mask_params, dtype=torch.int32).to(x.device).contiguous()
     if tuple(mp.shape) != (B, 4):
         raise ValueError(f"mask_params must have shape {(B, 4)}")
-    res = torch.empty_like(x) if out is None else out
+    res = torch.empty_like(x) if out is None else _checked_out(out, x)
     with torch.cuda.device(x.device):
         _lib.check(lib.wft_specaug_apply_f32(x.data_ptr(), res.data_ptr(), B, R, T, mp.data_ptr(),
                                              float(mask_value), _stream_ptr(x.device)))
@@ -68,6 +76,11 @@ def draw_mask_params(seed: int, clip_offset: int, batch: int, n_mels: int, n_fra
 
 
 class _AxisMask:
+    """One torchaudio-style mask along ``_axis``.  The result has the input's dtype and stays on the autograd graph: float32
+    spectrograms go through ``wft_specaug_apply_f32`` (any ``mask_value``); fp16 / bf16 tensors and tensors that require
+    grad (the reference also applies these transforms to encoder activations, model/model_utils.py:404-405) go through the
+    differentiable ``mask_activations`` (``wft_mask_bsd``, fill 0)."""
+
     _axis = -1  # -1 time, -2 frequency
 
     def __init__(self, mask_param: int):
@@ -81,12 +94,20 @@ class _AxisMask:
         size = mel.shape[self._axis]
         a, b = _interval_from_global_rng(self.mask_param, size)
         dev = resolve_device(None, mel)
-        x = mel.to(dev, torch.float32)
+        x = mel.to(dev)
         lead = x.shape[:-2]
         x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
-        row = [a, b, 0, 0] if self._axis == -1 else [0, 0, a, b]
-        mp = torch.tensor([row] * x3.shape[0], dtype=torch.int32)
-        res = apply_masks(x3, mp, mask_value).reshape(*lead, x.shape[-2], x.shape[-1])
+        if x3.dtype == torch.float32 and not x3.requires_grad:
+            row = [a, b, 0, 0] if self._axis == -1 else [0, 0, a, b]
+            mp = torch.tensor([row] * x3.shape[0], dtype=torch.int32)
+            res = apply_masks(x3, mp, mask_value)
+        else:
+            if mask_value != 0.0:
+                raise ValueError("a non-zero mask_value is only supported for float32 tensors that do not require grad")
+            from .deep import mask_activations   # [B, S, D]: S is this tensor's frequency axis, D its time axis
+
+            res = mask_activations(x3, (0, 0), (a, b)) if self._axis == -1 else mask_activations(x3, (a, b), (0, 0))
+        res = res.reshape(*lead, x.shape[-2], x.shape[-1])
         return res if mel.is_cuda else res.to(mel.device)
 
 
@@ -124,10 +145,51 @@ def time_warp(mel: torch.Tensor, warp_params: torch.Tensor, out: Optional[torch.
     wp = torch.as_tensor(warp_params, dtype=torch.int32).to(x.device).contiguous()
     if tuple(wp.shape) != (B, 2):
         raise ValueError(f"warp_params must have shape {(B, 2)}")
-    res = torch.empty_like(x) if out is None else out
+    res = torch.empty_like(x) if out is None else _checked_out(out, x)
     with torch.cuda.device(x.device):
         _lib.check(lib.wft_time_warp_f32(x.data_ptr(), res.data_ptr(), B, R, T, wp.data_ptr(), _stream_ptr(x.device)))
     return res[0] if squeeze else res
+
+
+def augment_epilogue(mel: torch.Tensor, warp_params: Optional[torch.Tensor] = None,
+                     mask_params: Optional[torch.Tensor] = None, extremes: Optional[torch.Tensor] = None,
+                     mask_value: float = 0.0, out: Optional[torch.Tensor] = None, spline: str = "f64") -> torch.Tensor:
+    """Everything ``_calculate_mel`` does after ``pad_or_trim`` (data_loader.py:284-290), in one pass over the features:
+    time-warp -> time mask -> frequency mask -> extremes mask (``wft_augment_f32``).
+
+    ``mel`` CUDA float32 ``[B, R, T]``; ``warp_params`` int32 ``[B, 2]`` (``warp_p <= 0`` = leave the clip alone),
+    ``mask_params`` int32 ``[B, 4]``, ``extremes`` int32 ``[B, 2]`` = (rows masked from the bottom, from the top); any of
+    them may be ``None``.  ``spline="f32"`` restates the reference's float32 spline arithmetic, ``"f64"`` rounds once."""
+    lib = _lib.load()
+    if not mel.is_cuda or mel.dtype != torch.float32 or mel.dim() != 3:
+        raise ValueError("mel must be a CUDA float32 tensor of shape [B, R, T]")
+    if spline not in ("f32", "f64"):
+        raise ValueError("spline must be 'f32' or 'f64'")
+    x = mel.contiguous()
+    B, R, T = x.shape
+
+    def _i32(t, cols, name):
+        if t is None:
+            return None
+        t = torch.as_tensor(t, dtype=torch.int32).to(x.device).contiguous()
+        if tuple(t.shape) != (B, cols):
+            raise ValueError(f"{name} must have shape {(B, cols)}")
+        return t
+
+    wp, mp, ex = _i32(warp_params, 2, "warp_params"), _i32(mask_params, 4, "mask_params"), _i32(extremes, 2, "extremes")
+    if out is None:
+        res = torch.empty_like(x)
+    else:
+        res = out
+        if not res.is_cuda or res.dtype != torch.float32 or tuple(res.shape) != (B, R, T) or not res.is_contiguous():
+            raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {(B, R, T)}")
+        if wp is not None and res.data_ptr() == x.data_ptr():
+            raise ValueError("time warp cannot run in place")
+    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    with torch.cuda.device(x.device):
+        _lib.check(lib.wft_augment_f32(x.data_ptr(), res.data_ptr(), B, R, T, ptr(wp), ptr(mp), ptr(ex), float(mask_value),
+                                       1 if spline == "f32" else 0, _stream_ptr(x.device)))
+    return res
 
 
 def draw_warp_params(seed: int, clip_offset: int, batch: int, n_frames: int, time_warp_w: int, p: float = 1.0,
@@ -192,8 +254,5 @@ class ExtremesFrequencyMasking:
             rows.append((low, high))
         if not specs.is_cuda or specs.dtype != torch.float32 or not x.is_contiguous():
             raise ValueError("ExtremesFrequencyMasking expects a contiguous CUDA float32 spectrogram (in-place op)")
-        low_p = torch.tensor([[0, 0, 0, lo] for lo, _ in rows], dtype=torch.int32)
-        high_p = torch.tensor([[0, 0, n_mels - hi, n_mels] for _, hi in rows], dtype=torch.int32)
-        apply_masks(x, low_p, 0.0, out=x)
-        apply_masks(x, high_p, 0.0, out=x)
+        augment_epilogue(x, None, None, torch.tensor(rows, dtype=torch.int32), 0.0, out=x)
         return specs

@@ -71,7 +71,7 @@ constexpr int kTwFloats = WFT_TWIDDLE_TABLE_LEN;                 // 880
 constexpr int kTwRow = WFT_TWIDDLE_ROW;                          // 44
 constexpr int kMelWFloats = ((WFT_MEL80_W_LEN > WFT_MEL128_W_LEN ? WFT_MEL80_W_LEN : WFT_MEL128_W_LEN) + 3) & ~3;
 constexpr int kRing = 16;         // pending-tile FIFO slots in sm_ctl (power of two)
-constexpr int kCtlInts = 116;
+constexpr int kCtlInts = 120;
 constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats + kMelWFloats) * 4 + kCtlInts * 4;
 
 static_assert(kPFloats <= kAudioBase, "power tile and prefetched audio tile must not overlap");
@@ -106,10 +106,10 @@ __host__ __device__ constexpr int mel_warp_wstride(int w) {
   return NM == 80 ? a[w] : b[w];
 }
 
-struct ClipStat {
-  uint32_t max_enc;   // ordered-int encoding of max log10(mel) over ALL frames of the clip
-  uint32_t min_inv;   // ~encoding of min log10(mel) over the KEPT frames (pad value of pad_or_trim)
+struct ClipStat {      // {max_enc, done} share one aligned 8-byte word: ld_stat reads both with a single load
+  uint32_t max_enc;   // ordered-int encoding of max L2 = log2(mel) over ALL frames of the clip
   uint32_t done;      // tiles of this clip whose stat atomics have been performed (and values written)
+  uint32_t min_inv;   // ~encoding of min L2 over the KEPT frames (pad value of pad_or_trim)
   uint32_t pad_;
 };
 
@@ -134,6 +134,8 @@ struct FrontendParams {
   uint32_t zero;        // always 0; gives the completion counter a data dependency the compiler cannot fold
   uint32_t tpc_magic;   // floor(2^32 / tiles_per_clip): tile -> clip by multiply-high (+ one correction step)
   int32_t vec_ok;       // `out` is 32-byte aligned and n_frames_out % 8 == 0: the mel phase may use 32-byte stores
+  int32_t chunk;        // consecutive tiles a CTA takes per claim (>= 1): neighbours share the clip, so the per-clip loads of
+                        // describe_tile hit its memo and the tile counter sees 1 / chunk of the atomics
 };
 
 __device__ __forceinline__ uint32_t enc_ordered(float f) {
@@ -198,18 +200,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 }
 
 // interior tile: the 2800 samples travel as 9 bulk copies (8 blocks of 320 samples + a 240-sample tail), block b landing
-// at element (320 + skew) * b (the skew keeps stage A's stride-20 gathers conflict free).  Called by ONE thread, as a real
-// call (measured: inlining it, or spreading the 9 copies over 9 lanes, made the kernel 2 % slower).
+// at element (320 + skew) * b (the skew keeps stage A's stride-20 gathers conflict free).  The issue is SPLIT over the five
+// warps -- lane 0 of warp w sends blocks w and w + 5 and announces their bytes with its own arrive.expect_tx (the mbarrier
+// expects kWarps arrivals per phase): a single thread issuing all nine copies held its warp back by ~2000 cycles per tile
+// (per-warp clock stamps, tools/timeline.cu), and every phase of a tile ends on a CTA barrier.
 template <typename PcmT>
-__device__ __noinline__ void prefetch_audio(PcmT* __restrict__ sm_audio, const PcmT* __restrict__ src, uint64_t* bar) {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the region comes first
-  mbar_expect_tx(bar, kTileSamples * sizeof(PcmT));
+__device__ __forceinline__ void prefetch_audio_part(PcmT* __restrict__ sm_audio, const PcmT* __restrict__ src, uint64_t* bar, int warp) {
   constexpr int kBlocks = (kTileSamples + kSkewBlock - 1) / kSkewBlock;  // 9
-#pragma unroll 1
-  for (int b = 0; b < kBlocks; ++b) {
-    const int n = (b + 1) * kSkewBlock <= kTileSamples ? kSkewBlock : kTileSamples - b * kSkewBlock;
-    tma_bulk_g2s(sm_audio + b * (kSkewBlock + Skew<PcmT>::value), src + b * kSkewBlock, n * sizeof(PcmT), bar);
-  }
+  constexpr uint32_t kFull = kSkewBlock * sizeof(PcmT), kTail = (kTileSamples - (kBlocks - 1) * kSkewBlock) * sizeof(PcmT);
+  static_assert(kBlocks > kWarps && kBlocks <= 2 * kWarps, "every warp sends one or two blocks");
+  const int b1 = warp + kWarps;
+  const bool two = b1 < kBlocks;
+  const uint32_t bytes1 = b1 == kBlocks - 1 ? kTail : kFull;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the region comes first
+  mbar_expect_tx(bar, kFull + (two ? bytes1 : 0u));
+  tma_bulk_g2s(sm_audio + warp * (kSkewBlock + Skew<PcmT>::value), src + warp * kSkewBlock, kFull, bar);
+  if (two) tma_bulk_g2s(sm_audio + b1 * (kSkewBlock + Skew<PcmT>::value), src + b1 * kSkewBlock, bytes1, bar);
 }
 
 // generic synchronous staging (clip edges, ragged lengths, unaligned sources)
@@ -557,8 +563,11 @@ enum { kCtlDesc = 0, kCtlSlot = 16, kCtlRing = 32, kCtlRingClip = 48, kCtlRingMi
        kCtlRed = 80,    // 3 floats per warp (max, kept min, live min)
        kCtlMbar = 96,   // 8 bytes
        kCtlMemo = 100,  // describe_tile's per-clip memo: clip, len, keep, -, mask[4]
-       kCtlHead = 108, kCtlCount = 109, kCtlChain = 110, kCtlReady = 111, kCtlReadyClip = 112, kCtlDrain = 113, kCtlDrainClip = 114 };
-static_assert(kCtlDrainClip < kCtlInts && kCtlRed + 3 * kWarps <= kCtlMbar && kRing == 16, "sm_ctl layout");
+       kCtlHead = 108, kCtlCount = 109, kCtlChain = 110, kCtlReady = 111, kCtlReadyClip = 112, kCtlDrain = 113, kCtlDrainClip = 114,
+       kCtlChunkNext = 115,   // next tile of the chunk this CTA claimed, and how many of its tiles are still to be described
+       kCtlChunkLeft = 116,
+       kCtlPubClip = 117 };   // clip whose completion count is still owed (publish_finish), -1 = none
+static_assert(kCtlPubClip < kCtlInts && kCtlRed + 3 * kWarps <= kCtlMbar && kRing == 16, "sm_ctl layout");
 
 // how a tile's PCM reaches shared memory
 enum { kTileEdge = 0,      // reflection / zero extension / unaligned source: scalar staging
@@ -645,7 +654,17 @@ __device__ __forceinline__ void describe_tile(const TileGeom p, int t, int* __re
   *reinterpret_cast<int2*>(slot + 12) = make_int2(static_cast<int>(out_off & 0xffffffffll), static_cast<int>(out_off >> 32));
 }
 
-// acquire read of a clip's completion counter, then its maximum: pairs with the publisher's dependent atomics
+// One 8-byte snapshot {max_enc, done} of a clip's statistics.  A naturally aligned 64-bit load is single-copy atomic, and the
+// publisher performs its atomicMax on max_enc before the (data dependent) atomicAdd on done, so a snapshot whose `done` is
+// complete carries the clip's final maximum.  Relaxed on purpose: it is issued in the power phase and looked at after the
+// mel phase, and nothing waits for it in between (an acquire load here stalled thread 0 -- and with it a CTA barrier -- for
+// a full L2 round trip per tile).  Whoever goes on to READ other data of the clip (the fix-up) does ld_acquire first.
+__device__ __forceinline__ uint2 ld_stat(const ClipStat* st) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(st) : "memory");
+  return make_uint2(static_cast<uint32_t>(v), static_cast<uint32_t>(v >> 32));   // x = max_enc, y = done
+}
+// acquire read of a clip's completion counter: pairs with the publisher's dependent atomics
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* addr) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(addr) : "memory");
@@ -710,21 +729,27 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     }
   }
   uint64_t* audio_bar = reinterpret_cast<uint64_t*>(sm_ctl + kCtlMbar);  // completion of the audio tile's bulk copies
-  constexpr int kTmaThread = kThreads - 32;                               // the thread that issues the bulk copies
   if (tid == 0) {
     sm_ctl[kCtlMemo] = -1;
     sm_ctl[kCtlHead] = 0;
     sm_ctl[kCtlCount] = 0;
     sm_ctl[kCtlChain] = -1;
-    mbar_init(audio_bar, 1);
-    describe_tile<NM, PcmT>(tile_geom(p), static_cast<int>(atomicAdd(p.tile_counter, 1u)), sm_ctl + kCtlDesc, sm_ctl + kCtlMemo);
+    sm_ctl[kCtlPubClip] = -1;
+    mbar_init(audio_bar, kWarps);   // one arrive.expect_tx per warp and tile (prefetch_audio_part)
+    const int first = static_cast<int>(atomicAdd(p.tile_counter, static_cast<uint32_t>(p.chunk)));
+    sm_ctl[kCtlChunkNext] = first + 1;
+    sm_ctl[kCtlChunkLeft] = p.chunk - 1;
+    describe_tile<NM, PcmT>(tile_geom(p), first, sm_ctl + kCtlDesc, sm_ctl + kCtlMemo);
   }
   __syncthreads();
   // a tile of kind kTileInterior always arrives by TMA: the first one is sent here, every later one under the tile before it
-  if (tid == kTmaThread && sm_ctl[kCtlDesc + kDescKind] == kTileInterior) {
+  if (lane == 0 && sm_ctl[kCtlDesc + kDescKind] == kTileInterior) {
     const long long off = (static_cast<long long>(sm_ctl[kCtlDesc + kDescPcmHi]) << 32) | static_cast<unsigned int>(sm_ctl[kCtlDesc + kDescPcmLo]);
-    prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
+    prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
   }
+  // publication state of warp 0: lanes 0 / 1 hold what their atomicMax on the clip's max / min returned for the tile
+  // just finished; the completion count that depends on both is added one stage later (publish_finish)
+  uint32_t pub_dep = 0u;
   // loop state in ONE register: bit 4 (kCtlSlot) = descriptor slot of the CURRENT tile, bit 0 = parity of the audio mbarrier
   int lstate = 0;
 
@@ -744,14 +769,34 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
 #define DESC (sm_ctl + (launder(lstate) & kCtlSlot))
 #define NDESC (sm_ctl + ((launder(lstate) & kCtlSlot) ^ kCtlSlot))
 #define DESC4 (*reinterpret_cast<const int4*>(DESC))
+    // thread 0: the tile after the current one = the next tile of the claimed chunk, or the first tile of the chunk just claimed
+#define DESCRIBE_NEXT()                                                                              \
+  do {                                                                                               \
+    const int left_ = sm_ctl[kCtlChunkLeft];                                                         \
+    const int t_ = left_ == 0 ? nxt_claim : sm_ctl[kCtlChunkNext];                                   \
+    sm_ctl[kCtlChunkLeft] = left_ == 0 ? p.chunk - 1 : left_ - 1;                                    \
+    sm_ctl[kCtlChunkNext] = t_ + 1;                                                                  \
+    describe_tile<NM, PcmT>(tile_geom(p), t_, NDESC, sm_ctl + kCtlMemo);                             \
+  } while (0)
+    // warp 0, lanes 0 / 1: the completion count of the tile published one stage ago, now that both atomics have returned
+    // (true data dependency through p.zero: no fence, nobody waited for them)
+#define PUBLISH_FINISH()                                                                             \
+  do {                                                                                               \
+    const uint32_t dep_ = pub_dep | __shfl_sync(0x3u, pub_dep, 1);                                   \
+    const int pc_ = sm_ctl[kCtlPubClip];                                                             \
+    if (lane == 0 && pc_ >= 0) {                                                                     \
+      atomicAdd(&p.stats[pc_].done, 1u + (dep_ & p.zero));                                           \
+      sm_ctl[kCtlPubClip] = -1;                                                                      \
+    }                                                                                                \
+  } while (0)
     const int4 d_top = DESC4;
     if (d_top.x >= p.total_tiles) break;
     WFT_TL(0);
     // claim the tile AFTER this one now; the answer is consumed two barriers later (latency hidden by stage A)
     int nxt_claim = 0;
-    if (tid == 0) nxt_claim = static_cast<int>(atomicAdd(p.tile_counter, 1u));
+    if (tid == 0 && sm_ctl[kCtlChunkLeft] == 0) nxt_claim = static_cast<int>(atomicAdd(p.tile_counter, static_cast<uint32_t>(p.chunk)));
     // thread 0: (max, done) of the clips of the two oldest pending tiles, sampled early, looked at after the mel phase
-    uint32_t seen_max0 = 0u, seen_done0 = 0u, seen_max1 = 0u, seen_done1 = 0u;
+    uint2 seen0 = make_uint2(0u, 0u), seen1 = make_uint2(0u, 0u);   // x = max_enc, y = done
 
     if (d_top.z < p.n_frames && d_top.w != kTileSilent && d_top.w != kTileSilentRest) {
       // stage 0 ---------------------------------------------------------------------------------------------
@@ -807,7 +852,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           e2[k1 * (kRowStride / 2)] = make_float2(x[k1].x * t.z - x[k1].y * t.w, fmaf(x[k1].x, t.w, x[k1].y * t.z));
         }
       }
-      if (tid == 0) describe_tile<NM, PcmT>(tile_geom(p), nxt_claim, NDESC, sm_ctl + kCtlMemo);
+      WFT_TL(15);
+      if (warp == 0 && lane < 2) PUBLISH_FINISH();
+      if (tid == 0) DESCRIBE_NEXT();
       WFT_TL(4);
       __syncthreads();
       WFT_TL(5);
@@ -844,22 +891,16 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         __syncthreads();  // exchange is dead: the region becomes power tile (bottom) + next audio tile (top)
         WFT_TL(7);
         // prefetch the NEXT tile's PCM into the top of the region (its descriptor stays in sm_ctl until the loop ends)
-        if (tid == kTmaThread && NDESC[kDescKind] == kTileInterior) {
+        if (lane == 0 && NDESC[kDescKind] == kTileInterior) {
           const long long off = (static_cast<long long>(NDESC[kDescPcmHi]) << 32) | static_cast<unsigned int>(NDESC[kDescPcmLo]);
-          prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
+          WFT_TL(13);
+          prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
+          WFT_TL(14);
         }
         if (tid == 0) {
           const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
-          if (n > 0) {
-            const ClipStat* st = p.stats + sm_ctl[kCtlRingClip + head];
-            seen_done0 = ld_acquire(&st->done);
-            seen_max0 = ld_relaxed(&st->max_enc);
-          }
-          if (n > 1) {
-            const ClipStat* st = p.stats + sm_ctl[kCtlRingClip + ((head + 1) & (kRing - 1))];
-            seen_done1 = ld_acquire(&st->done);
-            seen_max1 = ld_relaxed(&st->max_enc);
-          }
+          if (n > 0) seen0 = ld_stat(p.stats + sm_ctl[kCtlRingClip + head]);
+          if (n > 1) seen1 = ld_stat(p.stats + sm_ctl[kCtlRingClip + ((head + 1) & (kRing - 1))]);
         }
 
         // power tile [bin][frame]: the pair's two frames are neighbours, one 8-byte store per bin
@@ -930,24 +971,17 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       // nothing to compute: a pad-only tile (n_frames_out > n_frames) or a silent tile (all-zero PCM: every mel value is
       // the 1e-10 clamp, so only its statistics are recorded here and the fix-up later writes the constant rows)
       __syncthreads();  // the previous tile's last readers of the other descriptor slot are done
-      if (tid == 0) describe_tile<NM, PcmT>(tile_geom(p), nxt_claim, NDESC, sm_ctl + kCtlMemo);
+      if (warp == 0 && lane < 2) PUBLISH_FINISH();
+      if (tid == 0) DESCRIBE_NEXT();
       __syncthreads();
-      if (tid == kTmaThread && NDESC[kDescKind] == kTileInterior) {
+      if (lane == 0 && NDESC[kDescKind] == kTileInterior) {
         const long long off = (static_cast<long long>(NDESC[kDescPcmHi]) << 32) | static_cast<unsigned int>(NDESC[kDescPcmLo]);
-        prefetch_audio<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar);
+        prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
       }
       if (tid == 0) {
         const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
-        if (n > 0) {
-          const ClipStat* st = p.stats + sm_ctl[kCtlRingClip + head];
-          seen_done0 = ld_acquire(&st->done);
-          seen_max0 = ld_relaxed(&st->max_enc);
-        }
-        if (n > 1) {
-          const ClipStat* st = p.stats + sm_ctl[kCtlRingClip + ((head + 1) & (kRing - 1))];
-          seen_done1 = ld_acquire(&st->done);
-          seen_max1 = ld_relaxed(&st->max_enc);
-        }
+        if (n > 0) seen0 = ld_stat(p.stats + sm_ctl[kCtlRingClip + head]);
+        if (n > 1) seen1 = ld_stat(p.stats + sm_ctl[kCtlRingClip + ((head + 1) & (kRing - 1))]);
       }
       if (lane == 0) {
         const int clip = d_top.y, t0 = d_top.z, kind = d_top.w;   // (short path: the loop-top read is still in registers)
@@ -966,26 +1000,28 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     if (tid == 0) {
       const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
       int ready = -1, ready_clip = 0, pops = 0;
-      if (n > 0 && seen_done0 >= tiles_per_clip_u) {
+      if (n > 0 && seen0.y >= tiles_per_clip_u) {
         const int e = sm_ctl[kCtlRing + head], ec = sm_ctl[kCtlRingClip + head];
         pops = 1;
         if ((e & kSilentBit) != 0 ||
-            tile_needs_fixup(__int_as_float(sm_ctl[kCtlRingMin + head]), seen_max0, ((e & kTileIdMask) - ec * p.tiles_per_clip) * kTileFrames,
+            tile_needs_fixup(__int_as_float(sm_ctl[kCtlRingMin + head]), seen0.x, ((e & kTileIdMask) - ec * p.tiles_per_clip) * kTileFrames,
                              kept_frames(p.n_valid, ec, p.n_frames), p.n_frames_out)) {
           ready = e;
           ready_clip = ec;
-        } else if (n > 1 && seen_done1 >= tiles_per_clip_u) {
+        } else if (n > 1 && seen1.y >= tiles_per_clip_u) {
           const int h1 = (head + 1) & (kRing - 1);
           const int e1 = sm_ctl[kCtlRing + h1], ec1 = sm_ctl[kCtlRingClip + h1];
           pops = 2;
           if ((e1 & kSilentBit) != 0 ||
-              tile_needs_fixup(__int_as_float(sm_ctl[kCtlRingMin + h1]), seen_max1, ((e1 & kTileIdMask) - ec1 * p.tiles_per_clip) * kTileFrames,
+              tile_needs_fixup(__int_as_float(sm_ctl[kCtlRingMin + h1]), seen1.x, ((e1 & kTileIdMask) - ec1 * p.tiles_per_clip) * kTileFrames,
                                kept_frames(p.n_valid, ec1, p.n_frames), p.n_frames_out)) {
             ready = e1;
             ready_clip = ec1;
           }
         }
       }
+      // a fix-up reads more of the clip than the snapshot (its minimum, through L2): acquire before anybody does
+      if (ready >= 0) (void)ld_acquire(&p.stats[ready_clip].done);
       sm_ctl[kCtlHead] = (head + pops) & (kRing - 1);
       sm_ctl[kCtlCount] = n - pops;
       sm_ctl[kCtlReady] = ready;
@@ -995,9 +1031,11 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     __syncthreads();  // tile finished: power tile free, ready tile and per-warp max/min visible
     WFT_TL(11);
 
-    // publish the tile's statistics: two returning atomics, then the completion count with a true data dependency on
-    // their results (through p.zero) -- no fence, so nobody waits for the tile's stores to drain.  The tile itself
-    // joins the pending FIFO (or is parked: a CTA never waits while tiles are unclaimed).
+    // publish the tile's statistics: lane 0 / lane 1 of warp 0 issue the returning atomicMax on the clip's max / min and
+    // move on; the completion count -- which must not become visible before both -- is added with a true data dependency
+    // on their results at the next tile's describe point (PUBLISH_FINISH), when they have long returned.  No fence, and
+    // nobody waits: done in-line, this chain cost warp 0 two L2 round trips per tile in front of a CTA barrier.  The tile
+    // itself joins the pending FIFO (or is parked: a CTA never waits while tiles are unclaimed).
     if (warp == 0) {
       const float* red = reinterpret_cast<const float*>(sm_ctl + kCtlRed) + 3 * (lane < kWarps ? lane : 0);
       float mx = lane < kWarps ? red[0] : -INFINITY;
@@ -1006,27 +1044,29 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       mx = warp_max(mx);
       mn_kept = warp_min(mn_kept);
       mn_live = warp_min(mn_live);
-      if (lane == 0) {
+      if (lane < 2) {
         const int4 d_pub = DESC4;
         const int cur = d_pub.x, clip = d_pub.y;
-        const bool silent = (d_pub.w == kTileSilent || d_pub.w == kTileSilentRest) && d_pub.z < p.n_frames;
         ClipStat* cs = p.stats + clip;
-        uint32_t dep = 0;
-        if (mx > -INFINITY) dep |= atomicMax(&cs->max_enc, enc_ordered(mx));
-        if (mn_kept < INFINITY) dep |= atomicMax(&cs->min_inv, ~enc_ordered(mn_kept));
-        const int tagged = cur | (silent ? kSilentBit : 0);
-        const int n = sm_ctl[kCtlCount];
-        if (n < kRing) {
-          const int slot = (sm_ctl[kCtlHead] + n) & (kRing - 1);
-          sm_ctl[kCtlRing + slot] = tagged;
-          sm_ctl[kCtlRingClip + slot] = clip;
-          sm_ctl[kCtlRingMin + slot] = __float_as_int(mn_live);
-          sm_ctl[kCtlCount] = n + 1;
-        } else {
-          p.next[cur] = sm_ctl[kCtlChain];           // parked tiles are re-examined (conservatively) in the drain
-          sm_ctl[kCtlChain] = tagged;
+        const bool has = lane == 0 ? mx > -INFINITY : mn_kept < INFINITY;
+        pub_dep = 0u;
+        if (has) pub_dep = atomicMax(lane == 0 ? &cs->max_enc : &cs->min_inv, lane == 0 ? enc_ordered(mx) : ~enc_ordered(mn_kept));
+        if (lane == 0) {
+          const bool silent = (d_pub.w == kTileSilent || d_pub.w == kTileSilentRest) && d_pub.z < p.n_frames;
+          const int tagged = cur | (silent ? kSilentBit : 0);
+          const int n = sm_ctl[kCtlCount];
+          if (n < kRing) {
+            const int slot = (sm_ctl[kCtlHead] + n) & (kRing - 1);
+            sm_ctl[kCtlRing + slot] = tagged;
+            sm_ctl[kCtlRingClip + slot] = clip;
+            sm_ctl[kCtlRingMin + slot] = __float_as_int(mn_live);
+            sm_ctl[kCtlCount] = n + 1;
+          } else {
+            p.next[cur] = sm_ctl[kCtlChain];           // parked tiles are re-examined (conservatively) in the drain
+            sm_ctl[kCtlChain] = tagged;
+          }
+          sm_ctl[kCtlPubClip] = clip;
         }
-        atomicAdd(&cs->done, 1u + (dep & p.zero));
       }
       __syncwarp();
     }
@@ -1035,9 +1075,12 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     WFT_TL(12);
     lstate ^= kCtlSlot;   // the next tile becomes current; its slot is rewritten only behind the tile-after-next's first barrier
   }
+  if (warp == 0 && lane < 2) PUBLISH_FINISH();   // the last tile's completion count
 #undef DESC
 #undef NDESC
 #undef DESC4
+#undef DESCRIBE_NEXT
+#undef PUBLISH_FINISH
 
   // drain: every tile is claimed by a running CTA now, so waiting on a clip's counter is safe
   for (;;) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -14,6 +15,7 @@ namespace {
 
 thread_local std::string g_last_error;
 thread_local int64_t g_launches = 0;
+int g_debug_chunk = 0;      // WFT_DEBUG_CHUNK (development): force the tiles-per-claim of the fused kernel
 int g_debug_max_ctas = 0;   // wft_debug_set_max_ctas: caps the persistent grid (tests of the parked-tile / drain paths)
 
 int fail(int code, const std::string& msg) {
@@ -60,12 +62,21 @@ int grid_for(KernelT kernel, GridInfo* cache, int* ctas) {
 template <int NM, typename PcmT>
 int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream) {
   static GridInfo cache[64];
+  static const bool env_read = [] {
+    if (const char* e = getenv("WFT_DEBUG_CHUNK")) g_debug_chunk = atoi(e);
+    return true;
+  }();
+  (void)env_read;
   int ctas = 0;
   int rc = grid_for(wft::frontend_kernel<NM, PcmT>, cache, &ctas);
   if (rc != WFT_OK) return rc;
   if (ctas > p.total_tiles) ctas = p.total_tiles;
   if (g_debug_max_ctas > 0 && ctas > g_debug_max_ctas) ctas = g_debug_max_ctas;
-  wft::frontend_kernel<NM, PcmT><<<ctas, wft::kThreads, wft::kSmemBytes, stream>>>(p);
+  // tiles a CTA takes per claim: at most 1/24 of its share (measured: chunks of 8 at 54 tiles per CTA cost 5 % in the tail)
+  wft::FrontendParams q = p;
+  const int per_cta = p.total_tiles / ctas;
+  q.chunk = g_debug_chunk > 0 ? g_debug_chunk : (per_cta / 24 < 1 ? 1 : (per_cta / 24 > 4 ? 4 : per_cta / 24));
+  wft::frontend_kernel<NM, PcmT><<<ctas, wft::kThreads, wft::kSmemBytes, stream>>>(q);
   ++g_launches;
   WFT_CUDA(cudaGetLastError());
   return WFT_OK;
@@ -238,59 +249,8 @@ __global__ void specaug_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t
 }
 
 
-// SpecAugment time-warp (data/utils.py:95-143): out[b, r, t] = bilinear sample of in[b] at the source frame given by a
-// cubic Hermite spline through (0,-1), (warp_p, (warp_p - warp_d) * 2 / (T-1) - 1), (T-1, 1) in grid_sample's normalised
-// (align_corners=True) coordinates, zeros outside.  The spline is evaluated in float64 and rounded once; the bilinear
-// stage mirrors torch.nn.functional.grid_sample's float32 arithmetic.  warp_params is device int32 [B,2] = (warp_p, warp_d).
-__global__ void time_warp_kernel(const float* __restrict__ in, float* __restrict__ out, int32_t n_rows, int32_t n_frames,
-                                 const int32_t* __restrict__ warp_params) {
-  const int b = blockIdx.z;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_frames) return;
-  const int2 wp = __ldg(reinterpret_cast<const int2*>(warp_params) + b);
-  const int T = n_frames, R = n_rows;
-  // source coordinate of output frame t
-  const double x1 = static_cast<double>(wp.x), x2 = static_cast<double>(T - 1);
-  const double y0 = -1.0, y1 = static_cast<double>(wp.x - wp.y) * 2.0 / (T - 1.0) - 1.0, y2 = 1.0;
-  const double s0 = (y1 - y0) / x1, s1 = (y2 - y1) / (x2 - x1);
-  const double m0 = s0, m1 = 0.5 * (s0 + s1), m2 = s1;
-  const bool second = static_cast<double>(t) > x1;
-  const double xa = second ? x1 : 0.0, dx = second ? (x2 - x1) : x1;
-  const double ya = second ? y1 : y0, yb = second ? y2 : y1, ma = second ? m1 : m0, mb = second ? m2 : m1;
-  const double u = (static_cast<double>(t) - xa) / dx, u2 = u * u, u3 = u2 * u;
-  const double gx64 = (1.0 - 3.0 * u2 + 2.0 * u3) * ya + (u - 2.0 * u2 + u3) * ma * dx + (3.0 * u2 - 2.0 * u3) * yb +
-                      (-u2 + u3) * mb * dx;
-  const float gx = static_cast<float>(gx64);
-  const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(T - 1);
-  const float ix0f = floorf(ix);
-  const int ix0 = static_cast<int>(ix0f), ix1 = ix0 + 1;
-  const float wx1 = ix - ix0f, wx0 = (ix0f + 1.0f) - ix;
-  const float step = 2.0f / static_cast<float>(R - 1);  // torch.linspace(-1, 1, R)
-  const size_t clip = static_cast<size_t>(b) * R * T;
-  for (int r = blockIdx.y; r < R; r += gridDim.y) {
-    const float gy = (r < R / 2) ? (-1.0f + step * static_cast<float>(r)) : (1.0f - step * static_cast<float>(R - 1 - r));
-    const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
-    const float iy0f = floorf(iy);
-    const int iy0 = static_cast<int>(iy0f), iy1 = iy0 + 1;
-    const float wy1 = iy - iy0f, wy0 = (iy0f + 1.0f) - iy;
-    float acc = 0.0f;
-    const bool cx0 = ix0 >= 0 && ix0 < T, cx1 = ix1 >= 0 && ix1 < T;
-    if (iy0 >= 0 && iy0 < R) {
-      const float* row = in + clip + static_cast<size_t>(iy0) * T;
-      if (cx0) acc += __ldg(row + ix0) * (wx0 * wy0);
-      if (cx1) acc += __ldg(row + ix1) * (wx1 * wy0);
-    }
-    if (iy1 >= 0 && iy1 < R && wy1 != 0.0f) {
-      const float* row = in + clip + static_cast<size_t>(iy1) * T;
-      if (cx0) acc += __ldg(row + ix0) * (wx0 * wy1);
-      if (cx1) acc += __ldg(row + ix1) * (wx1 * wy1);
-    }
-    out[clip + static_cast<size_t>(r) * T + t] = acc;
-  }
-}
-
 // counter-based draw of (warp_p, warp_d): warp_p uniform in [W, T-W), warp_d uniform in [-W, W) (the reference's randint
-// ranges, data/utils.py:107-111), Philox block 2 of the clip's counter; (T/2, 0) == identity when the p gate rejects
+// ranges, data/utils.py:107-111), Philox block 2 of the clip's counter; (-1, 0) == "no warp" when the p gate rejects
 __global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t W,
                                       float p, int32_t* __restrict__ out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,7 +264,7 @@ __global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32
     philox4x32_10(lo, hi, 1u, 0u, k0, k1, g);
     apply = u01(g[0]) < p;
   }
-  int2 w = make_int2(n_frames / 2, 0);
+  int2 w = make_int2(-1, 0);   // "no warp": the warp kernels copy such a clip
   if (apply && W > 0 && n_frames > 2 * W) {
     uint32_t r[4];
     philox4x32_10(lo, hi, 2u, 0u, k0, k1, r);
@@ -312,6 +272,151 @@ __global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32
     w.y = -W + static_cast<int>(__fmul_rn(u01(r[1]), static_cast<float>(2 * W)));
   }
   reinterpret_cast<int2*>(out)[b] = w;
+}
+
+// ---- fused augmentation epilogue: time-warp -> time mask -> frequency mask -> extremes mask in ONE read + write of the
+// features (data_loader.py:284-290: time_warping, time_masking, freq_masking, extreme_freq_masking).  Every step after the
+// warp only overwrites cells with the mask value, so out[b, r, t] = masked(b, r, t) ? mask_value : warp(in[b])[r, t].
+//
+// Source coordinate of output frame t (normalised, align_corners): the reference's 3-knot cubic Hermite spline
+// (data/utils.py:65-93).  kF32 = false evaluates it in float64 and rounds once; kF32 = true restates the reference's own
+// float32 evaluation order (knot slopes, (xs - x0) / dx, powers of t, the 4x4 basis product as a k-ascending FMA chain, the
+// four products summed left to right) so that the coordinate lands on the reference's float32 value wherever torch's pow
+// returns the correctly rounded power.
+template <bool kF32>
+__device__ __forceinline__ float warp_source_coord(int t, int T, int warp_p, int warp_d) {
+  if (kF32) {
+    const float y0 = -1.0f, y2 = 1.0f;
+    const float y1 = __fsub_rn(__fdiv_rn(static_cast<float>((warp_p - warp_d) * 2), static_cast<float>(T - 1)), 1.0f);
+    const float dxa = static_cast<float>(warp_p), dxb = static_cast<float>(T - 1 - warp_p);
+    const float s0 = __fdiv_rn(__fsub_rn(y1, y0), dxa), s1 = __fdiv_rn(__fsub_rn(y2, y1), dxb);
+    const float mm = __fdiv_rn(__fadd_rn(s1, s0), 2.0f);
+    const bool second = t > warp_p;
+    const float xa = second ? static_cast<float>(warp_p) : 0.0f, dx = second ? dxb : dxa;
+    const float ya = second ? y1 : y0, yb = second ? y2 : y1, ma = second ? mm : s0, mb = second ? s1 : mm;
+    const float u = __fdiv_rn(__fsub_rn(static_cast<float>(t), xa), dx);
+    const float u2 = __fmul_rn(u, u);
+    const float u3 = static_cast<float>(static_cast<double>(u) * static_cast<double>(u) * static_cast<double>(u));
+    // A @ [1, u, u2, u3]^T, rows of A = (1,0,-3,2), (0,1,-2,1), (0,0,3,-2), (0,0,-1,1)
+    const float h0 = __fmaf_rn(2.0f, u3, __fmaf_rn(-3.0f, u2, 1.0f));
+    const float h1 = __fmaf_rn(1.0f, u3, __fmaf_rn(-2.0f, u2, u));
+    const float h2 = __fmaf_rn(-2.0f, u3, __fmul_rn(3.0f, u2));
+    const float h3 = __fmaf_rn(1.0f, u3, __fmul_rn(-1.0f, u2));
+    float g = __fmul_rn(h0, ya);
+    g = __fadd_rn(g, __fmul_rn(__fmul_rn(h1, ma), dx));
+    g = __fadd_rn(g, __fmul_rn(h2, yb));
+    g = __fadd_rn(g, __fmul_rn(__fmul_rn(h3, mb), dx));
+    return g;
+  } else {
+    const double x1 = static_cast<double>(warp_p), x2 = static_cast<double>(T - 1);
+    const double y0 = -1.0, y1 = static_cast<double>(warp_p - warp_d) * 2.0 / (T - 1.0) - 1.0, y2 = 1.0;
+    const double s0 = (y1 - y0) / x1, s1 = (y2 - y1) / (x2 - x1);
+    const double m0 = s0, m1 = 0.5 * (s0 + s1), m2 = s1;
+    const bool second = static_cast<double>(t) > x1;
+    const double xa = second ? x1 : 0.0, dx = second ? (x2 - x1) : x1;
+    const double ya = second ? y1 : y0, yb = second ? y2 : y1, ma = second ? m1 : m0, mb = second ? m2 : m1;
+    const double u = (static_cast<double>(t) - xa) / dx, u2 = u * u, u3 = u2 * u;
+    return static_cast<float>((1.0 - 3.0 * u2 + 2.0 * u3) * ya + (u - 2.0 * u2 + u3) * ma * dx + (3.0 * u2 - 2.0 * u3) * yb +
+                              (-u2 + u3) * mb * dx);
+  }
+}
+
+constexpr int kAugThreads = 256;
+constexpr int kAugFramesPerThread = 4;
+constexpr int kAugRowsPerCta = 16;
+
+// grid = (frame blocks of 1024, row groups of 16, clips); a thread owns 4 consecutive output frames: it evaluates the source
+// coordinates once and walks the 16 rows of its group (bilinear taps mirror grid_sample's float32 arithmetic, zeros outside).
+template <bool kF32>
+__global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                             int32_t R, int32_t T, const int32_t* __restrict__ warp_params,
+                                                             const int32_t* __restrict__ mask_params,
+                                                             const int32_t* __restrict__ extremes, float mask_value) {
+  const int b = blockIdx.z;
+  const int tbase = (blockIdx.x * kAugThreads + threadIdx.x) * kAugFramesPerThread;
+  if (tbase >= T) return;
+  int wp = -1, wd = 0;
+  if (warp_params != nullptr) {
+    const int2 w = __ldg(reinterpret_cast<const int2*>(warp_params) + b);
+    wp = w.x; wd = w.y;
+  }
+  int4 mk = make_int4(0, 0, 0, 0);
+  if (mask_params != nullptr) mk = __ldg(reinterpret_cast<const int4*>(mask_params) + b);
+  int lo_rows = 0, hi_rows = 0;
+  if (extremes != nullptr) {
+    const int2 e = __ldg(reinterpret_cast<const int2*>(extremes) + b);
+    lo_rows = e.x; hi_rows = e.y;
+  }
+  const bool warp = wp > 0 && wp < T - 1;          // anything else (the draw's "gate rejected" marker is -1) = no warp
+  int ix0[kAugFramesPerThread];
+  float wx0[kAugFramesPerThread], wx1[kAugFramesPerThread];
+  bool tmask[kAugFramesPerThread];
+#pragma unroll
+  for (int k = 0; k < kAugFramesPerThread; ++k) {
+    const int t = tbase + k;
+    tmask[k] = t >= mk.x && t < mk.y;
+    ix0[k] = t; wx0[k] = 1.0f; wx1[k] = 0.0f;
+    if (warp && t < T) {
+      const float gx = warp_source_coord<kF32>(t, T, wp, wd);
+      const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(T - 1);
+      const float f = floorf(ix);
+      ix0[k] = static_cast<int>(f);
+      wx1[k] = ix - f;
+      wx0[k] = (f + 1.0f) - ix;
+    }
+  }
+  const bool vec = (T & 3) == 0 && tbase + kAugFramesPerThread <= T;
+  const float step = 2.0f / static_cast<float>(R - 1);  // torch.linspace(-1, 1, R)
+  const size_t clip = static_cast<size_t>(b) * R * T;
+  const int r_end = min(R, static_cast<int>(blockIdx.y + 1) * kAugRowsPerCta);
+  for (int r = blockIdx.y * kAugRowsPerCta; r < r_end; ++r) {
+    float v[kAugFramesPerThread];
+    const bool rowmask = (r >= mk.z && r < mk.w) || r < lo_rows || r >= R - hi_rows;
+    if (rowmask) {
+#pragma unroll
+      for (int k = 0; k < kAugFramesPerThread; ++k) v[k] = mask_value;
+    } else if (!warp) {
+      const float* row = in + clip + static_cast<size_t>(r) * T;
+#pragma unroll
+      for (int k = 0; k < kAugFramesPerThread; ++k) v[k] = (tmask[k] || tbase + k >= T) ? mask_value : __ldg(row + tbase + k);
+    } else {
+      const float gy = (r < R / 2) ? (-1.0f + step * static_cast<float>(r)) : (1.0f - step * static_cast<float>(R - 1 - r));
+      const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
+      const float iy0f = floorf(iy);
+      const int iy0 = static_cast<int>(iy0f), iy1 = iy0 + 1;
+      const float wy1 = iy - iy0f, wy0 = (iy0f + 1.0f) - iy;
+      const bool use0 = iy0 >= 0 && iy0 < R, use1 = iy1 >= 0 && iy1 < R && wy1 != 0.0f;
+      const float* row0 = in + clip + static_cast<size_t>(use0 ? iy0 : 0) * T;
+      const float* row1 = in + clip + static_cast<size_t>(use1 ? iy1 : 0) * T;
+#pragma unroll
+      for (int k = 0; k < kAugFramesPerThread; ++k) {
+        float acc = 0.0f;
+        if (!tmask[k] && tbase + k < T) {
+          const int a = ix0[k], c = a + 1;
+          const bool ca = a >= 0 && a < T, cc = c >= 0 && c < T;
+          if (use0) {
+            if (ca) acc += __ldg(row0 + a) * (wx0[k] * wy0);
+            if (cc) acc += __ldg(row0 + c) * (wx1[k] * wy0);
+          }
+          if (use1) {
+            if (ca) acc += __ldg(row1 + a) * (wx0[k] * wy1);
+            if (cc) acc += __ldg(row1 + c) * (wx1[k] * wy1);
+          }
+        } else {
+          acc = mask_value;
+        }
+        v[k] = acc;
+      }
+    }
+    float* dst = out + clip + static_cast<size_t>(r) * T + tbase;
+    if (vec) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kAugFramesPerThread; ++k)
+        if (tbase + k < T) dst[k] = v[k];
+    }
+  }
 }
 
 int grid_1d(int64_t n, int threads) {
@@ -532,21 +637,39 @@ int wft_specaug_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t
   return WFT_OK;
 }
 
-int wft_time_warp_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames,
-                      const int32_t* warp_params, void* stream_) {
+int wft_augment_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
+                    const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (batch < 0 || n_rows < 0 || n_frames < 0) return fail(WFT_ERR_INVALID, "negative extent");
   if (static_cast<int64_t>(batch) * n_rows * n_frames == 0) return WFT_OK;
-  if (in == nullptr || out == nullptr || warp_params == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
-  if (in == out) return fail(WFT_ERR_INVALID, "time warp cannot run in place");
-  if (n_rows < 2 || n_frames < 3) return fail(WFT_ERR_INVALID, "time warp needs at least 2 rows and 3 frames");
-  if ((reinterpret_cast<uintptr_t>(warp_params) & 7) != 0) return fail(WFT_ERR_INVALID, "warp_params must be 8-byte aligned");
+  if (in == nullptr || out == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
+  if (warp_params != nullptr) {
+    if (in == out) return fail(WFT_ERR_INVALID, "time warp cannot run in place");
+    if (n_rows < 2 || n_frames < 3) return fail(WFT_ERR_INVALID, "time warp needs at least 2 rows and 3 frames");
+    if ((reinterpret_cast<uintptr_t>(warp_params) & 7) != 0) return fail(WFT_ERR_INVALID, "warp_params must be 8-byte aligned");
+  }
+  if (mask_params != nullptr && (reinterpret_cast<uintptr_t>(mask_params) & 15) != 0)
+    return fail(WFT_ERR_INVALID, "mask_params must be 16-byte aligned");
+  if (extremes != nullptr && (reinterpret_cast<uintptr_t>(extremes) & 7) != 0)
+    return fail(WFT_ERR_INVALID, "extremes must be 8-byte aligned");
+  if ((n_frames & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0)
+    return fail(WFT_ERR_INVALID, "in and out must be 16-byte aligned");
   if (batch > 65535) return fail(WFT_ERR_INVALID, "batch too large for one launch (max 65535)");
-  dim3 grid((n_frames + 255) / 256, n_rows < 16 ? n_rows : 16, batch);
-  time_warp_kernel<<<grid, 256, 0, stream>>>(in, out, n_rows, n_frames, warp_params);
+  const int per_cta = kAugThreads * kAugFramesPerThread;
+  dim3 grid((n_frames + per_cta - 1) / per_cta, (n_rows + kAugRowsPerCta - 1) / kAugRowsPerCta, batch);
+  if (spline_f32)
+    augment_kernel<true><<<grid, kAugThreads, 0, stream>>>(in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value);
+  else
+    augment_kernel<false><<<grid, kAugThreads, 0, stream>>>(in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value);
   ++g_launches;
   WFT_CUDA(cudaGetLastError());
   return WFT_OK;
+}
+
+int wft_time_warp_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames,
+                      const int32_t* warp_params, void* stream_) {
+  if (static_cast<int64_t>(batch) * n_rows * n_frames != 0 && warp_params == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
+  return wft_augment_f32(in, out, batch, n_rows, n_frames, warp_params, nullptr, nullptr, 0.0f, 0, stream_);
 }
 
 int wft_time_warp_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t time_warp_w, float p,

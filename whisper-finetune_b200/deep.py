@@ -64,39 +64,63 @@ def draw_deep_spans(seq: int, dim: int, time_mask_param: int, freq_mask_param: i
     return t, f
 
 
+class DeepSpecAugment:
+    """Deep SpecAugment for ONE model: the gate, the two mask widths and the hooks that apply them.
+
+    ``attach(model)`` installs a forward pre-hook on the encoder (rolls the ``p`` gate once per encoder forward, so that a
+    gradient-checkpoint recomputation of the same forward sees the same decision) and a forward hook on ``attn_ln`` of the
+    selected blocks (masks the normalised activations while training and the gate is open)."""
+
+    def __init__(self, time_mask_param: int, freq_mask_param: int, p: float = 1.0):
+        p = float(p)
+        if not 0.0 <= p <= 1.0:
+            raise ValueError(f"deep_spec_augment p must be between 0 and 1, got {p}")
+        self.time_mask_param = int(time_mask_param)
+        self.freq_mask_param = int(freq_mask_param)
+        self.p = p
+        self.gate_open = False
+        self.handles = []
+
+    def roll_gate(self) -> bool:
+        """p >= 1 / p <= 0 decide without touching the RNG, like the reference; otherwise one ``torch.rand(1)``."""
+        if self.p >= 1.0 or self.p <= 0.0:
+            return self.p >= 1.0
+        return torch.rand(1).item() < self.p
+
+    def on_encoder_forward(self, encoder, args):
+        self.gate_open = self.roll_gate()
+
+    def on_attn_ln(self, layer_norm, args, normed):
+        if not (layer_norm.training and self.gate_open):
+            return normed
+        time_span, feature_span = draw_deep_spans(normed.shape[1], normed.shape[2], self.time_mask_param, self.freq_mask_param)
+        return mask_activations(normed, time_span, feature_span)
+
+    @staticmethod
+    def hooked_blocks(n_blocks: int, layer_indices: Optional[Iterable[int]]):
+        """Blocks that get the hook: every block but the last by default (the model needs one clean block to recover);
+        an explicit list is taken as given, minus the last block, and must stay in range."""
+        wanted = range(n_blocks - 1) if layer_indices is None else list(layer_indices)
+        for idx in wanted:
+            if idx >= n_blocks:
+                raise ValueError(f"Layer index {idx} out of range")
+        return [idx for idx in wanted if idx != n_blocks - 1]
+
+    def attach(self, model, layer_indices: Optional[Iterable[int]] = None) -> "DeepSpecAugment":
+        blocks = model.encoder.blocks
+        for idx in self.hooked_blocks(len(blocks), layer_indices):
+            self.handles.append(blocks[idx].attn_ln.register_forward_hook(self.on_attn_ln))
+        self.handles.append(model.encoder.register_forward_pre_hook(self.on_encoder_forward))
+        return self
+
+    def detach(self) -> None:
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+
 def register_deep_spec_augment_hooks(model, time_mask_param: int, freq_mask_param: int, p: float = 1.0,
                                      layer_indices: Optional[Iterable[int]] = None) -> None:
-    """Same arguments, gate and layer selection as the reference function of this name."""
-    p = float(p)
-    if not 0.0 <= p <= 1.0:
-        raise ValueError(f"deep_spec_augment p must be between 0 and 1, got {p}")
-    state = {"apply": False}
-
-    def _should_apply() -> bool:
-        if p >= 1.0:
-            return True
-        if p <= 0.0:
-            return False
-        return torch.rand(1).item() < p
-
-    def _encoder_pre_hook(module, input):
-        # decided once per encoder forward so that checkpoint recomputation sees the same on/off state
-        state["apply"] = _should_apply()
-
-    def _norm_hook(module, input, output):
-        if module.training and state["apply"]:
-            _, seq, dim = output.shape
-            t, f = draw_deep_spans(seq, dim, time_mask_param, freq_mask_param)
-            return mask_activations(output, t, f)
-        return output
-
-    n_blocks = len(model.encoder.blocks)
-    if layer_indices is None:
-        layer_indices = range(n_blocks - 1)   # the last block is left alone so the model can recover
-    for idx in layer_indices:
-        if idx >= n_blocks:
-            raise ValueError(f"Layer index {idx} out of range")
-        if idx == n_blocks - 1:
-            continue
-        model.encoder.blocks[idx].attn_ln.register_forward_hook(_norm_hook)
-    model.encoder.register_forward_pre_hook(_encoder_pre_hook)
+    """Drop-in for the reference function of this name (model/model_utils.py:382-437): same arguments, same gate, same
+    layer selection, same error messages."""
+    DeepSpecAugment(time_mask_param, freq_mask_param, p).attach(model, layer_indices)

@@ -15,21 +15,32 @@ from typing import Optional
 import torch
 
 from .audio import N_FRAMES, N_SAMPLES, frontend_forward, resolve_device
-from .augment import apply_masks, draw_mask_params, draw_warp_params, time_warp
+from .augment import augment_epilogue, draw_mask_params, draw_warp_params
 
 
 class FrontEnd:
+    """``spec_augment_params`` is the reference's ``augmentation.spec_augment`` block passed verbatim
+    (``time_mask_param``, ``freq_mask_param``, ``time_warp_w``, ``p``).  Like the reference
+    (data_loader.py:117, 284-287) a positive ``time_warp_w`` turns the time-warp ON whenever the gate passes; it then runs
+    with the masks (and the extremes mask) as ONE fused epilogue pass after the front-end kernel.  ``"time_warp": False``
+    in the params is the explicit opt-out (a single fused launch, masks only); a missing ``time_warp_w`` means no warp."""
+
     def __init__(self, n_mels: int = 80, device=None, spec_augment: bool = False,
                  spec_augment_params: Optional[dict] = None, seed: int = 0, n_samples: int = N_SAMPLES,
-                 n_frames: int = N_FRAMES):
+                 n_frames: int = N_FRAMES, warp_spline: str = "f64"):
         if n_mels not in (80, 128):
             raise ValueError(f"Unsupported n_mels: {n_mels}")
+        if warp_spline not in ("f32", "f64"):
+            raise ValueError("warp_spline must be 'f32' or 'f64'")
         self.n_mels = n_mels
         self.device = resolve_device(device)
         self.seed = int(seed)
         self.n_samples = int(n_samples)
         self.n_frames = int(n_frames)
+        self.warp_spline = warp_spline
         self.spec_augment = bool(spec_augment)
+        self.spec_augment_p = 0.0
+        self.time_mask_param = self.freq_mask_param = self.time_warp_w = 0
         if spec_augment:
             params = spec_augment_params or {}
             self.spec_augment_p = float(params.get("p", 1.0))
@@ -37,22 +48,19 @@ class FrontEnd:
                 raise ValueError(f"spec_augment p must be between 0 and 1, got {self.spec_augment_p}")
             self.time_mask_param = int(params["time_mask_param"])
             self.freq_mask_param = int(params["freq_mask_param"])
-            # time_warp_w (data_loader.py:117): off unless asked for -- the warp sits between pad_or_trim and the masks and
-            # needs the finished (floored) features, so it runs as a second kernel and the masks as a third
-            self.time_warp_w = int(params.get("time_warp_w", 0)) if params.get("fuse_time_warp", False) else 0
-        else:
-            self.spec_augment_p = 0.0
-            self.time_mask_param = 0
-            self.freq_mask_param = 0
-            self.time_warp_w = 0
+            if params.get("time_warp", True):
+                self.time_warp_w = int(params.get("time_warp_w", 0))
 
     def __call__(self, pcm: torch.Tensor, lengths=None, n_valid_frames=None, clip_offset: int = 0,
                  mask_params: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                 augment: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 augment: Optional[torch.Tensor] = None, extremes: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``pcm`` ``[B, N<=480000]`` float32 / int16 (host or device) -> ``[B, n_mels, 3000]`` on the device.
 
         ``augment`` (optional int / bool ``[B]``): per-clip outcome of the reference's SpecAugment gate
-        (data_loader.py:294-301) when it was already decided upstream; clips with 0 get no warp and no masks."""
+        (data_loader.py:294-301) when it was already decided upstream (the loader's workers draw it from their own RNG):
+        clips with 0 get no warp and no masks, clips with 1 get them -- the device-side ``p`` gate is then NOT rolled again.
+        ``extremes`` (optional int32 ``[B, 2]``): rows masked from the bottom / top by ExtremesFrequencyMasking
+        (data_loader.py:289-290), applied whatever the gate says, like the reference."""
         if not torch.is_tensor(pcm):
             pcm = torch.as_tensor(pcm)
         if pcm.dim() != 2:
@@ -61,29 +69,35 @@ class FrontEnd:
             raise ValueError(f"clips longer than {self.n_samples} samples must be chunked upstream")
         pcm = pcm.to(self.device, non_blocking=True)
         B, N = pcm.shape
-        if mask_params is None and self.spec_augment and self.spec_augment_p > 0.0:
-            mask_params = draw_mask_params(self.seed, clip_offset, B, self.n_mels, self.n_frames,
-                                           self.time_mask_param, self.freq_mask_param, self.spec_augment_p,
-                                           self.device)
         gate = None
+        p_draw = self.spec_augment_p
         if augment is not None:
             gate = torch.as_tensor(augment).to(self.device, torch.int32, non_blocking=True).reshape(B, 1)
-            if mask_params is not None:
-                mask_params = (mask_params * gate).contiguous()   # [0, 0) spans mask nothing
-        if self.time_warp_w > 0 and self.spec_augment_p > 0.0:
-            # reference order (data_loader.py:285-287): warp -> time mask -> frequency mask
-            plain = frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
-                                     n_frames_out=self.n_frames, n_valid_frames=n_valid_frames)
-            warps = draw_warp_params(self.seed, clip_offset, B, self.n_frames, self.time_warp_w, self.spec_augment_p,
-                                     self.device)
-            if gate is not None:   # (T / 2, 0) is the identity warp
-                ident = torch.tensor([self.n_frames // 2, 0], dtype=torch.int32, device=self.device)
-                warps = torch.where(gate != 0, warps, ident).contiguous()
-            warped = time_warp(plain, warps, out=out)
-            return apply_masks(warped, mask_params, 0.0, out=warped) if mask_params is not None else warped
-        return frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
-                                n_frames_out=self.n_frames, n_valid_frames=n_valid_frames,
-                                mask_params=mask_params, mask_value=0.0, out=out)
+            p_draw = 1.0 if self.spec_augment else 0.0   # the gate was rolled upstream: do not roll it a second time
+        if mask_params is None and self.spec_augment and p_draw > 0.0:
+            mask_params = draw_mask_params(self.seed, clip_offset, B, self.n_mels, self.n_frames,
+                                           self.time_mask_param, self.freq_mask_param, p_draw, self.device)
+        if gate is not None and mask_params is not None:
+            mask_params = (torch.as_tensor(mask_params).to(self.device, torch.int32) * gate).contiguous()   # [0, 0) masks nothing
+        warps = None
+        if self.time_warp_w > 0 and p_draw > 0.0:
+            warps = draw_warp_params(self.seed, clip_offset, B, self.n_frames, self.time_warp_w, p_draw, self.device)
+            if gate is not None:   # warp_p = -1: the clip is left alone
+                warps = torch.where(gate != 0, warps, torch.tensor([-1, 0], dtype=torch.int32, device=self.device)).contiguous()
+        if warps is None and extremes is None:
+            return frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
+                                    n_frames_out=self.n_frames, n_valid_frames=n_valid_frames,
+                                    mask_params=mask_params, mask_value=0.0, out=out)
+        if warps is None:
+            # no warp: the masks ride in the front-end kernel, the extremes mask is an in-place pass over its output
+            x = frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
+                                 n_frames_out=self.n_frames, n_valid_frames=n_valid_frames,
+                                 mask_params=mask_params, mask_value=0.0, out=out)
+            return augment_epilogue(x, None, None, extremes, 0.0, out=x)
+        # reference order (data_loader.py:285-290): warp -> time mask -> frequency mask -> extremes mask, one epilogue pass
+        plain = frontend_forward(pcm, self.n_mels, padding=self.n_samples - N, lengths=lengths,
+                                 n_frames_out=self.n_frames, n_valid_frames=n_valid_frames)
+        return augment_epilogue(plain, warps, mask_params, extremes, 0.0, out=out, spline=self.warp_spline)
 
 
 class HostPipeline:

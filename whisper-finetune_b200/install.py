@@ -10,6 +10,21 @@ from types import ModuleType
 from typing import Optional
 
 
+class _TransformsNamespace:
+    """What ``data_loader.T`` is rebound to by ``install(patch_masks=True)``: ``torchaudio.transforms`` with the two mask
+    classes swapped.  The real module is NOT touched -- ``model/model_utils.py`` builds its deep-SpecAugment hooks from the
+    same ``torchaudio.transforms`` (``T.TimeMasking`` on activations that require grad), and every other importer of
+    torchaudio keeps the stock classes."""
+
+    def __init__(self, transforms_module, time_masking, frequency_masking):
+        self._module = transforms_module
+        self.TimeMasking = time_masking
+        self.FrequencyMasking = frequency_masking
+
+    def __getattr__(self, name):
+        return getattr(self._module, name)
+
+
 def install(data_loader_module: Optional[ModuleType] = None, patch_whisper_audio: bool = True,
             patch_masks: bool = False) -> None:
     from . import audio, augment
@@ -22,9 +37,8 @@ def install(data_loader_module: Optional[ModuleType] = None, patch_whisper_audio
     if dl is not None:
         dl.log_mel_spectrogram = audio.log_mel_spectrogram
         dl.pad_or_trim = audio.pad_or_trim
-        if patch_masks and hasattr(dl, "T"):
-            dl.T.TimeMasking = augment.TimeMasking
-            dl.T.FrequencyMasking = augment.FrequencyMasking
+        if patch_masks and hasattr(dl, "T") and not isinstance(dl.T, _TransformsNamespace):
+            dl.T = _TransformsNamespace(dl.T, augment.TimeMasking, augment.FrequencyMasking)
         if patch_masks:
             if hasattr(dl, "TimeWarpAugmenter"):
                 dl.TimeWarpAugmenter = augment.TimeWarpAugmenter

@@ -26,7 +26,6 @@ import torch
 from torch.nn.utils.rnn import pad_sequence
 
 from .audio import N_FRAMES, N_SAMPLES
-from .augment import apply_masks
 from .frontend import FrontEnd
 
 TRAILER = 8
@@ -40,8 +39,10 @@ def encode_pcm_record(audio, n_valid_frames: Optional[int] = None, augment: bool
     if pcm_dtype not in (torch.float32, torch.int16):
         raise TypeError("pcm_dtype must be torch.float32 or torch.int16")
     a = np.asarray(audio.cpu() if torch.is_tensor(audio) else audio).reshape(-1)
-    if a.shape[0] > N_SAMPLES:
-        raise ValueError(f"clips longer than {N_SAMPLES} samples must be chunked upstream")
+    # an augmentation (time stretch) can leave a few samples more than 30 s: the reference trims the SPECTROGRAM to 3000
+    # frames (data_loader.py:281-282), here the audio is cut at 480000 samples -- same frames except the last one, whose
+    # window would have seen 40 samples beyond the cut
+    a = a[:N_SAMPLES]
     nz = np.flatnonzero(a)
     length = int(nz[-1]) + 1 if nz.size else 0          # trailing zeros are padding: the kernel skips those tiles
     nv = -1 if n_valid_frames is None else min(int(n_valid_frames), N_FRAMES)
@@ -115,12 +116,25 @@ def pcm_collate_fn(data):
 
 
 class DeviceFrontEndLoader:
-    """Iterate ``loader`` (built with ``pcm_collate_fn``) and yield ``(x, y_in, y_out)`` with ``x`` on the GPU."""
+    """Iterate ``loader`` (built with ``pcm_collate_fn``) and yield ``(x, y_in, y_out)`` with ``x`` on the GPU.
 
-    def __init__(self, loader: Iterable, front_end: FrontEnd, clip_offset: int = 0):
+    The mask / warp draws of a clip are keyed by a GLOBAL clip index so that ranks do not repeat each other: batch ``k`` of
+    rank ``r`` owns indices ``clip_offset + (k * world_size + r) * batch .. + batch`` (``rank`` / ``world_size`` default to
+    the initialised ``torch.distributed`` group, else 0 / 1)."""
+
+    def __init__(self, loader: Iterable, front_end: FrontEnd, clip_offset: int = 0, rank: Optional[int] = None,
+                 world_size: Optional[int] = None):
+        import torch.distributed as dist
+
         self.loader = loader
         self.fe = front_end
         self.clip_offset = int(clip_offset)
+        ddp = dist.is_available() and dist.is_initialized()
+        self.rank = int(rank) if rank is not None else (dist.get_rank() if ddp else 0)
+        self.world_size = int(world_size) if world_size is not None else (dist.get_world_size() if ddp else 1)
+        if not 0 <= self.rank < self.world_size:
+            raise ValueError(f"Invalid rank {self.rank}, rank should be in the interval [0, {self.world_size - 1}]")
+        self._batches = 0
         self._copy_stream = torch.cuda.Stream(device=front_end.device)
 
     def __len__(self):
@@ -141,16 +155,12 @@ class DeviceFrontEndLoader:
         cur.wait_event(ev)
         for t in (pcm, lengths, n_valid, augment, extremes):
             t.record_stream(cur)
-        x = self.fe(pcm, lengths=lengths, n_valid_frames=n_valid, clip_offset=self.clip_offset, augment=augment)
-        self.clip_offset += pcm.shape[0]
-        if bool(batch.extremes.any()):   # host copy: no device sync
-            n_mels = self.fe.n_mels
-            zeros = torch.zeros_like(extremes[:, :1])
-            low = torch.cat([zeros, zeros, zeros, extremes[:, :1]], dim=1).contiguous()
-            high = torch.cat([zeros, zeros, n_mels - extremes[:, 1:2], zeros + n_mels], dim=1).contiguous()
-            apply_masks(x, low, 0.0, out=x)
-            apply_masks(x, high, 0.0, out=x)
-        return x
+        B = pcm.shape[0]
+        offset = self.clip_offset + (self._batches * self.world_size + self.rank) * B
+        self._batches += 1
+        has_extremes = bool(batch.extremes.any())   # host copy: no device sync
+        return self.fe(pcm, lengths=lengths, n_valid_frames=n_valid, clip_offset=offset, augment=augment,
+                       extremes=extremes if has_extremes else None)
 
     def __iter__(self):
         for batch, y_in, y_out in self.loader:
