@@ -15,6 +15,9 @@ What gets pinned, and by what:
 * ``logmel_hf.npz``        -- log-mel of short seeded clips from the independent ``transformers`` Whisper feature extractor
                               (feature_extraction_whisper.py ``_np_extract_fbank_features``), the closest published
                               implementation available offline; cross-checks the oracle's STFT / mel / log recipe.
+* ``logmel_hf_torch.npz``  -- full 30-s clips (all six signal kinds, 80 and 128 mel) through the float32 torch.stft path of the
+                              same extractor (``_torch_extract_fbank_features``): agrees with the oracle to ONE float32 ulp
+                              (max-abs <= 2e-7), three orders tighter than the numpy variant above.
 * ``timewarp.npz``         -- outputs of the REFERENCE'S OWN ``TimeWarpAugmenter`` and ``ExtremesFrequencyMasking``
                               (data/utils.py:41-190) on oracle log-mels under fixed torch seeds, with the replayed
                               (warp_p, warp_d) / (low, high) parameters; sub-sampled rows to stay small.
@@ -135,6 +138,31 @@ def golden_logmel_hf():
     np.savez_compressed(os.path.join(HERE, "logmel_hf.npz"), n=len(cases), **out)
 
 
+def golden_logmel_hf_torch():
+    """Full 30-s clips through ``WhisperFeatureExtractor._torch_extract_fbank_features`` -- the float32 ``torch.stft`` path
+    of the independent ``transformers`` implementation, which agrees with the oracle to one float32 ulp.
+    Stored: every 24th frame, the first and last 32 frames, and float64 per-frame column sums (so EVERY frame is pinned)."""
+    from transformers import WhisperFeatureExtractor
+
+    out, k = {}, 0
+    for n_mels in (80, 128):
+        fe = WhisperFeatureExtractor(feature_size=n_mels)
+        for kind in ("white", "hdr", "int16", "zeros", "impulse", "chirp"):
+            x = S.make(kind)
+            if x.dtype == torch.int16:
+                x = x.float() / 32768.0
+            feats = np.asarray(fe._torch_extract_fbank_features(x.numpy()[None, :], "cpu"))[0].astype(np.float32)
+            assert feats.shape == (n_mels, 3000)
+            out[f"sub{k}"] = feats[:, ::24].copy()
+            out[f"head{k}"] = feats[:, :32].copy()
+            out[f"tail{k}"] = feats[:, -32:].copy()
+            out[f"colsum{k}"] = feats.astype(np.float64).sum(axis=0)
+            out[f"meta{k}"] = np.array([n_mels], dtype=np.int64)
+            out[f"kind{k}"] = np.array(kind)
+            k += 1
+    np.savez_compressed(os.path.join(HERE, "logmel_hf_torch.npz"), n=k, **out)
+
+
 def golden_timewarp():
     from whisper_finetune.data.utils import ExtremesFrequencyMasking, TimeWarpAugmenter
 
@@ -173,6 +201,7 @@ if __name__ == "__main__":
     golden_pad_or_trim()
     golden_calculate_mel()
     golden_logmel_hf()
+    golden_logmel_hf_torch()
     golden_timewarp()
     golden_mel_filters()
     for f in sorted(os.listdir(HERE)):

@@ -483,6 +483,63 @@ def test_front_end_with_time_warp_follows_reference_order(wft, cuda):
         assert torch.equal(got[b] == 0, ref == 0)
 
 
+def test_torch_custom_ops_pass_opcheck(wft, cuda):
+    """torch.library.opcheck: schema, fake kernel, autograd registration and AOT dispatch of every torch.ops.wft op."""
+    from torch.library import opcheck
+
+    g = torch.Generator().manual_seed(1)
+    pcm = (0.1 * torch.randn(3, 48000, generator=g)).to(cuda)
+    lengths = torch.tensor([48000, 20000, 333], dtype=torch.int32, device=cuda)
+    nv = torch.tensor([-1, 100, 3], dtype=torch.int32, device=cuda)
+    masks = torch.tensor([[10, 60, 3, 9], [0, 0, 0, 0], [290, 300, 70, 80]], dtype=torch.int32, device=cuda)
+    opcheck(torch.ops.wft.frontend_forward, (pcm, 80, 0, lengths, 300, nv, masks, 0.0))
+    opcheck(torch.ops.wft.frontend_forward, ((pcm * 32767).to(torch.int16), 128, 160, None, 0, None, None, 0.0))
+    opcheck(torch.ops.wft.frontend_forward_out, (pcm, 80, 0, None, 300, None, masks, 0.0, torch.empty(3, 80, 300, device=cuda)))
+    opcheck(torch.ops.wft.pad_or_trim, (torch.randn(2, 70, 5, device=cuda), 300))
+    opcheck(torch.ops.wft.pad_or_trim, (torch.randn(2, 70, 5, device=cuda), 30))
+    mel = torch.randn(3, 80, 300, device=cuda)
+    warps = torch.tensor([[100, 7], [-1, 0], [200, -9]], dtype=torch.int32, device=cuda)
+    ext = torch.tensor([[2, 3], [0, 0], [5, 0]], dtype=torch.int32, device=cuda)
+    opcheck(torch.ops.wft.augment, (mel, warps, masks, ext, 0.0, False))
+    opcheck(torch.ops.wft.augment, (mel, warps, None, None, 0.0, True))
+    opcheck(torch.ops.wft.augment_out, (mel, warps, masks, ext, 0.0, False, torch.empty_like(mel)))
+    opcheck(torch.ops.wft.augment_, (mel.clone(), masks, ext, 0.0))
+    opcheck(torch.ops.wft.specaug_apply, (mel, masks, 0.0))
+    opcheck(torch.ops.wft.specaug_apply_, (mel.clone(), masks, 0.0))
+    opcheck(torch.ops.wft.specaug_draw, (mel, 42, 7, 5, 80, 300, 100, 27, 0.5))
+    opcheck(torch.ops.wft.time_warp_draw, (mel, 42, 7, 5, 300, 20, 0.5))
+    for dtype in (torch.float32, torch.bfloat16):
+        act = torch.randn(2, 50, 64, device=cuda, dtype=dtype, requires_grad=True)
+        opcheck(torch.ops.wft.mask_bsd, (act, 3, 11, 8, 20))
+    # the ops are what the public functions run on
+    assert torch.equal(wft.frontend_forward(pcm, 80, lengths=lengths, n_frames_out=300, n_valid_frames=nv, mask_params=masks),
+                       torch.ops.wft.frontend_forward(pcm, 80, 0, lengths, 300, nv, masks, 0.0))
+
+
+def test_logmel_against_transformers_torch_extractor_full_clips(wft, cuda):
+    """CUDA against the float32 torch.stft path of the transformers extractor (tests/golden/logmel_hf_torch.npz), which the
+    oracle matches to one ulp: full 30-s clips, every signal kind, 80 / 128 mel."""
+    z = _gold("logmel_hf_torch.npz")
+    for k in range(int(z["n"])):
+        n_mels = int(z[f"meta{k}"][0])
+        got = wft.log_mel_spectrogram(S.make(str(z[f"kind{k}"])).to(cuda), n_mels=n_mels).cpu()
+        for name, view in (("sub", got[:, ::24]), ("head", got[:, :32]), ("tail", got[:, -32:])):
+            ma, rl = S.metrics(view, torch.from_numpy(z[f"{name}{k}"]))
+            assert ma <= S.MAX_ABS and rl <= S.REL_L2, (k, name, ma, rl)
+        assert np.abs(got.double().sum(dim=0).numpy() - z[f"colsum{k}"]).max() <= n_mels * 1e-4
+
+
+def test_pad_or_trim_keeps_half_precision_dtypes(wft, cuda):
+    from oracle.pad_or_trim import pad_or_trim as ref_pad
+
+    for dtype in (torch.float16, torch.bfloat16):
+        x = (torch.randn(8, 70) - 0.3).to(dtype)
+        got = wft.pad_or_trim(x.to(cuda), 300)
+        assert got.dtype == dtype and torch.equal(got.cpu(), ref_pad(x, 300))
+    with pytest.raises(TypeError):
+        wft.pad_or_trim(torch.zeros(4, 7, dtype=torch.float64, device=cuda), 30)
+
+
 def test_augment_epilogue_is_warp_then_masks_then_extremes(wft, cuda):
     """One pass == the reference's sequence time_warping -> time_masking -> freq_masking -> extreme_freq_masking
     (data_loader.py:284-290), and a front end built from the reference's config block runs exactly that."""
@@ -711,8 +768,17 @@ def test_device_front_end_loader_matches_oracle(wft, cuda, pcm_dtype):
     out = list(dl)
     assert len(out) == 1 and out[0][1] is y_in and out[0][2] is y_out
     x = out[0][0]
-    assert x.is_cuda and tuple(x.shape) == (B, n_mels, 3000) and dl.clip_offset == 40 + B
+    assert x.is_cuda and tuple(x.shape) == (B, n_mels, 3000) and dl._batches == 1
     masks = OS.draw_mask_params(9, 40, B, n_mels, 3000, 100, 27, 1.0)
+    # ranks of a DDP job draw from disjoint global clip indices: batch k of rank r starts at offset + (k * world + r) * B
+    dl2 = wft.DeviceFrontEndLoader([(batch, y_in, y_out)] * 2, fe, clip_offset=40, rank=1, world_size=4)
+    xs = [o[0].cpu() for o in dl2]
+    for k, xk in enumerate(xs):
+        mk = OS.draw_mask_params(9, 40 + (k * 4 + 1) * B, B, n_mels, 3000, 100, 27, 1.0)
+        for b in range(B):
+            if batch.augment[b]:
+                t0, t1, f0, f1 = mk[b]
+                assert (xk[b][:, t0:t1] == 0).all() and (xk[b][f0:f1] == 0).all()
     x = x.cpu()
     for b in range(B):
         nv = None if want_nv[b] < 0 else want_nv[b]
@@ -731,8 +797,9 @@ def test_device_front_end_loader_matches_oracle(wft, cuda, pcm_dtype):
 def test_pcm_record_errors(wft, cuda):
     with pytest.raises(RuntimeError):
         wft.encode_pcm_record(np.ones(100, np.float32), n_valid_frames=0)       # empty spectrogram: torch.min raises upstream
-    with pytest.raises(ValueError):
-        wft.encode_pcm_record(np.ones(480001, np.float32))
+    # a clip a few samples over 30 s (time-stretch augmentation) is cut at 480000 samples, not rejected
+    long = wft.encode_pcm_record(np.full(480123, 0.5, np.float32))
+    assert long.shape == (480008,) and wft.decode_pcm_records([long]).lengths.tolist() == [480000]
     bad = wft.encode_pcm_record(np.ones(100, np.float32))
     bad[480000] = 1
     with pytest.raises(ValueError):

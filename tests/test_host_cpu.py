@@ -281,3 +281,28 @@ def test_install_loader_rewires_reference_dataset(tmp_path):
     res = subprocess.run([sys.executable, str(script), ROOT, "/root/reference"], capture_output=True, text=True, timeout=600,
                          cwd=str(tmp_path))
     assert res.returncode == 0 and "LOADER-OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_torch_custom_ops_are_registered_with_fake_kernels(wft):
+    """north_star: "thin torch custom ops over a C-ABI shim" -- every op exists in torch.ops.wft, carries a schema, and its
+    fake kernel yields the right shape / dtype / device without a GPU (what torch.compile and make_fx trace through)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    names = {"frontend_forward", "frontend_forward_out", "pad_or_trim", "specaug_apply", "specaug_apply_", "augment",
+             "augment_out", "augment_", "specaug_draw", "time_warp_draw", "mask_bsd"}
+    assert names <= {n for n in dir(torch.ops.wft) if not n.startswith("_")}
+    assert "!) out" in str(torch.ops.wft.frontend_forward_out.default._schema), "out is declared as mutated"
+    with FakeTensorMode():
+        pcm = torch.empty(4, 480000, device="cuda")
+        y = torch.ops.wft.frontend_forward(pcm, 128, 0, None, 3000, None, None, 0.0)
+        assert tuple(y.shape) == (4, 128, 3000) and y.dtype == torch.float32 and y.device.type == "cuda"
+        y = torch.ops.wft.frontend_forward(torch.empty(2, 16000, device="cuda", dtype=torch.int16), 80, 160, None, 0, None, None, 0.0)
+        assert tuple(y.shape) == (2, 80, 101)
+        assert tuple(torch.ops.wft.pad_or_trim(torch.empty(3, 70, 5, device="cuda"), 3000).shape) == (3, 3000, 5)
+        mel = torch.empty(4, 128, 3000, device="cuda")
+        assert tuple(torch.ops.wft.augment(mel, None, None, None, 0.0, False).shape) == (4, 128, 3000)
+        assert tuple(torch.ops.wft.specaug_draw(mel, 1, 2, 7, 128, 3000, 100, 27, 1.0).shape) == (7, 4)
+        assert tuple(torch.ops.wft.time_warp_draw(mel, 1, 2, 7, 3000, 80, 1.0).shape) == (7, 2)
+        act = torch.empty(2, 1500, 1280, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        z = torch.ops.wft.mask_bsd(act, 1, 2, 3, 4)
+        assert z.dtype == torch.bfloat16 and z.requires_grad, "the autograd formula is registered"

@@ -82,6 +82,22 @@ def test_logmel_against_transformers_goldens():
         assert np.abs(got - want).max() <= 2e-4, (k, np.abs(got - want).max())
 
 
+def test_logmel_against_transformers_torch_extractor_full_clips():
+    """The tight independent anchor: full 30-s clips, all signal kinds, 80 / 128 mel, against the float32
+    torch.stft path of the ``transformers`` Whisper feature extractor -- one float32 ulp."""
+    z = _npz("logmel_hf_torch.npz")
+    assert int(z["n"]) == 12
+    for k in range(int(z["n"])):
+        n_mels = int(z[f"meta{k}"][0])
+        got = O.log_mel_spectrogram(S.make(str(z[f"kind{k}"])), n_mels).numpy()
+        assert got.shape == (n_mels, 3000)
+        for name, view in (("sub", got[:, ::24]), ("head", got[:, :32]), ("tail", got[:, -32:])):
+            d = np.abs(view - z[f"{name}{k}"]).max()
+            assert d <= 2e-7, (k, str(z[f"kind{k}"]), name, d)
+        # every frame: float64 column sums agree to n_mels x 2e-7
+        assert np.abs(got.astype(np.float64).sum(axis=0) - z[f"colsum{k}"]).max() <= n_mels * 2e-7
+
+
 def test_logmel_known_answers():
     z = O.log_mel_spectrogram(torch.zeros(480000), 80)
     assert z.shape == (80, 3000) and torch.all(z == -1.5)

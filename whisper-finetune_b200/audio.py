@@ -10,13 +10,13 @@ Same names, argument meaning and error behaviour as the callables the reference 
 Both are thin wrappers over the C ABI (``include/wft.h``): tensors provide device memory and the stream,
 nothing else.  CUDA only -- there is no CPU path.
 """
-import ctypes
 from typing import Optional, Union
 
 import numpy as np
 import torch
 
 from . import _lib
+from . import ops  # noqa: F401  (registers torch.ops.wft.*)
 
 SAMPLE_RATE = 16000
 N_FFT = 400
@@ -63,8 +63,9 @@ def frontend_forward(pcm: torch.Tensor, n_mels: int, padding: int = 0, lengths: 
                      n_frames_out: int = 0, n_valid_frames: Optional[torch.Tensor] = None,
                      mask_params: Optional[torch.Tensor] = None, mask_value: float = 0.0,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """One launch of ``wft_frontend_forward`` on a CUDA ``[B, N]`` float32 / int16 batch -> ``[B, n_mels, T]``."""
-    lib = _lib.load()
+    """One launch of ``wft_frontend_forward`` (through ``torch.ops.wft.frontend_forward``) on a CUDA ``[B, N]`` float32 /
+    int16 batch -> ``[B, n_mels, T]``."""
+    _lib.load()   # fail loudly, before any tensor work, if the CUDA library is missing
     if n_mels not in (80, 128):
         raise ValueError(f"Unsupported n_mels: {n_mels}")
     if not pcm.is_cuda or pcm.dim() != 2 or pcm.stride(1) != 1:
@@ -89,35 +90,12 @@ def frontend_forward(pcm: torch.Tensor, n_mels: int, padding: int = 0, lengths: 
     lengths = _i32(lengths, "lengths", (B,))
     n_valid_frames = _i32(n_valid_frames, "n_valid_frames", (B,))
     mask_params = _i32(mask_params, "mask_params", (B, 4))
-    n_frames = (N + padding) // HOP_LENGTH
-    T = n_frames_out if n_frames_out and n_frames_out > 0 else n_frames
-    with torch.cuda.device(dev):
-        need = ctypes.c_size_t(0)
-        _lib.check(lib.wft_frontend_workspace_bytes(B, N + padding, T, ctypes.byref(need)))
-        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
-        if out is None:
-            out = torch.empty((B, n_mels, T), dtype=torch.float32, device=dev)
-        elif (not out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != (B, n_mels, T)
-              or not out.is_contiguous()):
-            raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {(B, n_mels, T)}")
-        args = _lib.FrontendArgs(
-            pcm=pcm.data_ptr(),
-            pcm_dtype=_lib.WFT_PCM_F32 if pcm.dtype == torch.float32 else _lib.WFT_PCM_I16,
-            batch=B,
-            clip_stride=pcm.stride(0) if B > 1 else max(pcm.stride(0), N),
-            n_samples=N,
-            padding=padding,
-            lengths=None if lengths is None else lengths.data_ptr(),
-            n_mels=n_mels,
-            n_frames_out=T,
-            n_valid_frames=None if n_valid_frames is None else n_valid_frames.data_ptr(),
-            mask_params=None if mask_params is None else mask_params.data_ptr(),
-            mask_value=mask_value,
-            out=out.data_ptr(),
-            workspace=ws.data_ptr(),
-            workspace_bytes=need.value,
-        )
-        _lib.check(lib.wft_frontend_forward(ctypes.byref(args), _stream_ptr(dev)))
+    T = n_frames_out if n_frames_out and n_frames_out > 0 else (N + padding) // HOP_LENGTH
+    if out is None:
+        return torch.ops.wft.frontend_forward(pcm, n_mels, padding, lengths, T, n_valid_frames, mask_params, float(mask_value))
+    if not out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != (B, n_mels, T) or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {(B, n_mels, T)}")
+    torch.ops.wft.frontend_forward_out(pcm, n_mels, padding, lengths, T, n_valid_frames, mask_params, float(mask_value), out)
     return out
 
 
@@ -155,19 +133,12 @@ def log_mel_spectrogram(
 
 
 def _pad_or_trim_cuda(x: torch.Tensor, length: int, axis: int) -> torch.Tensor:
-    lib = _lib.load()
     x = x.contiguous()
     shape = list(x.shape)
     outer = int(np.prod(shape[:axis], dtype=np.int64)) if axis > 0 else 1
     inner = int(np.prod(shape[axis + 1:], dtype=np.int64)) if axis + 1 < len(shape) else 1
-    len_in = shape[axis]
     shape[axis] = length
-    out = torch.empty(shape, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        scratch = torch.empty(16, dtype=torch.uint8, device=x.device)
-        _lib.check(lib.wft_pad_or_trim_f32(x.data_ptr(), outer, len_in, inner, length, out.data_ptr(),
-                                           scratch.data_ptr(), _stream_ptr(x.device)))
-    return out
+    return torch.ops.wft.pad_or_trim(x.reshape(outer, x.shape[axis], inner), length).reshape(shape)
 
 
 def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):
@@ -176,7 +147,8 @@ def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):
     Mirror of the reference's ``pad_or_trim`` (data/utils.py:380-404; note: min-value pad, not whisper's zero
     pad): tensor in -> tensor out on the same device, ndarray in -> ndarray out, and the input object itself is
     returned when it already has the requested length.  The minimum is reduced on the GPU (no ``.item()`` sync
-    for CUDA tensors).  float32 only.
+    for CUDA tensors).  The kernel works in float32: float16 / bfloat16 inputs make the round trip through float32
+    exactly (min and copies are exact) and come back in their own dtype; other dtypes raise ``TypeError``.
     """
     ndim = array.ndim
     ax = axis + ndim if axis < 0 else axis
@@ -192,10 +164,10 @@ def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):
             raise RuntimeError("pad_or_trim: min(): cannot take the minimum of an empty tensor")
         raise ValueError("zero-size array to reduction operation minimum which has no identity")
     src = array if is_tensor else torch.from_numpy(np.ascontiguousarray(array))
-    if src.dtype != torch.float32:
-        raise TypeError(f"pad_or_trim supports float32 only, got {src.dtype}")
+    if src.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise TypeError(f"pad_or_trim supports float32 / float16 / bfloat16, got {src.dtype}")
     dev = resolve_device(None, src)
-    res = _pad_or_trim_cuda(src.to(dev, non_blocking=True), length, ax)
+    res = _pad_or_trim_cuda(src.to(dev, torch.float32, non_blocking=True), length, ax).to(src.dtype)
     if is_tensor:
         return res if array.is_cuda else res.to(array.device)
     return res.cpu().numpy()

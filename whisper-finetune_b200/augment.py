@@ -10,13 +10,13 @@ these classes mask the same cells.  The fill itself is ``wft_specaug_apply_f32``
 For batches the intervals are drawn on the device by ``draw_mask_params`` (Philox4x32-10 keyed by
 ``(seed, global clip index)``), which makes the masks independent of the number of GPUs.
 """
-import ctypes
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
-from .audio import _stream_ptr, resolve_device
+from . import ops  # noqa: F401  (registers torch.ops.wft.*)
+from .audio import resolve_device
 
 
 def _interval_from_global_rng(mask_param: int, size: int) -> Tuple[int, int]:
@@ -41,7 +41,7 @@ def _checked_out(out: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
 def apply_masks(mel: torch.Tensor, mask_params: torch.Tensor, mask_value: float = 0.0,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``mel`` CUDA float32 ``[B, R, T]`` (or ``[R, T]``), ``mask_params`` int32 ``[B, 4]`` = (t0, t1, f0, f1)."""
-    lib = _lib.load()
+    _lib.load()
     if not mel.is_cuda or mel.dtype != torch.float32:
         raise ValueError("mel must be a CUDA float32 tensor")
     squeeze = mel.dim() == 2
@@ -49,14 +49,18 @@ def apply_masks(mel: torch.Tensor, mask_params: torch.Tensor, mask_value: float 
     if x.dim() != 3:
         raise ValueError("mel must be [R, T] or [B, R, T]")
     x = x.contiguous()
-    B, R, T = x.shape
+    B = x.shape[0]
     mp = torch.as_tensor(mask_params, dtype=torch.int32).to(x.device).contiguous()
     if tuple(mp.shape) != (B, 4):
         raise ValueError(f"mask_params must have shape {(B, 4)}")
-    res = torch.empty_like(x) if out is None else _checked_out(out, x)
-    with torch.cuda.device(x.device):
-        _lib.check(lib.wft_specaug_apply_f32(x.data_ptr(), res.data_ptr(), B, R, T, mp.data_ptr(),
-                                             float(mask_value), _stream_ptr(x.device)))
+    if out is None:
+        res = torch.ops.wft.specaug_apply(x, mp, float(mask_value))
+    else:
+        res = _checked_out(out, x)
+        if res.data_ptr() == x.data_ptr():
+            torch.ops.wft.specaug_apply_(res, mp, float(mask_value))
+        else:
+            torch.ops.wft.augment_out(x, None, mp, None, float(mask_value), False, res)
     return res[0] if squeeze else res
 
 
@@ -65,14 +69,13 @@ def draw_mask_params(seed: int, clip_offset: int, batch: int, n_mels: int, n_fra
     """Device-side counter-based draw -> int32 ``[batch, 4]`` (``wft_specaug_draw``)."""
     if not 0.0 <= p <= 1.0:
         raise ValueError(f"spec_augment p must be between 0 and 1, got {p}")
-    lib = _lib.load()
+    _lib.load()
+    if batch < 1:
+        raise ValueError("batch must be >= 1")
     dev = resolve_device(device)
-    out = torch.empty((batch, 4), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.wft_specaug_draw(ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(clip_offset), batch,
-                                        n_mels, n_frames, time_mask_param, freq_mask_param, float(p),
-                                        out.data_ptr(), _stream_ptr(dev)))
-    return out
+    like = torch.empty(0, dtype=torch.int32, device=dev)
+    return torch.ops.wft.specaug_draw(like, int(seed), int(clip_offset), int(batch), int(n_mels), int(n_frames),
+                                      int(time_mask_param), int(freq_mask_param), float(p))
 
 
 class _AxisMask:
@@ -133,21 +136,18 @@ class FrequencyMasking(_AxisMask):
 
 def time_warp(mel: torch.Tensor, warp_params: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``mel`` CUDA float32 ``[B, R, T]`` (or ``[R, T]``), ``warp_params`` int32 ``[B, 2]`` = (warp_p, warp_d) ->
-    time-warped copy (``wft_time_warp_f32``: cubic Hermite source map, bilinear resampling, zeros outside)."""
-    lib = _lib.load()
+    time-warped copy (cubic Hermite source map, bilinear resampling, zeros outside; ``warp_p <= 0`` copies the clip)."""
     if not mel.is_cuda or mel.dtype != torch.float32:
         raise ValueError("mel must be a CUDA float32 tensor")
     squeeze = mel.dim() == 2
     x = (mel.unsqueeze(0) if squeeze else mel).contiguous()
     if x.dim() != 3:
         raise ValueError("You sure it's a Spectrogram?")
-    B, R, T = x.shape
-    wp = torch.as_tensor(warp_params, dtype=torch.int32).to(x.device).contiguous()
-    if tuple(wp.shape) != (B, 2):
-        raise ValueError(f"warp_params must have shape {(B, 2)}")
-    res = torch.empty_like(x) if out is None else _checked_out(out, x)
-    with torch.cuda.device(x.device):
-        _lib.check(lib.wft_time_warp_f32(x.data_ptr(), res.data_ptr(), B, R, T, wp.data_ptr(), _stream_ptr(x.device)))
+    if x.shape[1] < 2 or x.shape[2] < 3:
+        raise ValueError("time warp needs at least 2 rows and 3 frames")
+    if warp_params is None:
+        raise ValueError("warp_params is required")
+    res = augment_epilogue(x, warp_params, None, None, 0.0, out=None if out is None else _checked_out(out, x))
     return res[0] if squeeze else res
 
 
@@ -178,32 +178,29 @@ def augment_epilogue(mel: torch.Tensor, warp_params: Optional[torch.Tensor] = No
 
     wp, mp, ex = _i32(warp_params, 2, "warp_params"), _i32(mask_params, 4, "mask_params"), _i32(extremes, 2, "extremes")
     if out is None:
-        res = torch.empty_like(x)
-    else:
-        res = out
-        if not res.is_cuda or res.dtype != torch.float32 or tuple(res.shape) != (B, R, T) or not res.is_contiguous():
-            raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {(B, R, T)}")
-        if wp is not None and res.data_ptr() == x.data_ptr():
+        return torch.ops.wft.augment(x, wp, mp, ex, float(mask_value), spline == "f32")
+    res = _checked_out(out, x)
+    if res.data_ptr() == x.data_ptr():
+        if wp is not None:
             raise ValueError("time warp cannot run in place")
-    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-    with torch.cuda.device(x.device):
-        _lib.check(lib.wft_augment_f32(x.data_ptr(), res.data_ptr(), B, R, T, ptr(wp), ptr(mp), ptr(ex), float(mask_value),
-                                       1 if spline == "f32" else 0, _stream_ptr(x.device)))
+        torch.ops.wft.augment_(res, mp, ex, float(mask_value))
+    else:
+        torch.ops.wft.augment_out(x, wp, mp, ex, float(mask_value), spline == "f32", res)
     return res
 
 
 def draw_warp_params(seed: int, clip_offset: int, batch: int, n_frames: int, time_warp_w: int, p: float = 1.0,
                      device=None) -> torch.Tensor:
-    """Device-side counter-based draw of (warp_p, warp_d) -> int32 ``[batch, 2]`` (``wft_time_warp_draw``)."""
+    """Device-side counter-based draw of (warp_p, warp_d) -> int32 ``[batch, 2]`` (``wft_time_warp_draw``); (-1, 0) for a
+    clip the ``p`` gate rejects."""
     if not 0.0 <= p <= 1.0:
         raise ValueError(f"spec_augment p must be between 0 and 1, got {p}")
-    lib = _lib.load()
+    _lib.load()
+    if batch < 1:
+        raise ValueError("batch must be >= 1")
     dev = resolve_device(device)
-    out = torch.empty((batch, 2), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.wft_time_warp_draw(ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(clip_offset), batch,
-                                          n_frames, time_warp_w, float(p), out.data_ptr(), _stream_ptr(dev)))
-    return out
+    like = torch.empty(0, dtype=torch.int32, device=dev)
+    return torch.ops.wft.time_warp_draw(like, int(seed), int(clip_offset), int(batch), int(n_frames), int(time_warp_w), float(p))
 
 
 class TimeWarpAugmenter:

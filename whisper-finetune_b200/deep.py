@@ -16,45 +16,17 @@ from typing import Iterable, Optional, Tuple
 import torch
 
 from . import _lib
-from .audio import _stream_ptr
+from . import ops  # noqa: F401  (registers torch.ops.wft.*)
 from .augment import _interval_from_global_rng
-
-_ELEM_BYTES = {torch.float32: 4, torch.float16: 2, torch.bfloat16: 2}
-
-
-def _mask_bsd(x: torch.Tensor, t0: int, t1: int, f0: int, f1: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    lib = _lib.load()
-    if not x.is_cuda:
-        raise RuntimeError("whisper-finetune_b200 computes on CUDA only; the activations must be a CUDA tensor")
-    if x.dtype not in _ELEM_BYTES:
-        raise TypeError(f"activations must be float32, float16 or bfloat16, got {x.dtype}")
-    if x.dim() != 3:
-        raise ValueError(f"activations must be [batch, seq, dim], got shape {tuple(x.shape)}")
-    x = x.contiguous()
-    B, S, D = x.shape
-    res = torch.empty_like(x) if out is None else out
-    with torch.cuda.device(x.device):
-        _lib.check(lib.wft_mask_bsd(x.data_ptr(), res.data_ptr(), _ELEM_BYTES[x.dtype], B, S, D, int(t0), int(t1),
-                                    int(f0), int(f1), 0, _stream_ptr(x.device)))
-    return res
-
-
-class _MaskActivations(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, t0, t1, f0, f1):
-        ctx.spans = (t0, t1, f0, f1)
-        return _mask_bsd(x, t0, t1, f0, f1)
-
-    @staticmethod
-    def backward(ctx, grad):
-        # y = x * m with m in {0, 1}: the gradient is masked by the same spans
-        return _mask_bsd(grad, *ctx.spans), None, None, None, None
-
 
 def mask_activations(x: torch.Tensor, time_span: Tuple[int, int], feature_span: Tuple[int, int]) -> torch.Tensor:
     """``x[b, s, d] := 0`` for ``s`` in ``time_span`` or ``d`` in ``feature_span``; ``x`` is ``[batch, seq, dim]``
-    (CUDA, fp32 / fp16 / bf16).  Returns a new tensor; differentiable."""
-    return _MaskActivations.apply(x, int(time_span[0]), int(time_span[1]), int(feature_span[0]), int(feature_span[1]))
+    (CUDA, fp32 / fp16 / bf16).  Returns a new tensor; differentiable (``torch.ops.wft.mask_bsd`` registers its backward:
+    the same mask over the gradient)."""
+    _lib.load()
+    if not x.is_cuda:
+        raise RuntimeError("whisper-finetune_b200 computes on CUDA only; the activations must be a CUDA tensor")
+    return torch.ops.wft.mask_bsd(x, int(time_span[0]), int(time_span[1]), int(feature_span[0]), int(feature_span[1]))
 
 
 def draw_deep_spans(seq: int, dim: int, time_mask_param: int, freq_mask_param: int) -> Tuple[Tuple[int, int], Tuple[int, int]]:

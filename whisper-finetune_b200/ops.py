@@ -1,0 +1,287 @@
+"""``torch.ops.wft.*``: the C ABI (include/wft.h) as torch custom ops.
+
+``north_star`` asks for "thin torch custom ops over a C-ABI shim": every kernel entry point of ``libwft_b200.so`` is
+registered here with ``torch.library`` -- schema, CUDA implementation (a ctypes call on the tensor's data pointers and the
+current stream), a fake / meta implementation (so ``torch.compile``, ``make_fx`` and FakeTensor tracing see shapes without
+running anything) and, for the one op that sits on an autograd graph (``mask_bsd``, the deep-SpecAugment mask of
+``model/model_utils.py:382-437``), its backward formula.  The reference-facing Python functions in ``audio.py`` /
+``augment.py`` / ``deep.py`` validate their arguments and then call these ops; nothing else touches the library.
+
+    wft::frontend_forward      PCM [B, N] (+ lengths, n_valid_frames, mask_params)        -> features [B, n_mels, T]
+    wft::frontend_forward_out  same, written into a caller-owned buffer                   (mutates ``out``)
+    wft::pad_or_trim           [outer, len_in, inner] float32 -> [outer, length, inner], min-value pad (data/utils.py:380-404)
+    wft::specaug_apply         features, mask_params [B, 4]                               -> masked copy
+    wft::specaug_apply_        in place
+    wft::augment               time-warp -> masks -> extremes mask in one pass            -> new tensor
+    wft::augment_out           same into ``out`` (``out`` may alias the input when there is no warp)
+    wft::specaug_draw          (seed, clip_offset, ...)                                   -> int32 [B, 4]
+    wft::time_warp_draw        (seed, clip_offset, ...)                                   -> int32 [B, 2]
+    wft::mask_bsd              activations [B, S, D] fp32 / fp16 / bf16, spans            -> masked copy (differentiable)
+
+CUDA only: there is no CPU kernel behind any of them (the ops are registered for ``device_types="cuda"``).
+"""
+import ctypes
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+HOP_LENGTH = 160
+_ELEM_BYTES = {torch.float32: 4, torch.float16: 2, torch.bfloat16: 2}
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[Tensor], n_frames_out: int,
+                     n_valid_frames: Optional[Tensor], mask_params: Optional[Tensor], mask_value: float, out: Tensor) -> None:
+    lib = _lib.load()
+    B, N = pcm.shape
+    dev = pcm.device
+    with torch.cuda.device(dev):
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.wft_frontend_workspace_bytes(B, N + padding, out.shape[2], ctypes.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        args = _lib.FrontendArgs(
+            pcm=pcm.data_ptr(),
+            pcm_dtype=_lib.WFT_PCM_F32 if pcm.dtype == torch.float32 else _lib.WFT_PCM_I16,
+            batch=B,
+            clip_stride=pcm.stride(0) if B > 1 else max(pcm.stride(0), N),
+            n_samples=N,
+            padding=padding,
+            lengths=_ptr(lengths),
+            n_mels=n_mels,
+            n_frames_out=out.shape[2],
+            n_valid_frames=_ptr(n_valid_frames),
+            mask_params=_ptr(mask_params),
+            mask_value=mask_value,
+            out=out.data_ptr(),
+            workspace=ws.data_ptr(),
+            workspace_bytes=need.value,
+        )
+        _lib.check(lib.wft_frontend_forward(ctypes.byref(args), _stream(dev)))
+
+
+def _frames(pcm: Tensor, padding: int, n_frames_out: int) -> int:
+    return n_frames_out if n_frames_out > 0 else (pcm.shape[1] + padding) // HOP_LENGTH
+
+
+def _check_frontend_inputs(pcm, n_mels, lengths, n_valid_frames, mask_params):
+    if n_mels not in (80, 128):
+        raise ValueError(f"Unsupported n_mels: {n_mels}")
+    if pcm.dim() != 2 or pcm.stride(1) != 1 or pcm.dtype not in (torch.float32, torch.int16) or pcm.shape[0] < 1:
+        raise ValueError("pcm must be a non-empty float32 / int16 tensor of shape [B, N] with unit stride along N")
+    B = pcm.shape[0]
+    for t, name, shape in ((lengths, "lengths", (B,)), (n_valid_frames, "n_valid_frames", (B,)), (mask_params, "mask_params", (B, 4))):
+        if t is not None and (t.dtype != torch.int32 or tuple(t.shape) != shape or not t.is_contiguous() or t.device != pcm.device):
+            raise ValueError(f"{name} must be a contiguous int32 tensor of shape {shape} on {pcm.device}")
+
+
+@torch.library.custom_op("wft::frontend_forward", mutates_args=(), device_types="cuda")
+def frontend_forward(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[Tensor], n_frames_out: int,
+                     n_valid_frames: Optional[Tensor], mask_params: Optional[Tensor], mask_value: float) -> Tensor:
+    _check_frontend_inputs(pcm, n_mels, lengths, n_valid_frames, mask_params)
+    out = torch.empty((pcm.shape[0], n_mels, _frames(pcm, padding, n_frames_out)), dtype=torch.float32, device=pcm.device)
+    _launch_frontend(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, mask_params, mask_value, out)
+    return out
+
+
+@frontend_forward.register_fake
+def _(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, mask_params, mask_value):
+    return pcm.new_empty((pcm.shape[0], n_mels, _frames(pcm, padding, n_frames_out)), dtype=torch.float32)
+
+
+@torch.library.custom_op("wft::frontend_forward_out", mutates_args=("out",), device_types="cuda")
+def frontend_forward_out(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[Tensor], n_frames_out: int,
+                         n_valid_frames: Optional[Tensor], mask_params: Optional[Tensor], mask_value: float, out: Tensor) -> None:
+    _check_frontend_inputs(pcm, n_mels, lengths, n_valid_frames, mask_params)
+    want = (pcm.shape[0], n_mels, _frames(pcm, padding, n_frames_out))
+    if out.dtype != torch.float32 or tuple(out.shape) != want or not out.is_contiguous() or out.device != pcm.device:
+        raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {want}")
+    _launch_frontend(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, mask_params, mask_value, out)
+
+
+@frontend_forward_out.register_fake
+def _(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, mask_params, mask_value, out):
+    return None
+
+
+@torch.library.custom_op("wft::pad_or_trim", mutates_args=(), device_types="cuda")
+def pad_or_trim(x: Tensor, length: int) -> Tensor:
+    """``x`` is ``[outer, len_in, inner]`` float32 contiguous -> ``[outer, length, inner]`` (min-value pad or trim)."""
+    lib = _lib.load()
+    if x.dim() != 3 or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous float32 tensor of shape [outer, len_in, inner]")
+    outer, len_in, inner = x.shape
+    if length > len_in and x.numel() == 0:
+        raise RuntimeError("pad_or_trim: min(): cannot take the minimum of an empty tensor")
+    out = torch.empty((outer, length, inner), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        scratch = torch.empty(16, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.wft_pad_or_trim_f32(x.data_ptr(), outer, len_in, inner, length, out.data_ptr(), scratch.data_ptr(),
+                                           _stream(x.device)))
+    return out
+
+
+@pad_or_trim.register_fake
+def _(x, length):
+    return x.new_empty((x.shape[0], length, x.shape[2]))
+
+
+def _launch_augment(mel: Tensor, warp_params: Optional[Tensor], mask_params: Optional[Tensor], extremes: Optional[Tensor],
+                    mask_value: float, spline_f32: bool, out: Tensor) -> None:
+    lib = _lib.load()
+    if mel.dim() != 3 or mel.dtype != torch.float32 or not mel.is_contiguous():
+        raise ValueError("mel must be a contiguous CUDA float32 tensor of shape [B, R, T]")
+    B, R, T = mel.shape
+    for t, name, cols in ((warp_params, "warp_params", 2), (mask_params, "mask_params", 4), (extremes, "extremes", 2)):
+        if t is not None and (t.dtype != torch.int32 or tuple(t.shape) != (B, cols) or not t.is_contiguous() or t.device != mel.device):
+            raise ValueError(f"{name} must be a contiguous int32 tensor of shape {(B, cols)} on {mel.device}")
+    if out.dtype != torch.float32 or tuple(out.shape) != (B, R, T) or not out.is_contiguous() or out.device != mel.device:
+        raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {(B, R, T)}")
+    with torch.cuda.device(mel.device):
+        _lib.check(lib.wft_augment_f32(mel.data_ptr(), out.data_ptr(), B, R, T, _ptr(warp_params), _ptr(mask_params),
+                                       _ptr(extremes), float(mask_value), 1 if spline_f32 else 0, _stream(mel.device)))
+
+
+@torch.library.custom_op("wft::augment", mutates_args=(), device_types="cuda")
+def augment(mel: Tensor, warp_params: Optional[Tensor], mask_params: Optional[Tensor], extremes: Optional[Tensor],
+            mask_value: float, spline_f32: bool) -> Tensor:
+    out = torch.empty_like(mel)
+    _launch_augment(mel, warp_params, mask_params, extremes, mask_value, spline_f32, out)
+    return out
+
+
+@augment.register_fake
+def _(mel, warp_params, mask_params, extremes, mask_value, spline_f32):
+    return torch.empty_like(mel)
+
+
+@torch.library.custom_op("wft::augment_out", mutates_args=("out",), device_types="cuda")
+def augment_out(mel: Tensor, warp_params: Optional[Tensor], mask_params: Optional[Tensor], extremes: Optional[Tensor],
+                mask_value: float, spline_f32: bool, out: Tensor) -> None:
+    _launch_augment(mel, warp_params, mask_params, extremes, mask_value, spline_f32, out)
+
+
+@augment_out.register_fake
+def _(mel, warp_params, mask_params, extremes, mask_value, spline_f32, out):
+    return None
+
+
+@torch.library.custom_op("wft::augment_", mutates_args=("mel",), device_types="cuda")
+def augment_(mel: Tensor, mask_params: Optional[Tensor], extremes: Optional[Tensor], mask_value: float) -> None:
+    """In place (no warp): the masks only overwrite cells."""
+    _launch_augment(mel, None, mask_params, extremes, mask_value, False, mel)
+
+
+@augment_.register_fake
+def _(mel, mask_params, extremes, mask_value):
+    return None
+
+
+def _launch_specaug_apply(mel: Tensor, mask_params: Tensor, mask_value: float, out: Tensor) -> None:
+    lib = _lib.load()
+    if mel.dim() != 3 or mel.dtype != torch.float32 or not mel.is_contiguous():
+        raise ValueError("mel must be a contiguous CUDA float32 tensor of shape [B, R, T]")
+    B, R, T = mel.shape
+    if mask_params.dtype != torch.int32 or tuple(mask_params.shape) != (B, 4) or not mask_params.is_contiguous():
+        raise ValueError(f"mask_params must have shape {(B, 4)}")
+    with torch.cuda.device(mel.device):
+        _lib.check(lib.wft_specaug_apply_f32(mel.data_ptr(), out.data_ptr(), B, R, T, mask_params.data_ptr(), float(mask_value),
+                                             _stream(mel.device)))
+
+
+@torch.library.custom_op("wft::specaug_apply", mutates_args=(), device_types="cuda")
+def specaug_apply(mel: Tensor, mask_params: Tensor, mask_value: float) -> Tensor:
+    out = torch.empty_like(mel)
+    _launch_specaug_apply(mel, mask_params, mask_value, out)
+    return out
+
+
+@specaug_apply.register_fake
+def _(mel, mask_params, mask_value):
+    return torch.empty_like(mel)
+
+
+@torch.library.custom_op("wft::specaug_apply_", mutates_args=("mel",), device_types="cuda")
+def specaug_apply_(mel: Tensor, mask_params: Tensor, mask_value: float) -> None:
+    _launch_specaug_apply(mel, mask_params, mask_value, mel)
+
+
+@specaug_apply_.register_fake
+def _(mel, mask_params, mask_value):
+    return None
+
+
+@torch.library.custom_op("wft::specaug_draw", mutates_args=(), device_types="cuda")
+def specaug_draw(like: Tensor, seed: int, clip_offset: int, batch: int, n_mels: int, n_frames: int, time_mask_param: int,
+                 freq_mask_param: int, p: float) -> Tensor:
+    """``like`` only names the device (custom ops take their device from a tensor argument)."""
+    lib = _lib.load()
+    out = torch.empty((batch, 4), dtype=torch.int32, device=like.device)
+    with torch.cuda.device(like.device):
+        _lib.check(lib.wft_specaug_draw(ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(clip_offset & (2**64 - 1)), batch,
+                                        n_mels, n_frames, time_mask_param, freq_mask_param, float(p), out.data_ptr(),
+                                        _stream(like.device)))
+    return out
+
+
+@specaug_draw.register_fake
+def _(like, seed, clip_offset, batch, n_mels, n_frames, time_mask_param, freq_mask_param, p):
+    return like.new_empty((batch, 4), dtype=torch.int32)
+
+
+@torch.library.custom_op("wft::time_warp_draw", mutates_args=(), device_types="cuda")
+def time_warp_draw(like: Tensor, seed: int, clip_offset: int, batch: int, n_frames: int, time_warp_w: int, p: float) -> Tensor:
+    lib = _lib.load()
+    out = torch.empty((batch, 2), dtype=torch.int32, device=like.device)
+    with torch.cuda.device(like.device):
+        _lib.check(lib.wft_time_warp_draw(ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(clip_offset & (2**64 - 1)), batch,
+                                          n_frames, time_warp_w, float(p), out.data_ptr(), _stream(like.device)))
+    return out
+
+
+@time_warp_draw.register_fake
+def _(like, seed, clip_offset, batch, n_frames, time_warp_w, p):
+    return like.new_empty((batch, 2), dtype=torch.int32)
+
+
+@torch.library.custom_op("wft::mask_bsd", mutates_args=(), device_types="cuda")
+def mask_bsd(x: Tensor, t0: int, t1: int, f0: int, f1: int) -> Tensor:
+    """``x`` ``[batch, seq, dim]`` (fp32 / fp16 / bf16): ``out[b, s, d] = 0`` for ``s`` in ``[t0, t1)`` or ``d`` in ``[f0, f1)``."""
+    lib = _lib.load()
+    if x.dtype not in _ELEM_BYTES:
+        raise TypeError(f"activations must be float32, float16 or bfloat16, got {x.dtype}")
+    if x.dim() != 3:
+        raise ValueError(f"activations must be [batch, seq, dim], got shape {tuple(x.shape)}")
+    x = x.contiguous()
+    B, S, D = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.wft_mask_bsd(x.data_ptr(), out.data_ptr(), _ELEM_BYTES[x.dtype], B, S, D, int(t0), int(t1), int(f0),
+                                    int(f1), 0, _stream(x.device)))
+    return out
+
+
+@mask_bsd.register_fake
+def _(x, t0, t1, f0, f1):
+    return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+def _mask_bsd_setup(ctx, inputs, output):
+    _, ctx.t0, ctx.t1, ctx.f0, ctx.f1 = inputs
+
+
+def _mask_bsd_backward(ctx, grad):
+    # y = x * m with m in {0, 1}: the gradient is masked by the same spans
+    return torch.ops.wft.mask_bsd(grad, ctx.t0, ctx.t1, ctx.f0, ctx.f1), None, None, None, None
+
+
+mask_bsd.register_autograd(_mask_bsd_backward, setup_context=_mask_bsd_setup)
