@@ -35,6 +35,7 @@ N_SAMPLES = 480000
 N_FRAMES = 3000
 TIME_MASK = 100
 FREQ_MASK = 43
+TIME_WARP_W = 80
 SEED = 42
 N_STREAMS = 2   # batches in flight in the throughput loop (the roofline loop stays strictly one launch after another)
 BYTES_PER_CLIP = 4 * N_SAMPLES + 4 * N_MELS * N_FRAMES  # 3 456 000 (algorithmic bytes, f32 in, 128 mel)
@@ -63,7 +64,8 @@ def workload_config(n_gpus):
         "spec_augment": True, "sharding": "DistributedSampler-style batch shards, no data-path collective",
         "cache": "4 rotating input/output buffer sets (885 MB per GPU) > 126 MB L2",
         "streams": N_STREAMS,
-        "in_flight": "value: step i on stream i % 2 (two batches in flight); roofline: one launch after another on one stream",
+        "in_flight": "value: step i on stream i % 2 (two batches in flight, plain launches); roofline: one launch after another on "
+                     "one stream with programmatic dependent launch (the next grid is scheduled under the tail of the previous one)",
     }
 
 
@@ -351,9 +353,13 @@ def run_ours(args):
             step(i)
         join()
 
+    # programmatic dependent launch pays on ONE busy stream (the roofline loop below); with two batches in flight on two
+    # streams the early CTAs of a dependent launch take SM slots from the other stream's kernel (measured: -6 %), so off here
+    wft.set_programmatic_launch(False)
     with ClockSampler(local_rank) as clocks:
         block_ms, block_times = repeat_blocks(value_body)
         launches_total = int(lib.wft_launch_count(0))
+    wft.set_programmatic_launch(True)
     launches = launches_total // len(block_times)      # launches of ONE timed K-step block
     ms_max = block_ms
     value = world * BATCH * args.steps / (ms_max * 1e-3)
@@ -370,6 +376,40 @@ def run_ours(args):
 
     kernel_block_ms, kernel_times = repeat_blocks(kernel_body, min_gpu_seconds=0.3)
     kernel_ms = kernel_block_ms / args.steps
+
+    # the production configs also time-warp (configs/config_turbo_best.yaml:97, config_large_v3_best_muon_ddp4.yaml:120:
+    # time_warp_w = 80; applied at data_loader.py:285): front-end kernel -> ONE fused epilogue pass (warp + masks)
+    fe_warp = wft.FrontEnd(n_mels=N_MELS, device=dev, spec_augment=True, seed=SEED,
+                           spec_augment_params={"time_mask_param": TIME_MASK, "freq_mask_param": FREQ_MASK,
+                                                "time_warp_w": TIME_WARP_W, "p": 1.0})
+    warp_out = [torch.empty(BATCH, N_MELS, N_FRAMES, device=dev) for _ in range(n_sets)]
+
+    def warp_body(first_step):
+        fork()
+        for i in range(first_step, first_step + args.steps):
+            with torch.cuda.stream(streams[i % N_STREAMS]):
+                fe_warp(pcm_sets[i % n_sets], clip_offset=(i * world + rank) * BATCH, out=warp_out[i % n_sets])
+        join()
+
+    wft.set_programmatic_launch(False)
+    warp_body(0)
+    torch.cuda.synchronize()
+    lib.wft_launch_count(1)
+    warp_block_ms, warp_times = repeat_blocks(warp_body, min_gpu_seconds=0.3)
+    warp_launches = int(lib.wft_launch_count(0)) // len(warp_times)
+    wft.set_programmatic_launch(True)
+    value_warp = world * BATCH * args.steps / (warp_block_ms * 1e-3)
+    # the epilogue kernel alone, for its own roofline: one read + one write of the features
+    warps = wft.draw_warp_params(SEED, 0, BATCH, N_FRAMES, TIME_WARP_W, 1.0, dev)
+
+    def epilogue_body(first_step):
+        for i in range(first_step, first_step + args.steps):
+            wft.augment_epilogue(out_sets[i % n_sets], warps, masks, None, 0.0, out=warp_out[i % n_sets])
+
+    epilogue_body(0)
+    torch.cuda.synchronize()
+    epi_block_ms, _ = repeat_blocks(epilogue_body, min_gpu_seconds=0.2)
+    epi_ms = epi_block_ms / args.steps
 
     # end to end through the public API with host buffers (pinned): H2D + kernels + D2H every step
     def run_e2e(pcm_dtype, readback):
@@ -475,6 +515,14 @@ def run_ours(args):
                          "kernel": "wft::frontend_kernel<128,float>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": BATCH * BYTES_PER_CLIP},
         }
+        epi_bytes = 2 * 4 * N_MELS * N_FRAMES * BATCH
+        line["value_with_time_warp"] = {
+            "value": value_warp, "unit": UNIT, "ms_per_step": warp_block_ms / args.steps, "gpu_launches_per_step": warp_launches / args.steps,
+            "what": "mask + warp draws, fused front-end kernel, ONE fused epilogue pass (time-warp W=80 -> time mask -> frequency mask), "
+                    "device-resident PCM, same blocks / streams as `value`",
+            "epilogue_roofline": {"bound": "hbm", "kernel": "augment_kernel<false>", "kernel_ms": epi_ms,
+                                  "algorithmic_bytes_per_launch": epi_bytes, "achieved": epi_bytes / (epi_ms * 1e-3) / 1e9,
+                                  "peak": peak, "unit": "GB/s", "frac": epi_bytes / (epi_ms * 1e-3) / 1e9 / peak}}
         if multi is not None:
             line["multi_gpu"] = multi
             line["shard_union_equal"] = multi["shard_union_equal"]

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WFT_ABI_VERSION 4
+#define WFT_ABI_VERSION 6
 
 /* Front-end constants (whisper.audio: SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES;
  * imported by the reference at data_loader.py:13 and data/utils.py:10). */
@@ -41,6 +41,20 @@ extern "C" {
 #define WFT_N_FRAMES 3000
 
 enum wft_pcm_dtype { WFT_PCM_F32 = 0, WFT_PCM_I16 = 1 };
+
+/* How the few counters in the workspace get back to zero between launches.
+ *   WFT_WS_MEMSET   the library enqueues a cudaMemsetAsync in front of every launch; the workspace may hold anything.
+ *   WFT_WS_PHASE_A / WFT_WS_PHASE_B   self-cleaning: the counters exist twice, a launch uses one copy and zeroes the other
+ *       for the launch after it (no memset node, so back-to-back launches chain kernel to kernel and the next grid is
+ *       scheduled under the tail of the previous one).  Contract: the caller zeroes the whole workspace ONCE before its
+ *       first use, passes A, B, A, B, ... on consecutive launches that use it, and never shares it between streams. */
+enum wft_workspace_mode { WFT_WS_MEMSET = 0, WFT_WS_PHASE_A = 1, WFT_WS_PHASE_B = 2 };
+
+/* launch_flags.  WFT_LAUNCH_PDL: programmatic dependent launch -- when the previous operation on the stream is a kernel, this
+ * grid is scheduled while that kernel drains (its table prologue overlaps the tail) and waits on the device before it touches
+ * anything.  Worth ~4 % on back-to-back front-end launches of one stream; it does NOT pay when other streams are busy on the
+ * same GPU (the early CTAs hold SM slots while they wait), so it is a per-call choice. */
+#define WFT_LAUNCH_PDL 1
 
 enum wft_status {
   WFT_OK = 0,
@@ -71,6 +85,18 @@ typedef struct wft_frontend_args {
   float* out;               /* device [B, n_mels, n_frames_out] contiguous                                      */
   void* workspace;          /* device, >= wft_frontend_workspace_bytes(); contents are scratch                  */
   size_t workspace_bytes;
+  int32_t workspace_mode;   /* enum wft_workspace_mode; 0 (a zero-initialised struct) = WFT_WS_MEMSET                */
+  int32_t launch_flags;     /* WFT_LAUNCH_*; 0 = plain launch                                                    */
+  /* ---- optional: draw the SpecAugment intervals inside this call (mask_params must be NULL) ----
+   * draw_masks != 0: the library launches wft_specaug_draw's kernel into a corner of the workspace right in front of the
+   * fused kernel -- (seed, clip_offset, time / freq mask parameter, p) mean what they mean for wft_specaug_draw, n_mels and
+   * n_frames_out are this call's -- so that one augmented batch is ONE call from the host. */
+  int32_t draw_masks;
+  int32_t draw_time_mask_param;
+  int32_t draw_freq_mask_param;
+  float draw_p;
+  uint64_t draw_seed;
+  uint64_t draw_clip_offset;
 } wft_frontend_args;
 
 /* ABI version of the loaded library (== WFT_ABI_VERSION of the header it was built from). */

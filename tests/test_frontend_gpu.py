@@ -495,6 +495,12 @@ def test_torch_custom_ops_pass_opcheck(wft, cuda):
     opcheck(torch.ops.wft.frontend_forward, (pcm, 80, 0, lengths, 300, nv, masks, 0.0))
     opcheck(torch.ops.wft.frontend_forward, ((pcm * 32767).to(torch.int16), 128, 160, None, 0, None, None, 0.0))
     opcheck(torch.ops.wft.frontend_forward_out, (pcm, 80, 0, None, 300, None, masks, 0.0, torch.empty(3, 80, 300, device=cuda)))
+    opcheck(torch.ops.wft.frontend_forward_drawn_out,
+            (pcm, 80, 0, lengths, 300, nv, 42, 7, 100, 27, 0.5, 0.0, torch.empty(3, 80, 300, device=cuda)))
+    drawn = torch.empty(3, 80, 300, device=cuda)
+    torch.ops.wft.frontend_forward_drawn_out(pcm, 80, 0, lengths, 300, nv, 42, 7, 100, 27, 1.0, 0.0, drawn)
+    assert torch.equal(drawn, torch.ops.wft.frontend_forward(pcm, 80, 0, lengths, 300, nv,
+                                                               wft.draw_mask_params(42, 7, 3, 80, 300, 100, 27, 1.0), 0.0))
     opcheck(torch.ops.wft.pad_or_trim, (torch.randn(2, 70, 5, device=cuda), 300))
     opcheck(torch.ops.wft.pad_or_trim, (torch.randn(2, 70, 5, device=cuda), 30))
     mel = torch.randn(3, 80, 300, device=cuda)

@@ -6,7 +6,7 @@
 #include "../include/wft.h"
 extern "C" int wft_debug_read(int*);
 int main(int argc, char** argv) {
-  int B = argc > 1 ? atoi(argv[1]) : 16, nm = argc > 2 ? atoi(argv[2]) : 128, iters = argc > 3 ? atoi(argv[3]) : 4; int ragged = argc > 4 ? atoi(argv[4]) : 0;
+  int B = argc > 1 ? atoi(argv[1]) : 16, nm = argc > 2 ? atoi(argv[2]) : 128, iters = argc > 3 ? atoi(argv[3]) : 4; int ragged = argc > 4 ? atoi(argv[4]) : 0; int selfclean = argc > 5 ? atoi(argv[5]) : 1; int pdl = argc > 6 ? atoi(argv[6]) : 1;
   size_t n = (size_t)B * 480000;
   std::vector<float> h(n);
   unsigned s = 12345;
@@ -14,20 +14,30 @@ int main(int argc, char** argv) {
   float *d_pcm, *d_out; void* ws; size_t wsb = 0;
   cudaMalloc(&d_pcm, n * 4); cudaMemcpy(d_pcm, h.data(), n * 4, cudaMemcpyHostToDevice);
   cudaMalloc(&d_out, (size_t)B * nm * 3000 * 4);
-  wft_frontend_workspace_bytes(B, 480000, 3000, &wsb); cudaMalloc(&ws, wsb);
+  wft_frontend_workspace_bytes(B, 480000, 3000, &wsb); cudaMalloc(&ws, wsb); cudaMemset(ws, 0, wsb);
   int32_t* d_len = nullptr;
   if (ragged) { std::vector<int32_t> hl(B); unsigned r = 777; for (int i = 0; i < B; ++i) { r = r * 1664525u + 1013904223u; hl[i] = 16000 + (r >> 8) % 464001; }
     cudaMalloc(&d_len, B * 4); cudaMemcpy(d_len, hl.data(), B * 4, cudaMemcpyHostToDevice); }
   wft_frontend_args a{}; a.pcm = d_pcm; a.pcm_dtype = WFT_PCM_F32; a.batch = B; a.clip_stride = 480000; a.n_samples = 480000;
-  a.lengths = d_len; a.n_mels = nm; a.n_frames_out = 3000; a.out = d_out; a.workspace = ws; a.workspace_bytes = wsb;
+  a.lengths = d_len; a.n_mels = nm; a.n_frames_out = 3000; a.out = d_out; a.workspace = ws; a.workspace_bytes = wsb; a.launch_flags = pdl ? WFT_LAUNCH_PDL : 0;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < iters; ++it) {
+    a.workspace_mode = selfclean ? (it & 1 ? WFT_WS_PHASE_B : WFT_WS_PHASE_A) : WFT_WS_MEMSET;
     cudaEventRecord(e0);
     int rc = wft_frontend_forward(&a, 0);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     printf("iter %d rc=%d cuda=%s %.1f us (%.3f us/clip)\n", it, rc, cudaGetErrorString(e), ms * 1e3, ms * 1e3 / B);
+  }
+  {
+    const int K = 20;
+    cudaEventRecord(e0);
+    for (int it = 0; it < K; ++it) { a.workspace_mode = selfclean ? ((iters + it) & 1 ? WFT_WS_PHASE_B : WFT_WS_PHASE_A) : WFT_WS_MEMSET; wft_frontend_forward(&a, 0); }
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    printf("back-to-back x%d: %.1f us per launch\n", K, ms * 1e3 / K);
   }
 #ifdef WFT_DEBUG_SPIN
   int dbg[8]; wft_debug_read(dbg);

@@ -1,15 +1,49 @@
-import sys, torch, numpy as np
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
-import whisper_finetune_b200 as w
+"""The workload run under compute-sanitizer (memcheck / synccheck / racecheck): every kernel of the library, and every path of
+the fused kernel -- ragged lengths (silent tiles), partial-segment cuts, masks, int16 / 80 mel, a capped grid (pending FIFO
+overflow -> parked chain -> drain fix-ups), one long clip whose floor binds, a config-3 style batch, the fused augmentation
+epilogue, the draws, pad_or_trim and the activation mask."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import whisper_finetune_b200 as w  # noqa: E402
+
 torch.cuda.set_device(0)
-pcm = (0.1*torch.randn(3, 480000, device='cuda')).clamp(-1,1)
-lengths = torch.tensor([480000, 100000, 31234], dtype=torch.int32, device='cuda')
-nv = torch.tensor([-1, 500, 100], dtype=torch.int32, device='cuda')
+lib = w._lib.load()
+g = torch.Generator().manual_seed(0)
+pcm = (0.1 * torch.randn(3, 480000, generator=g)).clamp(-1, 1).cuda()
+lengths = torch.tensor([480000, 100000, 31234], dtype=torch.int32, device="cuda")
+nv = torch.tensor([-1, 500, 100], dtype=torch.int32, device="cuda")
 masks = w.draw_mask_params(1, 0, 3, 128, 3000, 100, 27, 1.0)
 out = w.frontend_forward(pcm, 128, lengths=lengths, n_valid_frames=nv, mask_params=masks, n_frames_out=3000)
-out16 = w.frontend_forward((pcm*32767).round().to(torch.int16), 80, lengths=lengths)
+out16 = w.frontend_forward((pcm * 32767).round().to(torch.int16), 80, lengths=lengths)
+# capped grid: 2 CTAs hold far more than 16 pending tiles of an incomplete clip -> parked chain + drain
+lib.wft_debug_set_max_ctas(2)
+capped = w.frontend_forward(pcm, 128, lengths=lengths, n_valid_frames=nv, mask_params=masks, n_frames_out=3000)
+lib.wft_debug_set_max_ctas(0)
+assert torch.equal(capped, out)
+# a 2-minute clip: loud second, then faint noise (the floor binds on every later tile), full grid
+long = 1e-7 * torch.randn(120 * 16000, generator=g)
+long[:16000] += 0.5 * torch.sin(torch.arange(16000) * 0.17)
+lm = w.log_mel_spectrogram(long.cuda(), n_mels=128)
+# config-3 style batch: 24 ragged clips, cuts, masks, through FrontEnd with the reference's config block (warp + masks)
+B = 24
+ragged = (0.1 * torch.randn(B, 480000, generator=g)).clamp(-1, 1)
+rl = torch.randint(16000, 480001, (B,), generator=g).to(torch.int32)
+ragged[torch.arange(480000)[None, :] >= rl[:, None]] = 0
+rv = torch.full((B,), -1, dtype=torch.int32)
+rv[::4] = torch.randint(2, 3000, (B // 4,), generator=g).to(torch.int32)
+fe = w.FrontEnd(n_mels=128, spec_augment=True, seed=3,
+                spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "time_warp_w": 80, "p": 0.7})
+ext = torch.randint(0, 6, (B, 2), generator=g).to(torch.int32)
+x = fe(ragged.cuda(), lengths=rl, n_valid_frames=rv, clip_offset=100, extremes=ext)
 wp = w.draw_warp_params(1, 0, 3, 3000, 80)
 tw = w.time_warp(out, wp)
+ep = w.augment_epilogue(out, wp, masks, None, spline="f32")
 pt = w.pad_or_trim(out[0, :, :100].contiguous(), 3000)
+act = torch.randn(2, 150, 128, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+w.mask_activations(act, (3, 40), (10, 50)).float().sum().backward()
 torch.cuda.synchronize()
-print('ok', float(out.sum()), float(out16.sum()), float(tw.sum()), float(pt.sum()))
+print("ok", float(out.sum()), float(out16.sum()), float(lm.sum()), float(x.sum()), float(tw.sum()), float(ep.sum()), float(pt.sum()))

@@ -13,9 +13,11 @@ LIB_PATH = os.path.join(HERE, "libwft_b200.so")
 
 WFT_PCM_F32 = 0
 WFT_PCM_I16 = 1
+WFT_WS_MEMSET, WFT_WS_PHASE_A, WFT_WS_PHASE_B = 0, 1, 2
+WFT_LAUNCH_PDL = 1
 WFT_ERR_INVALID = -1
 WFT_ERR_CUDA = -2
-ABI_VERSION = 4
+ABI_VERSION = 6
 
 
 class FrontendArgs(Structure):
@@ -37,6 +39,14 @@ class FrontendArgs(Structure):
         ("out", c_void_p),
         ("workspace", c_void_p),
         ("workspace_bytes", c_size_t),
+        ("workspace_mode", c_int32),
+        ("launch_flags", c_int32),
+        ("draw_masks", c_int32),
+        ("draw_time_mask_param", c_int32),
+        ("draw_freq_mask_param", c_int32),
+        ("draw_p", c_float),
+        ("draw_seed", c_uint64),
+        ("draw_clip_offset", c_uint64),
     ]
 
 

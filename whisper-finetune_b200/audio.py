@@ -59,6 +59,18 @@ def _as_pcm_tensor(audio, device: torch.device) -> torch.Tensor:
     return audio
 
 
+def as_i32_on(t, dev, shape, name):
+    """Optional per-clip metadata (list / ndarray / tensor) -> contiguous int32 tensor on ``dev`` with ``shape``, or None."""
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(np.asarray(t), dtype=torch.int32)
+    t = t.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+    if tuple(t.shape) != shape:
+        raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+    return t
+
+
 def frontend_forward(pcm: torch.Tensor, n_mels: int, padding: int = 0, lengths: Optional[torch.Tensor] = None,
                      n_frames_out: int = 0, n_valid_frames: Optional[torch.Tensor] = None,
                      mask_params: Optional[torch.Tensor] = None, mask_value: float = 0.0,
@@ -78,14 +90,7 @@ def frontend_forward(pcm: torch.Tensor, n_mels: int, padding: int = 0, lengths: 
     dev = pcm.device
 
     def _i32(t, name, shape):
-        if t is None:
-            return None
-        if not torch.is_tensor(t):
-            t = torch.as_tensor(np.asarray(t), dtype=torch.int32)
-        t = t.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
-        if tuple(t.shape) != shape:
-            raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
-        return t
+        return as_i32_on(t, dev, shape, name)
 
     lengths = _i32(lengths, "lengths", (B,))
     n_valid_frames = _i32(n_valid_frames, "n_valid_frames", (B,))

@@ -134,6 +134,8 @@ struct FrontendParams {
   uint32_t zero;        // always 0; gives the completion counter a data dependency the compiler cannot fold
   uint32_t tpc_magic;   // floor(2^32 / tiles_per_clip): tile -> clip by multiply-high (+ one correction step)
   int32_t vec_ok;       // `out` is 32-byte aligned and n_frames_out % 8 == 0: the mel phase may use 32-byte stores
+  uint4* clean;         // self-cleaning workspace: the header + statistics of the OTHER phase, zeroed by CTA 0 for the launch
+  int32_t clean_vec;    // after this one (16-byte vectors; 0 = the host memsets before every launch)
   int32_t chunk;        // consecutive tiles a CTA takes per claim (>= 1): neighbours share the clip, so the per-clip loads of
                         // describe_tile hit its memo and the tile counter sees 1 / chunk of the atomics
 };
@@ -729,6 +731,13 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     }
   }
   uint64_t* audio_bar = reinterpret_cast<uint64_t*>(sm_ctl + kCtlMbar);  // completion of the audio tile's bulk copies
+  // Programmatic dependent launch: everything above (7.4 KB of tables into shared memory) may overlap the tail of the
+  // previous kernel on the stream; its results and the workspace may only be touched from here on.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // the other phase's counters belong to the launch BEFORE this one (complete: see above) and to the one AFTER it (not
+  // started: stream order): zeroing them here needs no fence and replaces a memset launch per call
+  if (blockIdx.x == 0)
+    for (int i = tid; i < p.clean_vec; i += kThreads) p.clean[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     sm_ctl[kCtlMemo] = -1;
     sm_ctl[kCtlHead] = 0;
@@ -783,10 +792,12 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
 #define PUBLISH_FINISH()                                                                             \
   do {                                                                                               \
     const uint32_t dep_ = pub_dep | __shfl_sync(0x3u, pub_dep, 1);                                   \
-    const int pc_ = sm_ctl[kCtlPubClip];                                                             \
-    if (lane == 0 && pc_ >= 0) {                                                                     \
-      atomicAdd(&p.stats[pc_].done, 1u + (dep_ & p.zero));                                           \
-      sm_ctl[kCtlPubClip] = -1;                                                                      \
+    if (lane == 0) {   /* kCtlPubClip is lane 0's alone (racecheck: no second reader) */               \
+      const int pc_ = sm_ctl[kCtlPubClip];                                                           \
+      if (pc_ >= 0) {                                                                                \
+        atomicAdd(&p.stats[pc_].done, 1u + (dep_ & p.zero));                                         \
+        sm_ctl[kCtlPubClip] = -1;                                                                    \
+      }                                                                                              \
     }                                                                                                \
   } while (0)
     const int4 d_top = DESC4;
@@ -1076,6 +1087,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     lstate ^= kCtlSlot;   // the next tile becomes current; its slot is rewritten only behind the tile-after-next's first barrier
   }
   if (warp == 0 && lane < 2) PUBLISH_FINISH();   // the last tile's completion count
+  // no more tiles: the next kernel on the stream may start filling the SM slots this grid frees (it waits at its own
+  // griddepcontrol.wait until this grid has completed)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #undef DESC
 #undef NDESC
 #undef DESC4

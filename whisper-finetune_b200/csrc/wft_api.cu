@@ -60,7 +60,7 @@ int grid_for(KernelT kernel, GridInfo* cache, int* ctas) {
 }
 
 template <int NM, typename PcmT>
-int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream) {
+int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launch_flags) {
   static GridInfo cache[64];
   static const bool env_read = [] {
     if (const char* e = getenv("WFT_DEBUG_CHUNK")) g_debug_chunk = atoi(e);
@@ -76,9 +76,20 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream) {
   wft::FrontendParams q = p;
   const int per_cta = p.total_tiles / ctas;
   q.chunk = g_debug_chunk > 0 ? g_debug_chunk : (per_cta / 24 < 1 ? 1 : (per_cta / 24 > 4 ? 4 : per_cta / 24));
-  wft::frontend_kernel<NM, PcmT><<<ctas, wft::kThreads, wft::kSmemBytes, stream>>>(q);
+  // programmatic stream serialization: this grid may be scheduled while the previous kernel on the stream drains; the
+  // kernel itself waits (griddepcontrol.wait) before it touches anything the previous one produced
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(wft::kThreads);
+  cfg.dynamicSmemBytes = wft::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (launch_flags & WFT_LAUNCH_PDL) ? 1 : 0;
+  WFT_CUDA(cudaLaunchKernelEx(&cfg, wft::frontend_kernel<NM, PcmT>, q));
   ++g_launches;
-  WFT_CUDA(cudaGetLastError());
   return WFT_OK;
 }
 
@@ -91,6 +102,7 @@ int query_grid(int32_t* ctas) {
   return rc;
 }
 
+// workspace = two phases of {16-byte header (tile counter), ClipStat[batch]} + the parked-tile chain (one int per tile)
 size_t ws_header_bytes(int32_t batch) { return 16 + sizeof(wft::ClipStat) * static_cast<size_t>(batch); }
 
 // ---- small stand-alone kernels ---------------------------------------------------------------------------
@@ -463,7 +475,9 @@ int wft_frontend_workspace_bytes(int32_t batch, int32_t n_samples_total, int32_t
   const int64_t span = n_frames_out > n_frames ? n_frames_out : n_frames;
   const int64_t tiles = (span + wft::kTileFrames - 1) / wft::kTileFrames * batch;
   if (tiles < 1 || tiles >= wft::kSilentBit) return fail(WFT_ERR_INVALID, "batch x frames out of range (tile ids must stay below 2^30)");
-  size_t b = ws_header_bytes(batch) + static_cast<size_t>(tiles) * sizeof(int32_t);
+  // two phases of counters, the parked-tile chain, and [batch, 4] int32 for intervals drawn inside the call
+  size_t b = 2 * ws_header_bytes(batch) + ((static_cast<size_t>(tiles) * sizeof(int32_t) + 15) & ~static_cast<size_t>(15)) +
+             static_cast<size_t>(batch) * 16;
   *bytes = (b + 255) & ~static_cast<size_t>(255);
   return WFT_OK;
 }
@@ -494,6 +508,10 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
   if ((reinterpret_cast<uintptr_t>(a->workspace) & 15) != 0) return fail(WFT_ERR_INVALID, "workspace must be 16-byte aligned");
   if (a->mask_params != nullptr && (reinterpret_cast<uintptr_t>(a->mask_params) & 15) != 0)
     return fail(WFT_ERR_INVALID, "mask_params must be 16-byte aligned");
+  if (a->draw_masks != 0) {
+    if (a->mask_params != nullptr) return fail(WFT_ERR_INVALID, "draw_masks and mask_params are mutually exclusive");
+    if (!(a->draw_p >= 0.0f && a->draw_p <= 1.0f)) return fail(WFT_ERR_INVALID, "spec_augment p must be between 0 and 1");
+  }
   if (((n_frames_out & 3) == 0) && (reinterpret_cast<uintptr_t>(a->out) & 15) != 0)
     return fail(WFT_ERR_INVALID, "out must be 16-byte aligned");
 
@@ -504,10 +522,20 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
   p.n_valid = a->n_valid_frames;
   p.masks = a->mask_params;
   p.out = a->out;
-  uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+  if (a->workspace_mode < WFT_WS_MEMSET || a->workspace_mode > WFT_WS_PHASE_B)
+    return fail(WFT_ERR_INVALID, "workspace_mode must be WFT_WS_MEMSET, WFT_WS_PHASE_A or WFT_WS_PHASE_B");
+  const size_t hdr = ws_header_bytes(a->batch);
+  const int phase = a->workspace_mode == WFT_WS_PHASE_B ? 1 : 0;
+  uint8_t* ws = static_cast<uint8_t*>(a->workspace) + phase * hdr;
   p.tile_counter = reinterpret_cast<uint32_t*>(ws);
   p.stats = reinterpret_cast<wft::ClipStat*>(ws + 16);
-  p.next = reinterpret_cast<int32_t*>(ws + ws_header_bytes(a->batch));
+  p.next = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(a->workspace) + 2 * hdr);
+  p.clean = nullptr;
+  p.clean_vec = 0;
+  if (a->workspace_mode != WFT_WS_MEMSET) {   // self-cleaning: this launch zeroes the other phase for the next one
+    p.clean = reinterpret_cast<uint4*>(static_cast<uint8_t*>(a->workspace) + (1 - phase) * hdr);
+    p.clean_vec = static_cast<int32_t>(hdr / 16);
+  }
   p.n_samples = a->n_samples;
   p.n_total = n_total;
   p.batch = a->batch;
@@ -522,11 +550,22 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
   p.tpc_magic = magic > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(magic);
   p.vec_ok = ((reinterpret_cast<uintptr_t>(a->out) & 31) == 0 && (n_frames_out & 7) == 0) ? 1 : 0;
 
-  WFT_CUDA(cudaMemsetAsync(ws, 0, ws_header_bytes(a->batch), stream));
-  if (a->n_mels == 128) {
-    return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<128, float>(p, stream) : launch_frontend<128, int16_t>(p, stream);
+  if (a->workspace_mode == WFT_WS_MEMSET) WFT_CUDA(cudaMemsetAsync(ws, 0, hdr, stream));
+  if (a->draw_masks != 0) {
+    const size_t chain = (static_cast<size_t>(p.total_tiles) * sizeof(int32_t) + 15) & ~static_cast<size_t>(15);
+    int32_t* drawn = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(a->workspace) + 2 * hdr + chain);
+    specaug_draw_kernel<<<(a->batch + 127) / 128, 128, 0, stream>>>(a->draw_seed, a->draw_clip_offset, a->batch, a->n_mels, n_frames_out,
+                                                                   a->draw_time_mask_param, a->draw_freq_mask_param, a->draw_p, drawn);
+    ++g_launches;
+    WFT_CUDA(cudaGetLastError());
+    p.masks = drawn;
   }
-  return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<80, float>(p, stream) : launch_frontend<80, int16_t>(p, stream);
+  if (a->n_mels == 128) {
+    return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<128, float>(p, stream, a->launch_flags)
+                                       : launch_frontend<128, int16_t>(p, stream, a->launch_flags);
+  }
+  return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<80, float>(p, stream, a->launch_flags)
+                                     : launch_frontend<80, int16_t>(p, stream, a->launch_flags);
 }
 
 int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t* threads, int32_t* smem_bytes) {

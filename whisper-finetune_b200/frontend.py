@@ -69,6 +69,18 @@ class FrontEnd:
             raise ValueError(f"clips longer than {self.n_samples} samples must be chunked upstream")
         pcm = pcm.to(self.device, non_blocking=True)
         B, N = pcm.shape
+        if (mask_params is None and augment is None and extremes is None and self.spec_augment and self.spec_augment_p > 0.0
+                and self.time_warp_w == 0 and pcm.dtype in (torch.float32, torch.int16) and pcm.stride(1) == 1):
+            # the common augmented batch (masks only): draw + fused kernel behind ONE op call
+            from .audio import as_i32_on
+
+            if out is None:
+                out = torch.empty((B, self.n_mels, self.n_frames), dtype=torch.float32, device=self.device)
+            torch.ops.wft.frontend_forward_drawn_out(pcm, self.n_mels, self.n_samples - N, as_i32_on(lengths, self.device, (B,), "lengths"),
+                                                     self.n_frames, as_i32_on(n_valid_frames, self.device, (B,), "n_valid_frames"),
+                                                     self.seed, int(clip_offset), self.time_mask_param, self.freq_mask_param,
+                                                     self.spec_augment_p, 0.0, out)
+            return out
         gate = None
         p_draw = self.spec_augment_p
         if augment is not None:

@@ -9,6 +9,7 @@ running anything) and, for the one op that sits on an autograd graph (``mask_bsd
 
     wft::frontend_forward      PCM [B, N] (+ lengths, n_valid_frames, mask_params)        -> features [B, n_mels, T]
     wft::frontend_forward_out  same, written into a caller-owned buffer                   (mutates ``out``)
+    wft::frontend_forward_drawn_out  the same with the SpecAugment intervals drawn inside the call (one host call per batch)
     wft::pad_or_trim           [outer, len_in, inner] float32 -> [outer, length, inner], min-value pad (data/utils.py:380-404)
     wft::specaug_apply         features, mask_params [B, 4]                               -> masked copy
     wft::specaug_apply_        in place
@@ -40,15 +41,51 @@ def _ptr(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# Self-cleaning workspaces (include/wft.h, enum wft_workspace_mode): one per (device, stream, size), zeroed once; every launch
+# flips the phase, so no memset is enqueued and consecutive launches on a stream chain kernel to kernel.  A workspace is
+# only ever used on the stream it was created for (stream order is what makes the phase hand-over safe).
+_WORKSPACES = {}
+_MAX_WORKSPACES = 64
+
+
+# Programmatic dependent launch of the fused kernel (include/wft.h, WFT_LAUNCH_PDL): on by default -- a training loop feeds
+# one stream.  Code that keeps several streams of this GPU busy at once (bench.py's two-batches-in-flight loop) turns it off.
+_PDL = {"enabled": True}
+
+
+def set_programmatic_launch(enabled: bool) -> bool:
+    """-> the previous setting."""
+    old = _PDL["enabled"]
+    _PDL["enabled"] = bool(enabled)
+    return old
+
+
+def _workspace(dev: torch.device, stream: int, batch: int, nbytes: int):
+    # the layout inside a workspace depends on the batch size (two phases of 16 + 16 * batch bytes, then the tile chain), so
+    # a workspace is only ever re-used for the same (batch, size): another batch would find its counters where this one's
+    # tile chain left data
+    key = (dev.index, stream, batch, nbytes)
+    ent = _WORKSPACES.get(key)
+    if ent is None:
+        if len(_WORKSPACES) >= _MAX_WORKSPACES:
+            _WORKSPACES.pop(next(iter(_WORKSPACES)))   # freed stream-ordered by the caching allocator
+        ent = _WORKSPACES[key] = [torch.zeros(nbytes, dtype=torch.uint8, device=dev), 0]
+    ent[1] += 1
+    return key, ent[0], _lib.WFT_WS_PHASE_A if ent[1] & 1 else _lib.WFT_WS_PHASE_B
+
+
 def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[Tensor], n_frames_out: int,
-                     n_valid_frames: Optional[Tensor], mask_params: Optional[Tensor], mask_value: float, out: Tensor) -> None:
+                     n_valid_frames: Optional[Tensor], mask_params: Optional[Tensor], mask_value: float, out: Tensor,
+                     draw=None) -> None:
+    """``draw`` = (seed, clip_offset, time_mask_param, freq_mask_param, p): the intervals are drawn inside the call."""
     lib = _lib.load()
     B, N = pcm.shape
     dev = pcm.device
     with torch.cuda.device(dev):
         need = ctypes.c_size_t(0)
         _lib.check(lib.wft_frontend_workspace_bytes(B, N + padding, out.shape[2], ctypes.byref(need)))
-        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        stream = _stream(dev)
+        key, ws, mode = _workspace(dev, stream, B, need.value)
         args = _lib.FrontendArgs(
             pcm=pcm.data_ptr(),
             pcm_dtype=_lib.WFT_PCM_F32 if pcm.dtype == torch.float32 else _lib.WFT_PCM_I16,
@@ -65,8 +102,18 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
             out=out.data_ptr(),
             workspace=ws.data_ptr(),
             workspace_bytes=need.value,
+            workspace_mode=mode,
+            launch_flags=_lib.WFT_LAUNCH_PDL if _PDL["enabled"] else 0,
         )
-        _lib.check(lib.wft_frontend_forward(ctypes.byref(args), _stream(dev)))
+        if draw is not None:
+            args.draw_masks = 1
+            args.draw_seed = draw[0] & (2**64 - 1)
+            args.draw_clip_offset = draw[1] & (2**64 - 1)
+            args.draw_time_mask_param, args.draw_freq_mask_param, args.draw_p = int(draw[2]), int(draw[3]), float(draw[4])
+        rc = lib.wft_frontend_forward(ctypes.byref(args), stream)
+        if rc != 0:
+            _WORKSPACES.pop(key, None)   # a launch that did not happen leaves the phase bookkeeping undefined
+        _lib.check(rc)
 
 
 def _frames(pcm: Tensor, padding: int, n_frames_out: int) -> int:
@@ -110,6 +157,28 @@ def frontend_forward_out(pcm: Tensor, n_mels: int, padding: int, lengths: Option
 
 @frontend_forward_out.register_fake
 def _(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, mask_params, mask_value, out):
+    return None
+
+
+@torch.library.custom_op("wft::frontend_forward_drawn_out", mutates_args=("out",), device_types="cuda")
+def frontend_forward_drawn_out(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[Tensor], n_frames_out: int,
+                               n_valid_frames: Optional[Tensor], seed: int, clip_offset: int, time_mask_param: int,
+                               freq_mask_param: int, p: float, mask_value: float, out: Tensor) -> None:
+    """The augmented batch as ONE call: SpecAugment intervals drawn on the device (Philox keyed by ``(seed, clip_offset + b)``,
+    same draw as ``wft::specaug_draw``) and the fused front end, two launches behind one trip through the dispatcher."""
+    _check_frontend_inputs(pcm, n_mels, lengths, n_valid_frames, None)
+    if not 0.0 <= p <= 1.0:
+        raise ValueError(f"spec_augment p must be between 0 and 1, got {p}")
+    want = (pcm.shape[0], n_mels, _frames(pcm, padding, n_frames_out))
+    if out.dtype != torch.float32 or tuple(out.shape) != want or not out.is_contiguous() or out.device != pcm.device:
+        raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {want}")
+    _launch_frontend(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, None, mask_value, out,
+                     draw=(seed, clip_offset, time_mask_param, freq_mask_param, p))
+
+
+@frontend_forward_drawn_out.register_fake
+def _(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, seed, clip_offset, time_mask_param, freq_mask_param, p,
+      mask_value, out):
     return None
 
 
