@@ -1,9 +1,12 @@
 #!/usr/bin/env python
-"""Turn the ncu artefacts a gpurun call left in gpurun_out/ into profiles/r01_ncu_summary.md (run in the build container).
+"""Turn the ncu artefacts a gpurun call left in gpurun_out/ into profiles/rNN_ncu_summary.md (run in the build container)
+and record the DRAM traffic of the captured launch in profiles/ncu_traffic.json (what bench.py reports as roofline.traffic).
 
-    python profiles/make_summary.py gpurun_out/launches_r1.csv gpurun_out/prof_r1.ncu-rep [n_tiles_per_launch]
+    python profiles/make_summary.py gpurun_out/launches.csv gpurun_out/prof.ncu-rep [n_tiles_per_launch] [round] > profiles/rNN_ncu_summary.md
 """
 import csv
+import json
+import os
 import subprocess
 import sys
 from collections import defaultdict
@@ -32,7 +35,8 @@ def ncu_csv(rep, page):
 def main():
     launches, rep = sys.argv[1], sys.argv[2]
     n_tiles = float(sys.argv[3]) if len(sys.argv) > 3 else 6016.0
-    out = ["# Round 1 ncu evidence — `wft::frontend_kernel<128,float>` on B200 (sm_100a)", "",
+    rnd = sys.argv[4] if len(sys.argv) > 4 else "1"
+    out = [f"# Round {rnd} ncu evidence — `wft::frontend_kernel<128,float>` on B200 (sm_100a)", "",
            "All captures ran under `gpurun` on one B200 with `--clock-control none`. Times under ncu are cold-cache and "
            "serialised: they are evidence of SHARES and counters, never bench values.", ""]
     agg = launch_list(launches)
@@ -75,6 +79,12 @@ def main():
             out.append(f"| {label} | {g(k)} {units.get(k, '')} |")
     try:
         rd, wr = float(d["dram__bytes_read.sum"]), float(d["dram__bytes_write.sum"])
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units["dram__bytes_read.sum"]]
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json"), "w") as fh:
+            json.dump({"dram_bytes_per_launch": (rd + wr) * scale, "read": rd * scale, "write": wr * scale,
+                       "kernel": "wft::frontend_kernel<128,float>, B=64", "source": f"round {rnd}: ncu --set full of tools/harness 64 128, "
+                       + os.path.basename(rep)}, fh)
+            fh.write("\n")
         out += ["", f"DRAM traffic of the launch = {rd + wr:.1f} {units['dram__bytes_read.sum']} (read {rd:.1f} + write {wr:.1f}) "
                 "against 221.2 MB of algorithmic bytes (122.9 MB PCM in + 98.3 MB features out): the input is read once, and "
                 "the output is written at most once (the rest of the dirty lines leave L2 after the kernel) — the in-place "
