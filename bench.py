@@ -37,7 +37,8 @@ TIME_MASK = 100
 FREQ_MASK = 43
 TIME_WARP_W = 80
 SEED = 42
-N_STREAMS = 2   # batches in flight in the throughput loop (the roofline loop stays strictly one launch after another)
+N_STREAMS = 1   # one stream; consecutive batches are declared independent (WFT_LAUNCH_OVERLAP), so batch i + 1 fills the SM slots
+                # batch i frees as it runs out of tiles
 BYTES_PER_CLIP = 4 * N_SAMPLES + 4 * N_MELS * N_FRAMES  # 3 456 000 (algorithmic bytes, f32 in, 128 mel)
 METRIC = "30-s clips/sec log-mel+SpecAugment"
 UNIT = "clips/s"
@@ -64,8 +65,9 @@ def workload_config(n_gpus):
         "spec_augment": True, "sharding": "DistributedSampler-style batch shards, no data-path collective",
         "cache": "4 rotating input/output buffer sets (885 MB per GPU) > 126 MB L2",
         "streams": N_STREAMS,
-        "in_flight": "value: step i on stream i % 2 (two batches in flight, plain launches); roofline: one launch after another on "
-                     "one stream with programmatic dependent launch (the next grid is scheduled under the tail of the previous one)",
+        "in_flight": "one stream, consecutive batches declared independent (wft.set_overlap(True) -> WFT_LAUNCH_OVERLAP: programmatic "
+                     "dependent launches that do not wait for the previous batch's grids, workspace ring of 16 counter sets); "
+                     "roofline.serialized is the same loop with every batch waiting for the one before it",
     }
 
 
@@ -353,13 +355,11 @@ def run_ours(args):
             step(i)
         join()
 
-    # programmatic dependent launch pays on ONE busy stream (the roofline loop below); with two batches in flight on two
-    # streams the early CTAs of a dependent launch take SM slots from the other stream's kernel (measured: -6 %), so off here
-    wft.set_programmatic_launch(False)
+    # consecutive steps use different buffer sets (4 rotating sets), so they are independent batches
+    wft.set_overlap(True)
     with ClockSampler(local_rank) as clocks:
         block_ms, block_times = repeat_blocks(value_body)
         launches_total = int(lib.wft_launch_count(0))
-    wft.set_programmatic_launch(True)
     launches = launches_total // len(block_times)      # launches of ONE timed K-step block
     ms_max = block_ms
     value = world * BATCH * args.steps / (ms_max * 1e-3)
@@ -376,6 +376,10 @@ def run_ours(args):
 
     kernel_block_ms, kernel_times = repeat_blocks(kernel_body, min_gpu_seconds=0.3)
     kernel_ms = kernel_block_ms / args.steps
+    wft.set_overlap(False)       # the same loop, every batch waiting for the one in front of it (plain programmatic launches)
+    serial_block_ms, _ = repeat_blocks(kernel_body, min_gpu_seconds=0.2)
+    serial_ms = serial_block_ms / args.steps
+    wft.set_overlap(True)
 
     # the production configs also time-warp (configs/config_turbo_best.yaml:97, config_large_v3_best_muon_ddp4.yaml:120:
     # time_warp_w = 80; applied at data_loader.py:285): front-end kernel -> ONE fused epilogue pass (warp + masks)
@@ -391,13 +395,12 @@ def run_ours(args):
                 fe_warp(pcm_sets[i % n_sets], clip_offset=(i * world + rank) * BATCH, out=warp_out[i % n_sets])
         join()
 
-    wft.set_programmatic_launch(False)
     warp_body(0)
     torch.cuda.synchronize()
     lib.wft_launch_count(1)
     warp_block_ms, warp_times = repeat_blocks(warp_body, min_gpu_seconds=0.3)
     warp_launches = int(lib.wft_launch_count(0)) // len(warp_times)
-    wft.set_programmatic_launch(True)
+    wft.set_overlap(False)
     value_warp = world * BATCH * args.steps / (warp_block_ms * 1e-3)
     # the epilogue kernel alone, for its own roofline: one read + one write of the features
     warps = wft.draw_warp_params(SEED, 0, BATCH, N_FRAMES, TIME_WARP_W, 1.0, dev)
@@ -512,8 +515,13 @@ def run_ours(args):
             "gpu_launches_per_step": launches / max(args.steps, 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "wft::frontend_kernel<128,float>", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": BATCH * BYTES_PER_CLIP},
+                         "kernel": "wft::frontend_kernel<128,float> (+ its fix-up grid)", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": BATCH * BYTES_PER_CLIP,
+                         "what": "K back-to-back batches on one stream, pre-drawn masks, independent batches overlapped; "
+                                 "kernel_ms = timed region / K",
+                         "serialized": {"kernel_ms": serial_ms, "achieved": BATCH * BYTES_PER_CLIP / (serial_ms * 1e-3) / 1e9,
+                                        "frac": BATCH * BYTES_PER_CLIP / (serial_ms * 1e-3) / 1e9 / peak,
+                                        "what": "same loop, every batch waits for the previous one (no overlap)"}},
         }
         epi_bytes = 2 * 4 * N_MELS * N_FRAMES * BATCH
         line["value_with_time_warp"] = {

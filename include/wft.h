@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WFT_ABI_VERSION 6
+#define WFT_ABI_VERSION 7
 
 /* Front-end constants (whisper.audio: SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES;
  * imported by the reference at data_loader.py:13 and data/utils.py:10). */
@@ -42,19 +42,33 @@ extern "C" {
 
 enum wft_pcm_dtype { WFT_PCM_F32 = 0, WFT_PCM_I16 = 1 };
 
-/* How the few counters in the workspace get back to zero between launches.
+/* How the few counters in the workspace get back to zero between launches (the workspace holds WFT_WS_PHASES copies of
+ * them -- one tile counter and 8 bytes of statistics per clip -- plus per-tile scratch).
  *   WFT_WS_MEMSET   the library enqueues a cudaMemsetAsync in front of every launch; the workspace may hold anything.
- *   WFT_WS_PHASE_A / WFT_WS_PHASE_B   self-cleaning: the counters exist twice, a launch uses one copy and zeroes the other
- *       for the launch after it (no memset node, so back-to-back launches chain kernel to kernel and the next grid is
- *       scheduled under the tail of the previous one).  Contract: the caller zeroes the whole workspace ONCE before its
- *       first use, passes A, B, A, B, ... on consecutive launches that use it, and never shares it between streams. */
-enum wft_workspace_mode { WFT_WS_MEMSET = 0, WFT_WS_PHASE_A = 1, WFT_WS_PHASE_B = 2 };
+ *   WFT_WS_PHASE_A / WFT_WS_PHASE_B   self-cleaning: a launch uses one copy and zeroes the other for the launch after it (no
+ *       memset node, so back-to-back launches chain kernel to kernel).  Contract: the caller zeroes the whole workspace ONCE
+ *       before its first use, passes A, B, A, B, ... on consecutive launches that use it, and never shares it between streams.
+ *   WFT_WS_RING + k, k = 0 .. WFT_WS_PHASES-1   the copies are used round robin; the call with k == 0 zeroes all of them with one
+ *       cudaMemsetAsync (the workspace may hold anything before it).  Contract: the caller passes k = 0, 1, ..., WFT_WS_PHASES-1,
+ *       0, 1, ... on consecutive launches that use the workspace and never shares it between streams.  The only mode in which
+ *       launches may overlap (WFT_LAUNCH_OVERLAP): two launches in flight never share a copy, and the memset at k == 0 is the
+ *       one point per WFT_WS_PHASES launches where everything in front of it has to be complete. */
+#define WFT_WS_PHASES 16
+enum wft_workspace_mode { WFT_WS_MEMSET = 0, WFT_WS_PHASE_A = 1, WFT_WS_PHASE_B = 2, WFT_WS_RING = 16 /* + k */ };
 
-/* launch_flags.  WFT_LAUNCH_PDL: programmatic dependent launch -- when the previous operation on the stream is a kernel, this
- * grid is scheduled while that kernel drains (its table prologue overlaps the tail) and waits on the device before it touches
- * anything.  Worth ~4 % on back-to-back front-end launches of one stream; it does NOT pay when other streams are busy on the
- * same GPU (the early CTAs hold SM slots while they wait), so it is a per-call choice. */
+/* launch_flags.
+ * WFT_LAUNCH_PDL: programmatic dependent launch -- when the previous operation on the stream is a kernel, this grid is scheduled
+ *   while that kernel drains (its table prologue overlaps the tail) and waits on the device before it touches anything.  Worth
+ *   a few per cent on back-to-back front-end launches of one stream; it does NOT pay when other streams are busy on the same GPU
+ *   (the early CTAs hold SM slots while they wait), so it is a per-call choice.
+ * WFT_LAUNCH_OVERLAP (implies PDL; needs WFT_WS_RING): the caller declares this call INDEPENDENT of the wft_frontend_forward call
+ *   in front of it on the stream -- it reads nothing that call writes (its `out`) and writes nothing that call reads or writes
+ *   (`pcm`, `lengths`, `n_valid_frames`, `mask_params`, `out`) -- and that nothing but wft_frontend_forward calls was enqueued
+ *   on the stream in between.  The grid then does not wait for the previous call's grids to complete: its CTAs start working
+ *   in the SM slots the previous batch frees as it runs out of tiles, so consecutive batches run without a tail (B = 64:
+ *   -12 % per launch).  Everything enqueued AFTER the call is ordered behind all of it as usual. */
 #define WFT_LAUNCH_PDL 1
+#define WFT_LAUNCH_OVERLAP 2
 
 enum wft_status {
   WFT_OK = 0,
@@ -183,9 +197,8 @@ int wft_mask_bsd(const void* in, void* out, int32_t elem_bytes, int64_t batch, i
 int64_t wft_launch_count(int reset);
 int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t* threads, int32_t* smem_bytes);
 
-/* Test hook: cap the persistent grid of wft_frontend_forward at `max_ctas` CTAs (0 = no cap, the default).  Results do not
- * depend on the grid; a tiny grid forces the kernel's pending-tile FIFO to overflow into the parked chain and every
- * fix-up into the drain loop, paths a full-size grid only takes for clips longer than ~19 minutes. */
+/* Test hook: cap the persistent grids of wft_frontend_forward (front-end and fix-up kernel) at `max_ctas` CTAs (0 = no cap, the
+ * default).  Results must not depend on the grid. */
 int wft_debug_set_max_ctas(int32_t max_ctas);
 
 #ifdef __cplusplus

@@ -232,10 +232,10 @@ def test_config3_batch_256_matches_oracle(wft, cuda):
 
 
 @pytest.mark.parametrize("max_ctas", [1, 3, 40])
-def test_tiny_grid_takes_the_parked_chain_and_drain(wft, cuda, max_ctas):
-    """The result must not depend on the persistent grid.  With 1-40 CTAs a CTA holds far more than 16 pending tiles of an
-    incomplete clip, so the pending FIFO overflows into the parked chain and the fix-ups (floor binds on the hdr clip,
-    min pad, silent tiles, masks) run from the drain loop -- the paths a full grid takes only for very long clips."""
+def test_result_does_not_depend_on_the_grid(wft, cuda, max_ctas):
+    """The result must not depend on the persistent grids: with 1-40 CTAs both the front-end kernel (tile claims, TMA
+    prefetch chain) and the fix-up kernel (grid-stride scan; floor binds on the hdr clip, min pad, silent tiles, masks)
+    walk many more tiles per CTA than on the full grid."""
     lib = wft._lib.load()
     pcm = torch.stack([S.make("hdr"), S.make("white", seed=3), S.make("int16").float() / 32768.0, S.make("chirp")])
     lengths = np.asarray([480000, 300000, 480000, 123456], dtype=np.int32)
@@ -258,9 +258,9 @@ def test_tiny_grid_takes_the_parked_chain_and_drain(wft, cuda, max_ctas):
         assert (capped[b].cpu() - ref[b]).abs().max() <= S.MAX_ABS
 
 
-def test_forty_minute_clip_overflows_the_pending_fifo(wft, cuda):
-    """One 40-minute clip = 15 000 tiles > 16 FIFO slots x 888 CTAs: on the FULL grid every CTA parks tiles, and the floor
-    binds on almost all of them (2 s of loud tone, then faint noise 14 decades down)."""
+def test_forty_minute_clip_floor_binds_almost_everywhere(wft, cuda):
+    """One 40-minute clip = 15 000 tiles of ONE clip: the floor binds on almost all of them (2 s of loud tone, then faint
+    noise 14 decades down), so the fix-up grid rewrites nearly the whole output."""
     n = 40 * 60 * 16000
     g = torch.Generator().manual_seed(40)
     x = 1e-7 * torch.randn(n, generator=g)
@@ -273,6 +273,65 @@ def test_forty_minute_clip_overflows_the_pending_fifo(wft, cuda):
     floor = got.min().item()
     assert (got == floor).float().mean().item() > 0.9, "the floor must bind on the quiet part"
     assert abs((got.max().item() - floor) - 2.0) <= 1e-5
+
+
+def test_overlapping_batches_equal_ordinary_launches(wft, cuda):
+    """WFT_LAUNCH_OVERLAP (independent batches do not wait for the grids in front of them): 40 consecutive calls on rotating
+    buffers -- more than two trips round the workspace ring -- must reproduce the ordinary launches bit for bit: full-length
+    batches (nothing to fix up), a ragged batch with cuts and masks (the fix-up grid rewrites a third of the tiles while the
+    next batch already runs), and a call that re-uses the previous call's output buffer (must NOT be overlapped)."""
+    B = 12
+    pcm, lengths, n_valid = _config3_batch(B, 7)
+    masks = OS.draw_mask_params(3, 100, B, 128, 3000, 100, 27, 1.0)
+    g = torch.Generator().manual_seed(11)
+    sets = []
+    for s in range(3):
+        x = (0.1 * torch.randn(B, 480000, generator=g)).clamp(-1, 1)
+        x[s] *= 1e-4                      # one quiet clip per batch
+        x[s + 3, 200000:] = 0.0           # exact zeros without `lengths`: the floor binds, nothing is "silent"
+        sets.append(x.to(cuda))
+    ragged = pcm.to(cuda)
+    # device-side metadata: no host-to-device copy sits between two calls, so the ragged batch overlaps its neighbours too
+    lengths, n_valid = torch.from_numpy(lengths).to(cuda), torch.from_numpy(n_valid).to(cuda)
+    masks = torch.as_tensor(np.asarray(masks), dtype=torch.int32).to(cuda)
+    fe = wft.FrontEnd(n_mels=128)
+    want = [fe(x) for x in sets]
+    want_ragged = fe(ragged, lengths=lengths, n_valid_frames=n_valid, mask_params=masks)
+    torch.cuda.synchronize()
+    outs = [torch.empty_like(want[0]) for _ in range(4)]
+    old = wft.set_overlap(True)
+    try:
+        got = []
+        for i in range(40):
+            k = i % 4
+            if k == 3:
+                fe(ragged, lengths=lengths, n_valid_frames=n_valid, mask_params=masks, out=outs[3])
+            else:
+                fe(sets[k], out=outs[k])
+            if i % 7 == 6:   # same output buffer twice in a row: the second call must wait for the first
+                fe(sets[(k + 1) % 3], out=outs[k])
+                fe(sets[k] if k < 3 else sets[0], out=outs[k])
+                if k == 3:
+                    fe(ragged, lengths=lengths, n_valid_frames=n_valid, mask_params=masks, out=outs[3])
+        torch.cuda.synchronize()
+    finally:
+        wft.set_overlap(old)
+    for k in range(3):
+        assert torch.equal(outs[k], want[k]), f"overlapped batch {k}"
+    assert torch.equal(outs[3], want_ragged), "overlapped ragged batch"
+    # and with the intervals drawn inside the call (draw grid -> front-end grid -> fix-up grid per batch)
+    fe_aug = wft.FrontEnd(n_mels=128, spec_augment=True, spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "p": 1.0},
+                          seed=5)
+    want_aug = [fe_aug(sets[k], clip_offset=64 * k).clone() for k in range(3)]
+    old = wft.set_overlap(True)
+    try:
+        for i in range(36):
+            fe_aug(sets[i % 3], clip_offset=64 * (i % 3), out=outs[i % 3])
+        torch.cuda.synchronize()
+    finally:
+        wft.set_overlap(old)
+    for k in range(3):
+        assert torch.equal(outs[k], want_aug[k]), f"overlapped augmented batch {k}"
 
 
 def _gold(name):

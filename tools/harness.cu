@@ -6,7 +6,7 @@
 #include "../include/wft.h"
 extern "C" int wft_debug_read(int*);
 int main(int argc, char** argv) {
-  int B = argc > 1 ? atoi(argv[1]) : 16, nm = argc > 2 ? atoi(argv[2]) : 128, iters = argc > 3 ? atoi(argv[3]) : 4; int ragged = argc > 4 ? atoi(argv[4]) : 0; int selfclean = argc > 5 ? atoi(argv[5]) : 1; int pdl = argc > 6 ? atoi(argv[6]) : 1;
+  int B = argc > 1 ? atoi(argv[1]) : 16, nm = argc > 2 ? atoi(argv[2]) : 128, iters = argc > 3 ? atoi(argv[3]) : 4; int ragged = argc > 4 ? atoi(argv[4]) : 0; int selfclean = argc > 5 ? atoi(argv[5]) : 1; int pdl = argc > 6 ? atoi(argv[6]) : 1; int overlap = argc > 7 ? atoi(argv[7]) : 0; int nbuf = argc > 8 ? atoi(argv[8]) : 1;
   size_t n = (size_t)B * 480000;
   std::vector<float> h(n);
   unsigned s = 12345;
@@ -22,7 +22,7 @@ int main(int argc, char** argv) {
   a.lengths = d_len; a.n_mels = nm; a.n_frames_out = 3000; a.out = d_out; a.workspace = ws; a.workspace_bytes = wsb; a.launch_flags = pdl ? WFT_LAUNCH_PDL : 0;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < iters; ++it) {
-    a.workspace_mode = selfclean ? (it & 1 ? WFT_WS_PHASE_B : WFT_WS_PHASE_A) : WFT_WS_MEMSET;
+    a.workspace_mode = selfclean == 2 ? WFT_WS_RING + it % WFT_WS_PHASES : selfclean ? (it & 1 ? WFT_WS_PHASE_B : WFT_WS_PHASE_A) : WFT_WS_MEMSET;
     cudaEventRecord(e0);
     int rc = wft_frontend_forward(&a, 0);
     cudaEventRecord(e1);
@@ -30,10 +30,25 @@ int main(int argc, char** argv) {
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     printf("iter %d rc=%d cuda=%s %.1f us (%.3f us/clip)\n", it, rc, cudaGetErrorString(e), ms * 1e3, ms * 1e3 / B);
   }
+  if (overlap) {   // independent batches: ring workspace, rotating output buffers, no wait for the launch in front
+    const int K = 32;
+    std::vector<float*> outs(nbuf, d_out);
+    for (int i = 1; i < nbuf; ++i) cudaMalloc(&outs[i], (size_t)B * nm * 3000 * 4);
+    a.launch_flags = WFT_LAUNCH_PDL | WFT_LAUNCH_OVERLAP;
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaEventRecord(e0);
+      for (int it = 0; it < K; ++it) { a.workspace_mode = WFT_WS_RING + it % WFT_WS_PHASES; a.out = outs[it % nbuf]; int rc = wft_frontend_forward(&a, 0); if (rc) { printf("rc=%d %s\n", rc, wft_last_error()); return 1; } }
+      cudaEventRecord(e1);
+      cudaError_t e = cudaDeviceSynchronize();
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      printf("overlapped x%d: %.1f us per launch (%s)\n", K, ms * 1e3 / K, cudaGetErrorString(e));
+    }
+    return 0;
+  }
   {
     const int K = 20;
     cudaEventRecord(e0);
-    for (int it = 0; it < K; ++it) { a.workspace_mode = selfclean ? ((iters + it) & 1 ? WFT_WS_PHASE_B : WFT_WS_PHASE_A) : WFT_WS_MEMSET; wft_frontend_forward(&a, 0); }
+    for (int it = 0; it < K; ++it) { a.workspace_mode = selfclean == 2 ? WFT_WS_RING + (iters + it) % WFT_WS_PHASES : selfclean ? ((iters + it) & 1 ? WFT_WS_PHASE_B : WFT_WS_PHASE_A) : WFT_WS_MEMSET; wft_frontend_forward(&a, 0); }
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

@@ -14,7 +14,7 @@ from .install import install
 from .loader import (DeviceFrontEndLoader, PcmBatch, decode_pcm_records, deferred_calculate_mel, encode_pcm_record,
                      install_loader, pcm_collate_fn)
 from .melbank import slaney_mel_bank
-from .ops import set_programmatic_launch
+from .ops import set_overlap, set_programmatic_launch
 from .sharding import all_gather_features, shard_indices
 
 __all__ = [
@@ -25,5 +25,5 @@ __all__ = [
     "mask_activations", "draw_deep_spans", "register_deep_spec_augment_hooks", "DeepSpecAugment",
     "encode_pcm_record", "decode_pcm_records", "PcmBatch", "pcm_collate_fn", "deferred_calculate_mel",
     "DeviceFrontEndLoader", "install_loader",
-    "shard_indices", "all_gather_features", "slaney_mel_bank", "install", "set_programmatic_launch",
+    "shard_indices", "all_gather_features", "slaney_mel_bank", "install", "set_programmatic_launch", "set_overlap",
 ]

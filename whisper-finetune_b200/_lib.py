@@ -13,11 +13,12 @@ LIB_PATH = os.path.join(HERE, "libwft_b200.so")
 
 WFT_PCM_F32 = 0
 WFT_PCM_I16 = 1
-WFT_WS_MEMSET, WFT_WS_PHASE_A, WFT_WS_PHASE_B = 0, 1, 2
-WFT_LAUNCH_PDL = 1
+WFT_WS_MEMSET, WFT_WS_PHASE_A, WFT_WS_PHASE_B, WFT_WS_RING = 0, 1, 2, 16
+WFT_WS_PHASES = 16
+WFT_LAUNCH_PDL, WFT_LAUNCH_OVERLAP = 1, 2
 WFT_ERR_INVALID = -1
 WFT_ERR_CUDA = -2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class FrontendArgs(Structure):

@@ -19,14 +19,18 @@
 //               are banded over the warps by tap count (wft_tables.inc) and each band's tap loop is fully unrolled;
 //               log10 via MUFU.LG2; the FINAL feature (L + 4) / 4 with the SpecAugment masks applied is written once to
 //               `out` as 32-byte stores (STG.256).
-//   per-clip max / min = ordered-int atomicMax into the workspace, completion counted per tile.  Once a clip is complete
-//               each CTA re-visits ITS OWN tiles of that clip only if something is still missing: the max-8 floor binds
-//               somewhere in the tile, the tile holds min-value pad frames, or it is a silent (all-zero PCM) tile that
-//               was never computed.  That fix-up runs on L2-resident lines, so HBM sees each output byte once.
+//   per-clip max / min = ordered-int red.max into the workspace (fire and forget), plus the tile's own minimum in a
+//               per-tile slot.  The few cells that can only be finished once the WHOLE clip is known -- the max-8 floor
+//               where it binds, the min-value pad of the frames beyond the kept part, silent (all-zero PCM) tiles that
+//               were never computed -- are left to `fixup_kernel`, a small second grid launched right behind this one:
+//               it looks at every tile's minimum against its clip's maximum and rewrites only the tiles that still
+//               differ from their final value (none at all for ordinary audio).  The kernel boundary is the only
+//               synchronisation between the two: no completion counters, no waiting CTAs, no fences in here.
 //   scheduling = persistent CTAs pulling tiles from an atomic counter in clip-major order, one tile ahead; the next tile's
-//               PCM travels global->shared by TMA bulk copies (mbarrier completion) under the current tile's mel phase;
-//               a CTA never waits while tiles are still unclaimed (pending tiles are ringed / parked), so the kernel is
-//               deadlock-free for any grid size.
+//               PCM travels global->shared by TMA bulk copies (mbarrier completion) under the current tile's mel phase.
+//               A CTA that runs out of tiles exits at once, and the grid behind it on the stream (programmatic dependent
+//               launch) takes its SM slot; a launch flagged WFT_LAUNCH_OVERLAP does not even wait for the grid in front of
+//               it to complete (independent batches), so consecutive batches run back to back without a tail.
 //
 // Shared memory per CTA: one 28.8 KB region time-multiplexed as
 //   [audio tile at the top] -> stage A->B exchange -> [power tile at the bottom | next audio tile at the top],
@@ -70,8 +74,7 @@ constexpr int kWinFloats = WFT_WINDOW_TABLE_LEN;                 // 400
 constexpr int kTwFloats = WFT_TWIDDLE_TABLE_LEN;                 // 880
 constexpr int kTwRow = WFT_TWIDDLE_ROW;                          // 44
 constexpr int kMelWFloats = ((WFT_MEL80_W_LEN > WFT_MEL128_W_LEN ? WFT_MEL80_W_LEN : WFT_MEL128_W_LEN) + 3) & ~3;
-constexpr int kRing = 16;         // pending-tile FIFO slots in sm_ctl (power of two)
-constexpr int kCtlInts = 120;
+constexpr int kCtlInts = 64;
 constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats + kMelWFloats) * 4 + kCtlInts * 4;
 
 static_assert(kPFloats <= kAudioBase, "power tile and prefetched audio tile must not overlap");
@@ -106,11 +109,9 @@ __host__ __device__ constexpr int mel_warp_wstride(int w) {
   return NM == 80 ? a[w] : b[w];
 }
 
-struct ClipStat {      // {max_enc, done} share one aligned 8-byte word: ld_stat reads both with a single load
+struct ClipStat {      // zeroed before the launch (0 is below every encoding)
   uint32_t max_enc;   // ordered-int encoding of max L2 = log2(mel) over ALL frames of the clip
-  uint32_t done;      // tiles of this clip whose stat atomics have been performed (and values written)
   uint32_t min_inv;   // ~encoding of min L2 over the KEPT frames (pad value of pad_or_trim)
-  uint32_t pad_;
 };
 
 struct FrontendParams {
@@ -122,7 +123,7 @@ struct FrontendParams {
   float* out;
   uint32_t* tile_counter;
   ClipStat* stats;
-  int32_t* next;        // [total_tiles] per-CTA chains of parked fix-ups
+  float* tile_min;      // [total_tiles] min L2 over the live cells of every computed tile (what fixup_kernel decides on)
   int32_t n_samples;
   int32_t n_total;      // n_samples + padding
   int32_t batch;
@@ -131,11 +132,16 @@ struct FrontendParams {
   int32_t tiles_per_clip;
   int32_t total_tiles;
   float mask_value;
-  uint32_t zero;        // always 0; gives the completion counter a data dependency the compiler cannot fold
   uint32_t tpc_magic;   // floor(2^32 / tiles_per_clip): tile -> clip by multiply-high (+ one correction step)
   int32_t vec_ok;       // `out` is 32-byte aligned and n_frames_out % 8 == 0: the mel phase may use 32-byte stores
   uint4* clean;         // self-cleaning workspace: the header + statistics of the OTHER phase, zeroed by CTA 0 for the launch
-  int32_t clean_vec;    // after this one (16-byte vectors; 0 = the host memsets before every launch)
+  int32_t clean_vec;    // after this one (16-byte vectors; 0 = zeroed by the host)
+  int32_t draw;         // != 0: masks == nullptr and the intervals are drawn in here (draw_mask_intervals)
+  int32_t draw_tparam, draw_fparam;
+  float draw_p;
+  uint64_t draw_seed, draw_clip_offset;
+  int32_t overlap;      // != 0 (WFT_LAUNCH_OVERLAP): independent of the grids in front of it on the stream -- does not wait for
+                        // them to complete, so its CTAs work in the SM slots their tails free
   int32_t chunk;        // consecutive tiles a CTA takes per claim (>= 1): neighbours share the clip, so the per-clip loads of
                         // describe_tile hit its memo and the tile counter sees 1 / chunk of the atomics
 };
@@ -147,6 +153,54 @@ __device__ __forceinline__ uint32_t enc_ordered(float f) {
 __device__ __forceinline__ float dec_ordered(uint32_t e) {
   const uint32_t b = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
   return __uint_as_float(b);
+}
+
+// ---- SpecAugment intervals drawn on the device (wft_specaug_draw / draw_masks): Philox4x32-10 keyed by the seed, counter =
+// global clip index, so the draw is a pure function of (seed, clip) -- any thread that needs a clip's intervals computes them
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t w) { return static_cast<float>(w >> 8) * 5.9604644775390625e-08f; }
+
+// torchaudio interval: width = u*param ; start = trunc(u' * (size - width)) ; end = start + trunc(width)
+__device__ __forceinline__ void interval(float u_w, float u_s, int param, int size, int& a, int& b) {
+  if (param < 1) { a = 0; b = 0; return; }
+  const float value = __fmul_rn(u_w, static_cast<float>(param));
+  const float minv = __fmul_rn(u_s, __fsub_rn(static_cast<float>(size), value));
+  a = static_cast<int>(minv);
+  b = a + static_cast<int>(value);
+}
+
+// (t0, t1, f0, f1) of one clip; `p` is the gate of data_loader.py:294-301 (block 1 of the clip's counter), block 0 the intervals
+__device__ __noinline__ int4 draw_mask_intervals(uint64_t seed, uint64_t clip_index, int n_mels, int n_frames, int tparam,
+                                                 int fparam, float p) {
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const uint32_t lo = static_cast<uint32_t>(clip_index), hi = static_cast<uint32_t>(clip_index >> 32);
+  uint32_t r[4];
+  philox4x32_10(lo, hi, 0u, 0u, k0, k1, r);
+  bool apply = p >= 1.0f;
+  if (!apply && p > 0.0f) {
+    uint32_t g[4];
+    philox4x32_10(lo, hi, 1u, 0u, k0, k1, g);
+    apply = u01(g[0]) < p;
+  }
+  int4 mk = make_int4(0, 0, 0, 0);
+  if (apply) {
+    interval(u01(r[0]), u01(r[1]), tparam, n_frames, mk.x, mk.y);
+    interval(u01(r[2]), u01(r[3]), fparam, n_mels, mk.z, mk.w);
+  }
+  return mk;
 }
 
 struct TileCoord {
@@ -231,12 +285,6 @@ __device__ __noinline__ void stage_audio_edge(PcmT* __restrict__ sm_audio, const
 __device__ __forceinline__ float pcm_as_float(float v) { return v; }
 __device__ __forceinline__ float pcm_as_float(int16_t v) { return static_cast<float>(v); }
 
-// relaxed gpu-scope read of a clip's completion counter (ordering comes from data dependencies, see publish)
-__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* addr) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(addr) : "memory");
-  return v;
-}
 __device__ __forceinline__ float fast_log2(float x) {  // x is a normal float here: plain MUFU.LG2
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -307,9 +355,6 @@ __device__ __forceinline__ int mirror_lane() {
   return t < 128 ? (lane ^ 16) : (lane < 16 ? lane : (lane ^ 8));
 }
 static_assert(kPairs == 8 && kThreads == 160, "pair_coord_a / pair_coord_b are written for 8 pairs x 20 slots");
-
-constexpr int kSilentBit = 1 << 30;   // flag carried by the tile id inside the pending ring / parked chain
-constexpr int kTileIdMask = kSilentBit - 1;
 
 constexpr float kLog10Of2 = 0.301029995663981195f;
 constexpr float kFeatScale = 0.25f * kLog10Of2;   // (log10 x + 4) / 4 == log2 x * kFeatScale + 1 (0.25 * c is exact)
@@ -456,17 +501,25 @@ __device__ __noinline__ void mel_edge(const float* __restrict__ sm_region, const
   }
 }
 
-// ---- deferred fix-up of one tile (only tiles that need it, see `tile_needs_fixup`) -----------------------------------
-// The mel phase wrote the feature with masks applied.  What may still be missing once the clip's max / min are known: the
-// floor max(feature, floor_feature(max)) and the min-value pad of the frames beyond the kept part (data/utils.py:380-404).
-// Masked cells keep the mask value.
-struct FixupArgs {
+// ---- fix-up grid: what can only be finished once the whole clip is known ---------------------------------------------
+// The front-end kernel wrote every computed cell as its final feature with the masks applied.  What may still be missing
+// once the clip's max / min are complete: the floor max(feature, floor_feature(max)) where it binds, the min-value pad of
+// the frames beyond the kept part (data/utils.py:380-404), and the constant rows of silent / pad-only tiles that were never
+// computed.  `fixup_kernel` runs right behind the front-end grid: a warp owns 32 consecutive tiles at a time, lane <-> tile
+// decides from the tile's recorded minimum whether anything is missing, and the warp rewrites the flagged tiles (in place,
+// from L2).  Ordinary full-length audio flags nothing and the grid is a few microseconds of scanning.
+struct FixupParams {
   float* out;
   const ClipStat* stats;
+  const float* tile_min;
+  const int32_t* lengths;
   const int32_t* n_valid;
   const int32_t* masks;
-  int32_t n_frames, n_frames_out, tiles_per_clip;
+  int32_t n_samples, n_total, n_frames, n_frames_out, tiles_per_clip, total_tiles;
   float mask_value;
+  int32_t draw, draw_tparam, draw_fparam;
+  float draw_p;
+  uint64_t draw_seed, draw_clip_offset;
 };
 
 __device__ __forceinline__ int kept_frames(const int32_t* n_valid, int clip, int n_frames) {
@@ -478,98 +531,136 @@ __device__ __forceinline__ int kept_frames(const int32_t* n_valid, int clip, int
   return keep;
 }
 
-// does tile (clip, t0) still differ from its final value?  tile_min = min L2 over the tile's live cells
-__device__ __forceinline__ bool tile_needs_fixup(float tile_min, uint32_t max_enc, int t0, int keep, int n_frames_out) {
-  const bool floor_binds = feature_of_l2(tile_min) < floor_feature(dec_ordered(max_enc));
-  const int hi = t0 + kTileFrames < n_frames_out ? t0 + kTileFrames : n_frames_out;
-  const bool has_pad = (t0 > keep ? t0 : keep) < hi;
-  return floor_binds || has_pad;
-}
+constexpr int kFixThreads = 128;
+constexpr int kFixWarps = kFixThreads / 32;
+constexpr int kFixTiles = 32;   // tiles per CTA: one per lane of the scan
 
+// one warp finishes one tile; `constant` = nothing was written yet (silent or pad-only tile): every kept cell is the clamp value
 template <int NM>
-__device__ __noinline__ void fixup_tile(const FixupArgs p, int tagged_tile, int clip, int tid) {
-  const bool silent = (tagged_tile & kSilentBit) != 0;   // nothing was written yet: every cell is the clamp constant
-  const int tile = tagged_tile & kTileIdMask;
+__device__ __forceinline__ void fixup_tile(const FixupParams& p, int clip, int t0, bool constant, int lane) {
   const float vsilent = feature_of_l2(silent_l2());
-  const ClipStat* st = p.stats + clip;
-  const float floorn = floor_feature(dec_ordered(__ldcg(&st->max_enc)));
-  const float padv = fmaxf(feature_of_l2(dec_ordered(~__ldcg(&st->min_inv))), floorn);
+  const ClipStat st = p.stats[clip];
+  const float floorn = floor_feature(dec_ordered(st.max_enc));
+  const float padv = fmaxf(feature_of_l2(dec_ordered(~st.min_inv)), floorn);
   const int keep = kept_frames(p.n_valid, clip, p.n_frames);
   int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
-  if (p.masks != nullptr) {
-    const int4 mk = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
+  if (p.masks != nullptr || p.draw) {
+    const int4 mk = p.masks != nullptr ? __ldg(reinterpret_cast<const int4*>(p.masks) + clip)
+                                       : draw_mask_intervals(p.draw_seed, p.draw_clip_offset + static_cast<uint64_t>(clip), NM,
+                                                             p.n_frames_out, p.draw_tparam, p.draw_fparam, p.draw_p);
     mt0 = mk.x; mt1 = mk.y; mf0 = mk.z; mf1 = mk.w;
   }
   const float mv = p.mask_value;
   const int pitch = p.n_frames_out;
   float* base = p.out + static_cast<size_t>(clip) * NM * pitch;
-  const int t0 = (tile - clip * p.tiles_per_clip) * kTileFrames;
   if ((pitch & 3) == 0) {
-    constexpr int kGroups = kTileFrames / 4;                      // float4 groups per row (4)
-    constexpr int kVec = NM * kGroups;                            // float4 groups per tile
-    constexpr int kIters = (kVec + kThreads - 1) / kThreads;      // 4 (128 mel) / 2 (80 mel)
-    const int f = t0 + ((tid & (kGroups - 1)) << 2);              // kThreads % kGroups == 0: same column group every iter
+    constexpr int kGroups = kTileFrames / 4;        // float4 groups per row (4)
+    constexpr int kRowsPerPass = 32 / kGroups;      // 8 rows per warp-wide access
+    constexpr int kBatch = 2;                       // rows in flight per lane (the kernel has to stay within 32 registers)
+    static_assert(NM % (kRowsPerPass * kBatch) == 0, "row loop");
+    const int f = t0 + ((lane & (kGroups - 1)) << 2);
     if (f >= pitch) return;
-    float4 v[kIters];
+    const bool load = !constant && f < keep;
+#pragma unroll 1
+    for (int r0 = lane / kGroups; r0 < NM; r0 += kRowsPerPass * kBatch) {
+      float4 v[kBatch];
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int row = (tid + kThreads * it) / kGroups;
-      v[it] = make_float4(vsilent, vsilent, vsilent, vsilent);
-      if (!silent && row < NM && f < keep)
-        v[it] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * pitch + f));
-    }
+      for (int it = 0; it < kBatch; ++it) {
+        const int row = r0 + kRowsPerPass * it;
+        v[it] = make_float4(vsilent, vsilent, vsilent, vsilent);
+        if (load && row < NM) v[it] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * pitch + f));
+      }
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int row = (tid + kThreads * it) / kGroups;
-      if (row < NM) {
-        const bool rowmask = row >= mf0 && row < mf1;
-        float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+      for (int it = 0; it < kBatch; ++it) {
+        const int row = r0 + kRowsPerPass * it;
+        if (row < NM) {
+          const bool rowmask = row >= mf0 && row < mf1;
+          float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int fc = f + c;
-          float r = (fc < keep) ? fmaxf(e[c], floorn) : padv;
-          if (rowmask || (fc >= mt0 && fc < mt1)) r = mv;
-          e[c] = r;
+          for (int c = 0; c < 4; ++c) {
+            const int fc = f + c;
+            float r = (fc < keep) ? fmaxf(e[c], floorn) : padv;
+            if (rowmask || (fc >= mt0 && fc < mt1)) r = mv;
+            e[c] = r;
+          }
+          *reinterpret_cast<float4*>(base + static_cast<size_t>(row) * pitch + f) = make_float4(e[0], e[1], e[2], e[3]);
         }
-        *reinterpret_cast<float4*>(base + static_cast<size_t>(row) * pitch + f) = make_float4(e[0], e[1], e[2], e[3]);
       }
     }
   } else {
-    for (int idx = tid; idx < NM * kTileFrames; idx += kThreads) {
+    for (int idx = lane; idx < NM * kTileFrames; idx += 32) {
       const int row = idx / kTileFrames;
       const int f = t0 + (idx % kTileFrames);
       if (f >= pitch) continue;
       float* ptr = base + static_cast<size_t>(row) * pitch + f;
       float r = padv;
-      if (f < keep) r = fmaxf(silent ? vsilent : __ldcg(ptr), floorn);
+      if (f < keep) r = fmaxf(constant ? vsilent : __ldcg(ptr), floorn);
       if ((row >= mf0 && row < mf1) || (f >= mt0 && f < mt1)) r = mv;
       *ptr = r;
     }
   }
 }
 
-__device__ __forceinline__ FixupArgs make_fixup_args(const FrontendParams& p) {
-  FixupArgs fx;
-  fx.out = p.out; fx.stats = p.stats; fx.n_valid = p.n_valid; fx.masks = p.masks;
-  fx.n_frames = p.n_frames; fx.n_frames_out = p.n_frames_out; fx.tiles_per_clip = p.tiles_per_clip;
-  fx.mask_value = p.mask_value;
-  return fx;
+__device__ __forceinline__ bool tile_is_silent(int t0, int len, int n_total);
+
+template <int NM>
+__global__ void __launch_bounds__(kFixThreads, 16) fixup_kernel(const FixupParams p) {   // <= 32 registers: see launch_frontend
+  // the kernel behind this one may be scheduled now (it decides itself what it has to wait for); this grid needs the
+  // front-end grid complete: its features, the clip statistics and the per-tile minima
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int lane = static_cast<int>(threadIdx.x) & 31, warp = static_cast<int>(threadIdx.x) >> 5;
+  // a WARP owns groups of 32 consecutive tiles (lane <-> tile), grid-stride: no shared memory, no barrier
+  for (int base = (static_cast<int>(blockIdx.x) * kFixWarps + warp) * kFixTiles; base < p.total_tiles;
+       base += static_cast<int>(gridDim.x) * kFixWarps * kFixTiles) {
+    const int tile = base + lane;
+    bool needs = false, constant = false;
+    int clip = 0, t0 = 0;
+    if (tile < p.total_tiles) {
+      clip = tile / p.tiles_per_clip;
+      t0 = (tile - clip * p.tiles_per_clip) * kTileFrames;
+      if (t0 < p.n_frames_out) {
+        if (t0 >= p.n_frames) {            // pad-only tile (n_frames_out > n_frames)
+          needs = constant = true;
+        } else {
+          int len = p.n_samples;
+          if (p.lengths != nullptr) {
+            const int l = __ldg(p.lengths + clip);
+            len = l < 0 ? 0 : (l < len ? l : len);
+          }
+          if (tile_is_silent(t0, len, p.n_total)) {
+            needs = constant = true;
+          } else {
+            const int keep = kept_frames(p.n_valid, clip, p.n_frames);
+            const int hi = t0 + kTileFrames < p.n_frames_out ? t0 + kTileFrames : p.n_frames_out;
+            const bool has_pad = (t0 > keep ? t0 : keep) < hi;
+            const bool floor_binds = feature_of_l2(__ldcg(p.tile_min + tile)) < floor_feature(dec_ordered(__ldcg(&p.stats[clip].max_enc)));
+            needs = has_pad || floor_binds;
+          }
+        }
+      }
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, needs);
+    const uint32_t cst = __ballot_sync(0xffffffffu, constant);
+    while (todo != 0u) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1u;
+      fixup_tile<NM>(p, __shfl_sync(0xffffffffu, clip, l), __shfl_sync(0xffffffffu, t0, l), ((cst >> l) & 1u) != 0u, lane);
+    }
+  }
 }
 
 // sm_ctl slots
 // [kCtlDesc .. +15] and [kCtlDesc + kCtlSlot .. +15] = two tile descriptors (kDesc*): the tile being worked on and the one
 // after it, swapping roles every iteration.  Every phase re-reads the few fields it needs from here instead of carrying
-// them in registers across the FFT stages.  The pending-tile FIFO (kCtlRing*, kCtlHead, kCtlCount, kCtlChain) belongs to
-// thread 0 alone.
-enum { kCtlDesc = 0, kCtlSlot = 16, kCtlRing = 32, kCtlRingClip = 48, kCtlRingMin = 64,
-       kCtlRed = 80,    // 3 floats per warp (max, kept min, live min)
-       kCtlMbar = 96,   // 8 bytes
-       kCtlMemo = 100,  // describe_tile's per-clip memo: clip, len, keep, -, mask[4]
-       kCtlHead = 108, kCtlCount = 109, kCtlChain = 110, kCtlReady = 111, kCtlReadyClip = 112, kCtlDrain = 113, kCtlDrainClip = 114,
-       kCtlChunkNext = 115,   // next tile of the chunk this CTA claimed, and how many of its tiles are still to be described
-       kCtlChunkLeft = 116,
-       kCtlPubClip = 117 };   // clip whose completion count is still owed (publish_finish), -1 = none
-static_assert(kCtlPubClip < kCtlInts && kCtlRed + 3 * kWarps <= kCtlMbar && kRing == 16, "sm_ctl layout");
+// them in registers across the FFT stages.
+enum { kCtlDesc = 0, kCtlSlot = 16,
+       kCtlRed = 32,    // 3 floats per warp (max, kept min, live min)
+       kCtlMbar = 48,   // 8 bytes
+       kCtlMemo = 52,   // describe_tile's per-clip memo: clip, len, keep, -, mask[4]
+       kCtlChunkNext = 60,   // next tile of the chunk this CTA claimed, and how many of its tiles are still to be described
+       kCtlChunkLeft = 61 };
+static_assert(kCtlChunkLeft < kCtlInts && kCtlRed + 3 * kWarps <= kCtlMbar, "sm_ctl layout");
 
 // how a tile's PCM reaches shared memory
 enum { kTileEdge = 0,      // reflection / zero extension / unaligned source: scalar staging
@@ -592,12 +683,17 @@ struct TileGeom {   // the few launch constants describe_tile needs
   int32_t n_samples, n_total, n_frames, n_frames_out, tiles_per_clip, total_tiles;
   uint32_t tpc_magic;   // floor(2^32 / tiles_per_clip)
   int32_t vec_ok;
+  int32_t draw, draw_tparam, draw_fparam;
+  float draw_p;
+  uint64_t draw_seed, draw_clip_offset;
 };
 __device__ __forceinline__ TileGeom tile_geom(const FrontendParams& q) {
   TileGeom g;
   g.pcm = q.pcm; g.lengths = q.lengths; g.n_valid = q.n_valid; g.masks = q.masks; g.clip_stride = q.clip_stride;
   g.n_samples = q.n_samples; g.n_total = q.n_total; g.n_frames = q.n_frames; g.n_frames_out = q.n_frames_out;
   g.tiles_per_clip = q.tiles_per_clip; g.total_tiles = q.total_tiles; g.tpc_magic = q.tpc_magic; g.vec_ok = q.vec_ok;
+  g.draw = q.draw; g.draw_tparam = q.draw_tparam; g.draw_fparam = q.draw_fparam; g.draw_p = q.draw_p;
+  g.draw_seed = q.draw_seed; g.draw_clip_offset = q.draw_clip_offset;
   return g;
 }
 
@@ -626,6 +722,8 @@ __device__ __forceinline__ void describe_tile(const TileGeom p, int t, int* __re
       }
       int4 m = make_int4(0, 0, 0, 0);
       if (p.masks != nullptr) m = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
+      else if (p.draw) m = draw_mask_intervals(p.draw_seed, p.draw_clip_offset + static_cast<uint64_t>(clip), NM, p.n_frames_out,
+                                               p.draw_tparam, p.draw_fparam, p.draw_p);
       memo[0] = clip; memo[1] = len; memo[2] = kp;
       *reinterpret_cast<int4*>(memo + 4) = m;
     }
@@ -654,23 +752,6 @@ __device__ __forceinline__ void describe_tile(const TileGeom p, int t, int* __re
   *reinterpret_cast<int4*>(slot + 4) = make_int4(static_cast<int>(off & 0xffffffffll), static_cast<int>(off >> 32), flags, keep);
   *reinterpret_cast<int4*>(slot + 8) = mk;
   *reinterpret_cast<int2*>(slot + 12) = make_int2(static_cast<int>(out_off & 0xffffffffll), static_cast<int>(out_off >> 32));
-}
-
-// One 8-byte snapshot {max_enc, done} of a clip's statistics.  A naturally aligned 64-bit load is single-copy atomic, and the
-// publisher performs its atomicMax on max_enc before the (data dependent) atomicAdd on done, so a snapshot whose `done` is
-// complete carries the clip's final maximum.  Relaxed on purpose: it is issued in the power phase and looked at after the
-// mel phase, and nothing waits for it in between (an acquire load here stalled thread 0 -- and with it a CTA barrier -- for
-// a full L2 round trip per tile).  Whoever goes on to READ other data of the clip (the fix-up) does ld_acquire first.
-__device__ __forceinline__ uint2 ld_stat(const ClipStat* st) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(st) : "memory");
-  return make_uint2(static_cast<uint32_t>(v), static_cast<uint32_t>(v >> 32));   // x = max_enc, y = done
-}
-// acquire read of a clip's completion counter: pairs with the publisher's dependent atomics
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* addr) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(addr) : "memory");
-  return v;
 }
 
 // development build only (-DWFT_TIMELINE): lane 0 of every warp stamps %clock at 13 points of its first kTlIters tile
@@ -733,17 +814,16 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   uint64_t* audio_bar = reinterpret_cast<uint64_t*>(sm_ctl + kCtlMbar);  // completion of the audio tile's bulk copies
   // Programmatic dependent launch: everything above (7.4 KB of tables into shared memory) may overlap the tail of the
   // previous kernel on the stream; its results and the workspace may only be touched from here on.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  // the other phase's counters belong to the launch BEFORE this one (complete: see above) and to the one AFTER it (not
-  // started: stream order): zeroing them here needs no fence and replaces a memset launch per call
+  // The grid behind this one on the stream (the fix-up grid) may be scheduled as soon as SM slots free up.  An independent
+  // launch (p.overlap) never looks at what the grids in front of it produced and starts working at once.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!p.overlap) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // self-cleaning modes: the other phase's counters belong to the call BEFORE this one (complete: see above) and to the
+  // one AFTER it (not started: it waits for this grid): zeroing them here needs no fence and replaces a memset per call
   if (blockIdx.x == 0)
     for (int i = tid; i < p.clean_vec; i += kThreads) p.clean[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     sm_ctl[kCtlMemo] = -1;
-    sm_ctl[kCtlHead] = 0;
-    sm_ctl[kCtlCount] = 0;
-    sm_ctl[kCtlChain] = -1;
-    sm_ctl[kCtlPubClip] = -1;
     mbar_init(audio_bar, kWarps);   // one arrive.expect_tx per warp and tile (prefetch_audio_part)
     const int first = static_cast<int>(atomicAdd(p.tile_counter, static_cast<uint32_t>(p.chunk)));
     sm_ctl[kCtlChunkNext] = first + 1;
@@ -756,16 +836,12 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     const long long off = (static_cast<long long>(sm_ctl[kCtlDesc + kDescPcmHi]) << 32) | static_cast<unsigned int>(sm_ctl[kCtlDesc + kDescPcmLo]);
     prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
   }
-  // publication state of warp 0: lanes 0 / 1 hold what their atomicMax on the clip's max / min returned for the tile
-  // just finished; the completion count that depends on both is added one stage later (publish_finish)
-  uint32_t pub_dep = 0u;
   // loop state in ONE register: bit 4 (kCtlSlot) = descriptor slot of the CURRENT tile, bit 0 = parity of the audio mbarrier
   int lstate = 0;
 
   // mel phase role of this thread (fixed for the whole launch): row | start_bin << 8 | first_frame << 16 | weight_offset << 20
   // (kept packed in ONE register across the FFT stages; unpacked again in every mel phase)
   const uint32_t mel_desc = (NM == 128 ? g_mel128_thread : g_mel80_thread)[tid];
-  const uint32_t tiles_per_clip_u = static_cast<uint32_t>(p.tiles_per_clip);
 
 #ifdef WFT_TIMELINE
   int tl_iter = -1;
@@ -787,27 +863,12 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     sm_ctl[kCtlChunkNext] = t_ + 1;                                                                  \
     describe_tile<NM, PcmT>(tile_geom(p), t_, NDESC, sm_ctl + kCtlMemo);                             \
   } while (0)
-    // warp 0, lanes 0 / 1: the completion count of the tile published one stage ago, now that both atomics have returned
-    // (true data dependency through p.zero: no fence, nobody waited for them)
-#define PUBLISH_FINISH()                                                                             \
-  do {                                                                                               \
-    const uint32_t dep_ = pub_dep | __shfl_sync(0x3u, pub_dep, 1);                                   \
-    if (lane == 0) {   /* kCtlPubClip is lane 0's alone (racecheck: no second reader) */               \
-      const int pc_ = sm_ctl[kCtlPubClip];                                                           \
-      if (pc_ >= 0) {                                                                                \
-        atomicAdd(&p.stats[pc_].done, 1u + (dep_ & p.zero));                                         \
-        sm_ctl[kCtlPubClip] = -1;                                                                    \
-      }                                                                                              \
-    }                                                                                                \
-  } while (0)
     const int4 d_top = DESC4;
     if (d_top.x >= p.total_tiles) break;
     WFT_TL(0);
     // claim the tile AFTER this one now; the answer is consumed two barriers later (latency hidden by stage A)
     int nxt_claim = 0;
     if (tid == 0 && sm_ctl[kCtlChunkLeft] == 0) nxt_claim = static_cast<int>(atomicAdd(p.tile_counter, static_cast<uint32_t>(p.chunk)));
-    // thread 0: (max, done) of the clips of the two oldest pending tiles, sampled early, looked at after the mel phase
-    uint2 seen0 = make_uint2(0u, 0u), seen1 = make_uint2(0u, 0u);   // x = max_enc, y = done
 
     if (d_top.z < p.n_frames && d_top.w != kTileSilent && d_top.w != kTileSilentRest) {
       // stage 0 ---------------------------------------------------------------------------------------------
@@ -864,7 +925,6 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         }
       }
       WFT_TL(15);
-      if (warp == 0 && lane < 2) PUBLISH_FINISH();
       if (tid == 0) DESCRIBE_NEXT();
       WFT_TL(4);
       __syncthreads();
@@ -907,11 +967,6 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
           WFT_TL(13);
           prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
           WFT_TL(14);
-        }
-        if (tid == 0) {
-          const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
-          if (n > 0) seen0 = ld_stat(p.stats + sm_ctl[kCtlRingClip + head]);
-          if (n > 1) seen1 = ld_stat(p.stats + sm_ctl[kCtlRingClip + ((head + 1) & (kRing - 1))]);
         }
 
         // power tile [bin][frame]: the pair's two frames are neighbours, one 8-byte store per bin
@@ -982,17 +1037,11 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       // nothing to compute: a pad-only tile (n_frames_out > n_frames) or a silent tile (all-zero PCM: every mel value is
       // the 1e-10 clamp, so only its statistics are recorded here and the fix-up later writes the constant rows)
       __syncthreads();  // the previous tile's last readers of the other descriptor slot are done
-      if (warp == 0 && lane < 2) PUBLISH_FINISH();
       if (tid == 0) DESCRIBE_NEXT();
       __syncthreads();
       if (lane == 0 && NDESC[kDescKind] == kTileInterior) {
         const long long off = (static_cast<long long>(NDESC[kDescPcmHi]) << 32) | static_cast<unsigned int>(NDESC[kDescPcmLo]);
         prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
-      }
-      if (tid == 0) {
-        const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
-        if (n > 0) seen0 = ld_stat(p.stats + sm_ctl[kCtlRingClip + head]);
-        if (n > 1) seen1 = ld_stat(p.stats + sm_ctl[kCtlRingClip + ((head + 1) & (kRing - 1))]);
       }
       if (lane == 0) {
         const int clip = d_top.y, t0 = d_top.z, kind = d_top.w;   // (short path: the loop-top read is still in registers)
@@ -1006,47 +1055,13 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       }
     }
 
-    // thread 0 looks at the (up to) two oldest pending tiles: a tile whose clip is complete either needs the fix-up (the
-    // floor binds or it carries pad frames) or is already final and simply leaves the FIFO; one fix-up per iteration
-    if (tid == 0) {
-      const int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead];
-      int ready = -1, ready_clip = 0, pops = 0;
-      if (n > 0 && seen0.y >= tiles_per_clip_u) {
-        const int e = sm_ctl[kCtlRing + head], ec = sm_ctl[kCtlRingClip + head];
-        pops = 1;
-        if ((e & kSilentBit) != 0 ||
-            tile_needs_fixup(__int_as_float(sm_ctl[kCtlRingMin + head]), seen0.x, ((e & kTileIdMask) - ec * p.tiles_per_clip) * kTileFrames,
-                             kept_frames(p.n_valid, ec, p.n_frames), p.n_frames_out)) {
-          ready = e;
-          ready_clip = ec;
-        } else if (n > 1 && seen1.y >= tiles_per_clip_u) {
-          const int h1 = (head + 1) & (kRing - 1);
-          const int e1 = sm_ctl[kCtlRing + h1], ec1 = sm_ctl[kCtlRingClip + h1];
-          pops = 2;
-          if ((e1 & kSilentBit) != 0 ||
-              tile_needs_fixup(__int_as_float(sm_ctl[kCtlRingMin + h1]), seen1.x, ((e1 & kTileIdMask) - ec1 * p.tiles_per_clip) * kTileFrames,
-                               kept_frames(p.n_valid, ec1, p.n_frames), p.n_frames_out)) {
-            ready = e1;
-            ready_clip = ec1;
-          }
-        }
-      }
-      // a fix-up reads more of the clip than the snapshot (its minimum, through L2): acquire before anybody does
-      if (ready >= 0) (void)ld_acquire(&p.stats[ready_clip].done);
-      sm_ctl[kCtlHead] = (head + pops) & (kRing - 1);
-      sm_ctl[kCtlCount] = n - pops;
-      sm_ctl[kCtlReady] = ready;
-      sm_ctl[kCtlReadyClip] = ready_clip;
-    }
     WFT_TL(10);
-    __syncthreads();  // tile finished: power tile free, ready tile and per-warp max/min visible
+    __syncthreads();  // tile finished: power tile free, per-warp max / min visible
     WFT_TL(11);
 
-    // publish the tile's statistics: lane 0 / lane 1 of warp 0 issue the returning atomicMax on the clip's max / min and
-    // move on; the completion count -- which must not become visible before both -- is added with a true data dependency
-    // on their results at the next tile's describe point (PUBLISH_FINISH), when they have long returned.  No fence, and
-    // nobody waits: done in-line, this chain cost warp 0 two L2 round trips per tile in front of a CTA barrier.  The tile
-    // itself joins the pending FIFO (or is parked: a CTA never waits while tiles are unclaimed).
+    // publish the tile's statistics, fire and forget: lanes 0 / 1 of warp 0 reduce the clip's max / kept minimum into the
+    // workspace (red.max on ordered-int encodings), lane 2 records the tile's own minimum for the fix-up grid.  Nobody in
+    // this grid reads them back; the kernel boundary makes them visible to fixup_kernel.
     if (warp == 0) {
       const float* red = reinterpret_cast<const float*>(sm_ctl + kCtlRed) + 3 * (lane < kWarps ? lane : 0);
       float mx = lane < kWarps ? red[0] : -INFINITY;
@@ -1055,86 +1070,21 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       mx = warp_max(mx);
       mn_kept = warp_min(mn_kept);
       mn_live = warp_min(mn_live);
-      if (lane < 2) {
+      if (lane < 3) {
         const int4 d_pub = DESC4;
-        const int cur = d_pub.x, clip = d_pub.y;
-        ClipStat* cs = p.stats + clip;
-        const bool has = lane == 0 ? mx > -INFINITY : mn_kept < INFINITY;
-        pub_dep = 0u;
-        if (has) pub_dep = atomicMax(lane == 0 ? &cs->max_enc : &cs->min_inv, lane == 0 ? enc_ordered(mx) : ~enc_ordered(mn_kept));
-        if (lane == 0) {
-          const bool silent = (d_pub.w == kTileSilent || d_pub.w == kTileSilentRest) && d_pub.z < p.n_frames;
-          const int tagged = cur | (silent ? kSilentBit : 0);
-          const int n = sm_ctl[kCtlCount];
-          if (n < kRing) {
-            const int slot = (sm_ctl[kCtlHead] + n) & (kRing - 1);
-            sm_ctl[kCtlRing + slot] = tagged;
-            sm_ctl[kCtlRingClip + slot] = clip;
-            sm_ctl[kCtlRingMin + slot] = __float_as_int(mn_live);
-            sm_ctl[kCtlCount] = n + 1;
-          } else {
-            p.next[cur] = sm_ctl[kCtlChain];           // parked tiles are re-examined (conservatively) in the drain
-            sm_ctl[kCtlChain] = tagged;
-          }
-          sm_ctl[kCtlPubClip] = clip;
-        }
+        ClipStat* cs = p.stats + d_pub.y;
+        if (lane == 0 && mx > -INFINITY) atomicMax(&cs->max_enc, enc_ordered(mx));
+        if (lane == 1 && mn_kept < INFINITY) atomicMax(&cs->min_inv, ~enc_ordered(mn_kept));
+        if (lane == 2) p.tile_min[d_pub.x] = mn_live;
       }
-      __syncwarp();
     }
-    const int ready = sm_ctl[kCtlReady];
-    if (ready >= 0) fixup_tile<NM>(make_fixup_args(p), ready, sm_ctl[kCtlReadyClip], tid);
     WFT_TL(12);
     lstate ^= kCtlSlot;   // the next tile becomes current; its slot is rewritten only behind the tile-after-next's first barrier
   }
-  if (warp == 0 && lane < 2) PUBLISH_FINISH();   // the last tile's completion count
-  // no more tiles: the next kernel on the stream may start filling the SM slots this grid frees (it waits at its own
-  // griddepcontrol.wait until this grid has completed)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #undef DESC
 #undef NDESC
 #undef DESC4
 #undef DESCRIBE_NEXT
-#undef PUBLISH_FINISH
-
-  // drain: every tile is claimed by a running CTA now, so waiting on a clip's counter is safe
-  for (;;) {
-    __syncthreads();  // previous readers of sm_ctl are done
-    if (tid == 0) {
-      int t = -1, c = 0;
-      int n = sm_ctl[kCtlCount], head = sm_ctl[kCtlHead], chain = sm_ctl[kCtlChain];
-      for (;;) {
-        float tmin = -INFINITY;  // parked tiles lost their minimum: treat them as needing the fix-up
-        if (n > 0) {
-          t = sm_ctl[kCtlRing + head];
-          c = sm_ctl[kCtlRingClip + head];
-          tmin = __int_as_float(sm_ctl[kCtlRingMin + head]);
-          head = (head + 1) & (kRing - 1);
-          --n;
-        } else if (chain >= 0) {
-          t = chain;
-          c = (t & kTileIdMask) / p.tiles_per_clip;
-          chain = p.next[t & kTileIdMask];
-        } else {
-          t = -1;
-          break;
-        }
-        const ClipStat* st = p.stats + c;
-        while (ld_acquire(&st->done) < tiles_per_clip_u) __nanosleep(100);
-        const int tt0 = ((t & kTileIdMask) - c * p.tiles_per_clip) * kTileFrames;
-        if ((t & kSilentBit) != 0 ||
-            tile_needs_fixup(tmin, ld_relaxed(&st->max_enc), tt0, kept_frames(p.n_valid, c, p.n_frames), p.n_frames_out)) break;
-      }
-      sm_ctl[kCtlCount] = n;
-      sm_ctl[kCtlHead] = head;
-      sm_ctl[kCtlChain] = chain;
-      sm_ctl[kCtlDrain] = t;
-      sm_ctl[kCtlDrainClip] = c;
-    }
-    __syncthreads();
-    const int t = sm_ctl[kCtlDrain];
-    if (t < 0) break;
-    fixup_tile<NM>(make_fixup_args(p), t, sm_ctl[kCtlDrainClip], tid);
-  }
 }
 
 }  // namespace wft

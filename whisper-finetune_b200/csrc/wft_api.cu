@@ -16,7 +16,7 @@ namespace {
 thread_local std::string g_last_error;
 thread_local int64_t g_launches = 0;
 int g_debug_chunk = 0;      // WFT_DEBUG_CHUNK (development): force the tiles-per-claim of the fused kernel
-int g_debug_max_ctas = 0;   // wft_debug_set_max_ctas: caps the persistent grid (tests of the parked-tile / drain paths)
+int g_debug_max_ctas = 0;   // wft_debug_set_max_ctas: caps the persistent grids (results must not depend on the grid)
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -70,10 +70,12 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launc
   int ctas = 0;
   int rc = grid_for(wft::frontend_kernel<NM, PcmT>, cache, &ctas);
   if (rc != WFT_OK) return rc;
+  const int ctas_full = ctas;
   if (ctas > p.total_tiles) ctas = p.total_tiles;
   if (g_debug_max_ctas > 0 && ctas > g_debug_max_ctas) ctas = g_debug_max_ctas;
   // tiles a CTA takes per claim: at most 1/24 of its share (measured: chunks of 8 at 54 tiles per CTA cost 5 % in the tail)
   wft::FrontendParams q = p;
+  q.overlap = (launch_flags & WFT_LAUNCH_OVERLAP) ? 1 : 0;
   const int per_cta = p.total_tiles / ctas;
   q.chunk = g_debug_chunk > 0 ? g_debug_chunk : (per_cta / 24 < 1 ? 1 : (per_cta / 24 > 4 ? 4 : per_cta / 24));
   // programmatic stream serialization: this grid may be scheduled while the previous kernel on the stream drains; the
@@ -87,8 +89,33 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launc
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (launch_flags & WFT_LAUNCH_PDL) ? 1 : 0;
+  cfg.numAttrs = (launch_flags & (WFT_LAUNCH_PDL | WFT_LAUNCH_OVERLAP)) ? 1 : 0;
   WFT_CUDA(cudaLaunchKernelEx(&cfg, wft::frontend_kernel<NM, PcmT>, q));
+  ++g_launches;
+
+  // the fix-up grid right behind it: always a programmatic dependent (it waits for the front-end grid on the device), one
+  // lean CTA per SM -- 128 threads x 32 registers and no shared memory fit NEXT TO six front-end CTAs, so the blocks that
+  // sit waiting for the front-end grid (or for the tail of it, while an overlapping launch already runs) cost no SM slot
+  wft::FixupParams f{};
+  f.out = p.out; f.stats = p.stats; f.tile_min = p.tile_min; f.lengths = p.lengths; f.n_valid = p.n_valid; f.masks = p.masks;
+  f.draw = p.draw; f.draw_seed = p.draw_seed; f.draw_clip_offset = p.draw_clip_offset; f.draw_tparam = p.draw_tparam;
+  f.draw_fparam = p.draw_fparam; f.draw_p = p.draw_p;
+  f.n_samples = p.n_samples; f.n_total = p.n_total; f.n_frames = p.n_frames; f.n_frames_out = p.n_frames_out;
+  f.tiles_per_clip = p.tiles_per_clip; f.total_tiles = p.total_tiles; f.mask_value = p.mask_value;
+  const int groups = (p.total_tiles + wft::kFixTiles * wft::kFixWarps - 1) / (wft::kFixTiles * wft::kFixWarps);
+  // ragged inputs (lengths / cuts / output longer than the clip) mean many constant-fill tiles: more CTAs per SM
+  const bool heavy = p.lengths != nullptr || p.n_valid != nullptr || p.n_frames_out > p.n_frames;
+  int fix_ctas = (ctas_full / 6) * (heavy ? 4 : 1);
+  if (fix_ctas > groups) fix_ctas = groups;
+  if (g_debug_max_ctas > 0 && fix_ctas > g_debug_max_ctas) fix_ctas = g_debug_max_ctas;
+  cudaLaunchConfig_t fcfg{};
+  fcfg.gridDim = dim3(fix_ctas < 1 ? 1 : fix_ctas);
+  fcfg.blockDim = dim3(wft::kFixThreads);
+  fcfg.dynamicSmemBytes = 0;
+  fcfg.stream = stream;
+  fcfg.attrs = attr;
+  fcfg.numAttrs = 1;
+  WFT_CUDA(cudaLaunchKernelEx(&fcfg, wft::fixup_kernel<NM>, f));
   ++g_launches;
   return WFT_OK;
 }
@@ -102,8 +129,12 @@ int query_grid(int32_t* ctas) {
   return rc;
 }
 
-// workspace = two phases of {16-byte header (tile counter), ClipStat[batch]} + the parked-tile chain (one int per tile)
-size_t ws_header_bytes(int32_t batch) { return 16 + sizeof(wft::ClipStat) * static_cast<size_t>(batch); }
+// workspace = WFT_WS_PHASES headers {16 bytes (tile counter), ClipStat[batch]} (the part that has to be zero before a launch),
+// then WFT_WS_PHASES bodies {tile_min[tiles]}
+size_t ws_header_bytes(int32_t batch) { return (16 + sizeof(wft::ClipStat) * static_cast<size_t>(batch) + 15) & ~static_cast<size_t>(15); }
+size_t ws_body_bytes(int32_t /*batch*/, int64_t tiles) {
+  return (static_cast<size_t>(tiles) * sizeof(float) + 15) & ~static_cast<size_t>(15);
+}
 
 // ---- small stand-alone kernels ---------------------------------------------------------------------------
 
@@ -211,53 +242,12 @@ __global__ void mask_bsd_scalar_kernel(const ElemT* __restrict__ in, ElemT* __re
   }
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t (&o)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
-}
-
-__device__ __forceinline__ float u01(uint32_t w) { return static_cast<float>(w >> 8) * 5.9604644775390625e-08f; }
-
-// torchaudio interval: width = u*param ; start = trunc(u' * (size - width)) ; end = start + trunc(width)
-__device__ __forceinline__ void interval(float u_w, float u_s, int param, int size, int& a, int& b) {
-  if (param < 1) { a = 0; b = 0; return; }
-  const float value = __fmul_rn(u_w, static_cast<float>(param));
-  const float minv = __fmul_rn(u_s, __fsub_rn(static_cast<float>(size), value));
-  a = static_cast<int>(minv);
-  b = a + static_cast<int>(value);
-}
-
 __global__ void specaug_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_mels,
                                     int32_t n_frames, int32_t tparam, int32_t fparam, float p,
                                     int32_t* __restrict__ out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  const uint64_t idx = clip_offset + static_cast<uint64_t>(b);
-  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
-  const uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
-  uint32_t r[4];
-  philox4x32_10(lo, hi, 0u, 0u, k0, k1, r);
-  bool apply = p >= 1.0f;
-  if (!apply && p > 0.0f) {
-    uint32_t g[4];
-    philox4x32_10(lo, hi, 1u, 0u, k0, k1, g);
-    apply = u01(g[0]) < p;
-  }
-  int4 mk = make_int4(0, 0, 0, 0);
-  if (apply) {
-    interval(u01(r[0]), u01(r[1]), tparam, n_frames, mk.x, mk.y);
-    interval(u01(r[2]), u01(r[3]), fparam, n_mels, mk.z, mk.w);
-  }
-  reinterpret_cast<int4*>(out)[b] = mk;
+  reinterpret_cast<int4*>(out)[b] = wft::draw_mask_intervals(seed, clip_offset + static_cast<uint64_t>(b), n_mels, n_frames, tparam, fparam, p);
 }
 
 
@@ -273,15 +263,15 @@ __global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32
   bool apply = p >= 1.0f;
   if (!apply && p > 0.0f) {
     uint32_t g[4];
-    philox4x32_10(lo, hi, 1u, 0u, k0, k1, g);
-    apply = u01(g[0]) < p;
+    wft::philox4x32_10(lo, hi, 1u, 0u, k0, k1, g);
+    apply = wft::u01(g[0]) < p;
   }
   int2 w = make_int2(-1, 0);   // "no warp": the warp kernels copy such a clip
   if (apply && W > 0 && n_frames > 2 * W) {
     uint32_t r[4];
-    philox4x32_10(lo, hi, 2u, 0u, k0, k1, r);
-    w.x = W + static_cast<int>(__fmul_rn(u01(r[0]), static_cast<float>(n_frames - 2 * W)));
-    w.y = -W + static_cast<int>(__fmul_rn(u01(r[1]), static_cast<float>(2 * W)));
+    wft::philox4x32_10(lo, hi, 2u, 0u, k0, k1, r);
+    w.x = W + static_cast<int>(__fmul_rn(wft::u01(r[0]), static_cast<float>(n_frames - 2 * W)));
+    w.y = -W + static_cast<int>(__fmul_rn(wft::u01(r[1]), static_cast<float>(2 * W)));
   }
   reinterpret_cast<int2*>(out)[b] = w;
 }
@@ -474,10 +464,8 @@ int wft_frontend_workspace_bytes(int32_t batch, int32_t n_samples_total, int32_t
   const int64_t n_frames = n_samples_total / WFT_HOP_LENGTH;
   const int64_t span = n_frames_out > n_frames ? n_frames_out : n_frames;
   const int64_t tiles = (span + wft::kTileFrames - 1) / wft::kTileFrames * batch;
-  if (tiles < 1 || tiles >= wft::kSilentBit) return fail(WFT_ERR_INVALID, "batch x frames out of range (tile ids must stay below 2^30)");
-  // two phases of counters, the parked-tile chain, and [batch, 4] int32 for intervals drawn inside the call
-  size_t b = 2 * ws_header_bytes(batch) + ((static_cast<size_t>(tiles) * sizeof(int32_t) + 15) & ~static_cast<size_t>(15)) +
-             static_cast<size_t>(batch) * 16;
+  if (tiles < 1 || tiles >= (int64_t(1) << 30)) return fail(WFT_ERR_INVALID, "batch x frames out of range (tile ids must stay below 2^30)");
+  size_t b = WFT_WS_PHASES * (ws_header_bytes(batch) + ws_body_bytes(batch, tiles));
   *bytes = (b + 255) & ~static_cast<size_t>(255);
   return WFT_OK;
 }
@@ -522,18 +510,26 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
   p.n_valid = a->n_valid_frames;
   p.masks = a->mask_params;
   p.out = a->out;
-  if (a->workspace_mode < WFT_WS_MEMSET || a->workspace_mode > WFT_WS_PHASE_B)
-    return fail(WFT_ERR_INVALID, "workspace_mode must be WFT_WS_MEMSET, WFT_WS_PHASE_A or WFT_WS_PHASE_B");
+  const int mode = a->workspace_mode;
+  const bool ring = mode >= WFT_WS_RING && mode < WFT_WS_RING + WFT_WS_PHASES;
+  if (!ring && (mode < WFT_WS_MEMSET || mode > WFT_WS_PHASE_B))
+    return fail(WFT_ERR_INVALID, "workspace_mode must be WFT_WS_MEMSET, WFT_WS_PHASE_A, WFT_WS_PHASE_B or WFT_WS_RING + k");
+  if ((a->launch_flags & WFT_LAUNCH_OVERLAP) != 0 && !ring)
+    return fail(WFT_ERR_INVALID, "WFT_LAUNCH_OVERLAP needs workspace_mode WFT_WS_RING + k (launches in flight must not share counters)");
   const size_t hdr = ws_header_bytes(a->batch);
-  const int phase = a->workspace_mode == WFT_WS_PHASE_B ? 1 : 0;
-  uint8_t* ws = static_cast<uint8_t*>(a->workspace) + phase * hdr;
+  const int phase = ring ? mode - WFT_WS_RING : (mode == WFT_WS_PHASE_B ? 1 : 0);
+  uint8_t* wsbase = static_cast<uint8_t*>(a->workspace);
+  uint8_t* ws = wsbase + phase * hdr;
   p.tile_counter = reinterpret_cast<uint32_t*>(ws);
   p.stats = reinterpret_cast<wft::ClipStat*>(ws + 16);
-  p.next = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(a->workspace) + 2 * hdr);
+  const int32_t span0 = n_frames_out > n_frames ? n_frames_out : n_frames;
+  const int64_t tiles0 = static_cast<int64_t>((span0 + wft::kTileFrames - 1) / wft::kTileFrames) * a->batch;
+  uint8_t* body = wsbase + WFT_WS_PHASES * hdr + phase * ws_body_bytes(a->batch, tiles0);
+  p.tile_min = reinterpret_cast<float*>(body);
   p.clean = nullptr;
   p.clean_vec = 0;
-  if (a->workspace_mode != WFT_WS_MEMSET) {   // self-cleaning: this launch zeroes the other phase for the next one
-    p.clean = reinterpret_cast<uint4*>(static_cast<uint8_t*>(a->workspace) + (1 - phase) * hdr);
+  if (mode == WFT_WS_PHASE_A || mode == WFT_WS_PHASE_B) {   // self-cleaning: this launch zeroes the other phase for the next one
+    p.clean = reinterpret_cast<uint4*>(wsbase + (1 - phase) * hdr);
     p.clean_vec = static_cast<int32_t>(hdr / 16);
   }
   p.n_samples = a->n_samples;
@@ -545,27 +541,29 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
   p.tiles_per_clip = (span + wft::kTileFrames - 1) / wft::kTileFrames;
   p.total_tiles = p.tiles_per_clip * a->batch;
   p.mask_value = a->mask_value;
-  p.zero = 0u;
   const uint64_t magic = (uint64_t(1) << 32) / static_cast<uint64_t>(p.tiles_per_clip);
   p.tpc_magic = magic > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(magic);
   p.vec_ok = ((reinterpret_cast<uintptr_t>(a->out) & 31) == 0 && (n_frames_out & 7) == 0) ? 1 : 0;
 
-  if (a->workspace_mode == WFT_WS_MEMSET) WFT_CUDA(cudaMemsetAsync(ws, 0, hdr, stream));
-  if (a->draw_masks != 0) {
-    const size_t chain = (static_cast<size_t>(p.total_tiles) * sizeof(int32_t) + 15) & ~static_cast<size_t>(15);
-    int32_t* drawn = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(a->workspace) + 2 * hdr + chain);
-    specaug_draw_kernel<<<(a->batch + 127) / 128, 128, 0, stream>>>(a->draw_seed, a->draw_clip_offset, a->batch, a->n_mels, n_frames_out,
-                                                                   a->draw_time_mask_param, a->draw_freq_mask_param, a->draw_p, drawn);
-    ++g_launches;
-    WFT_CUDA(cudaGetLastError());
-    p.masks = drawn;
+  // MEMSET: this call's counters; RING: all phases at once when the ring wraps (a plain stream operation, i.e. the one
+  // point per WFT_WS_PHASES calls where everything in front has to be complete)
+  if (mode == WFT_WS_MEMSET) WFT_CUDA(cudaMemsetAsync(ws, 0, hdr, stream));
+  if (ring && phase == 0) WFT_CUDA(cudaMemsetAsync(wsbase, 0, WFT_WS_PHASES * hdr, stream));
+  int launch_flags = a->launch_flags;
+  if (a->draw_masks != 0) {   // the intervals are a pure function of (seed, clip index): every CTA draws what it needs itself
+    p.draw = 1;
+    p.draw_seed = a->draw_seed;
+    p.draw_clip_offset = a->draw_clip_offset;
+    p.draw_tparam = a->draw_time_mask_param;
+    p.draw_fparam = a->draw_freq_mask_param;
+    p.draw_p = a->draw_p;
   }
   if (a->n_mels == 128) {
-    return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<128, float>(p, stream, a->launch_flags)
-                                       : launch_frontend<128, int16_t>(p, stream, a->launch_flags);
+    return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<128, float>(p, stream, launch_flags)
+                                       : launch_frontend<128, int16_t>(p, stream, launch_flags);
   }
-  return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<80, float>(p, stream, a->launch_flags)
-                                     : launch_frontend<80, int16_t>(p, stream, a->launch_flags);
+  return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<80, float>(p, stream, launch_flags)
+                                     : launch_frontend<80, int16_t>(p, stream, launch_flags);
 }
 
 int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t* threads, int32_t* smem_bytes) {

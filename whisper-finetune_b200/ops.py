@@ -30,27 +30,39 @@ from torch import Tensor
 from . import _lib
 
 HOP_LENGTH = 160
+_LAST_CALL = {}   # (device, stream) -> byte ranges the last front-end call enqueued there reads / writes
 _ELEM_BYTES = {torch.float32: 4, torch.float16: 2, torch.bfloat16: 2}
 
 
 def _stream(device: torch.device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Stream handle for any op OTHER than the front end: also forgets the stream's last front-end call, so that the next one
+    is launched the ordinary way (an overlapping launch may only follow another front-end launch directly)."""
+    st = torch.cuda.current_stream(device).cuda_stream
+    _LAST_CALL.pop((device.index, st), None)
+    return st
 
 
 def _ptr(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
-# Self-cleaning workspaces (include/wft.h, enum wft_workspace_mode): one per (device, stream, size), zeroed once; every launch
-# flips the phase, so no memset is enqueued and consecutive launches on a stream chain kernel to kernel.  A workspace is
-# only ever used on the stream it was created for (stream order is what makes the phase hand-over safe).
+# Workspaces (include/wft.h, enum wft_workspace_mode): one per (device, stream, batch, size), used in WFT_WS_RING mode -- the
+# library keeps WFT_WS_PHASES copies of its counters in it, every launch takes the next copy and the launch that wraps the ring
+# zeroes all of them with one memset, so consecutive launches on a stream chain kernel to kernel.  A workspace is only ever
+# used on the stream it was created for.
 _WORKSPACES = {}
 _MAX_WORKSPACES = 64
 
 
 # Programmatic dependent launch of the fused kernel (include/wft.h, WFT_LAUNCH_PDL): on by default -- a training loop feeds
-# one stream.  Code that keeps several streams of this GPU busy at once (bench.py's two-batches-in-flight loop) turns it off.
+# one stream.  Code that keeps several streams of this GPU busy at once turns it off.
 _PDL = {"enabled": True}
+# Independent batches (WFT_LAUNCH_OVERLAP): off by default.  A caller that enqueues NOTHING but front-end calls on the stream
+# between two batches (a loader that keeps several PCM batches resident, bench.py) switches it on: a launch then does not
+# wait for the previous batch's grids to complete and fills the SM slots its tail frees.  The buffers of consecutive calls
+# are still checked here -- a call that touches anything the previous call wrote (or writes anything it read) is launched
+# the ordinary way.
+_OVERLAP = {"enabled": False}
 
 
 def set_programmatic_launch(enabled: bool) -> bool:
@@ -60,18 +72,35 @@ def set_programmatic_launch(enabled: bool) -> bool:
     return old
 
 
+def set_overlap(enabled: bool) -> bool:
+    """Declare consecutive front-end calls of a stream independent batches (see ``_OVERLAP``) -> the previous setting."""
+    old = _OVERLAP["enabled"]
+    _OVERLAP["enabled"] = bool(enabled)
+    return old
+
+
 def _workspace(dev: torch.device, stream: int, batch: int, nbytes: int):
-    # the layout inside a workspace depends on the batch size (two phases of 16 + 16 * batch bytes, then the tile chain), so
-    # a workspace is only ever re-used for the same (batch, size): another batch would find its counters where this one's
-    # tile chain left data
+    # the layout inside a workspace depends on the batch size, so a workspace is only ever re-used for the same (batch, size)
     key = (dev.index, stream, batch, nbytes)
     ent = _WORKSPACES.get(key)
     if ent is None:
         if len(_WORKSPACES) >= _MAX_WORKSPACES:
             _WORKSPACES.pop(next(iter(_WORKSPACES)))   # freed stream-ordered by the caching allocator
-        ent = _WORKSPACES[key] = [torch.zeros(nbytes, dtype=torch.uint8, device=dev), 0]
+        ent = _WORKSPACES[key] = [torch.empty(nbytes, dtype=torch.uint8, device=dev), -1]
     ent[1] += 1
-    return key, ent[0], _lib.WFT_WS_PHASE_A if ent[1] & 1 else _lib.WFT_WS_PHASE_B
+    return key, ent, _lib.WFT_WS_RING + ent[1] % _lib.WFT_WS_PHASES
+
+
+def _span(t: Optional[Tensor]):
+    """Byte range [lo, hi) a (non-overlapping, positively strided) tensor touches."""
+    if t is None or t.numel() == 0:
+        return None
+    lo = t.data_ptr()
+    return (lo, lo + (1 + sum((n - 1) * st for n, st in zip(t.shape, t.stride()))) * t.element_size())
+
+
+def _disjoint(a, b) -> bool:
+    return a is None or b is None or a[1] <= b[0] or b[1] <= a[0]
 
 
 def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[Tensor], n_frames_out: int,
@@ -84,8 +113,19 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
     with torch.cuda.device(dev):
         need = ctypes.c_size_t(0)
         _lib.check(lib.wft_frontend_workspace_bytes(B, N + padding, out.shape[2], ctypes.byref(need)))
-        stream = _stream(dev)
-        key, ws, mode = _workspace(dev, stream, B, need.value)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        key, ent, mode = _workspace(dev, stream, B, need.value)
+        ws = ent[0]
+        flags = _lib.WFT_LAUNCH_PDL if _PDL["enabled"] else 0
+        reads = [_span(t) for t in (pcm, lengths, n_valid_frames, mask_params)]
+        writes = _span(out)
+        prev = _LAST_CALL.get((dev.index, stream))
+        if _OVERLAP["enabled"] and prev is not None:
+            prev_reads, prev_writes = prev
+            if (_disjoint(writes, prev_writes) and all(_disjoint(writes, r) for r in prev_reads)
+                    and all(_disjoint(r, prev_writes) for r in reads)):
+                flags |= _lib.WFT_LAUNCH_OVERLAP
+        _LAST_CALL[(dev.index, stream)] = (reads, writes)
         args = _lib.FrontendArgs(
             pcm=pcm.data_ptr(),
             pcm_dtype=_lib.WFT_PCM_F32 if pcm.dtype == torch.float32 else _lib.WFT_PCM_I16,
@@ -103,7 +143,7 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
             workspace=ws.data_ptr(),
             workspace_bytes=need.value,
             workspace_mode=mode,
-            launch_flags=_lib.WFT_LAUNCH_PDL if _PDL["enabled"] else 0,
+            launch_flags=flags,
         )
         if draw is not None:
             args.draw_masks = 1
@@ -112,7 +152,7 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
             args.draw_time_mask_param, args.draw_freq_mask_param, args.draw_p = int(draw[2]), int(draw[3]), float(draw[4])
         rc = lib.wft_frontend_forward(ctypes.byref(args), stream)
         if rc != 0:
-            _WORKSPACES.pop(key, None)   # a launch that did not happen leaves the phase bookkeeping undefined
+            _WORKSPACES.pop(key, None)   # a launch that did not happen leaves the ring bookkeeping undefined
         _lib.check(rc)
 
 
