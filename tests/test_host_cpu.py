@@ -100,9 +100,11 @@ def test_generated_tables_are_current(wft):
         bank = wft.slaney_mel_bank(n_mels)
         plan = gen.mel_plan(bank)
         gen.simulate(bank, plan)
-        assert len(plan["thread"]) == 160 and sorted({t[0] for t in plan["thread"]}) == list(range(n_mels))
-        assert all(1 <= t[1] and t[1] + plan["warp_t"][i // 32] - 1 <= 199 for i, t in enumerate(plan["thread"]))
-        assert all(t[2] + plan["warp_nf"][i // 32] <= 16 for i, t in enumerate(plan["thread"]))
+        rows = sorted({row for passes in plan["thread"] for row, _ in passes})
+        assert len(plan["thread"]) == 160 and rows == list(range(n_mels))
+        for i, passes in enumerate(plan["thread"]):
+            assert len(passes) == len(plan["warp_t"][i // 32]) <= 2
+            assert all(1 <= start and start + taps - 1 <= 199 for (_, start), taps in zip(passes, plan["warp_t"][i // 32]))
 
 
 @pytest.mark.parametrize("n,world,drop_last,shuffle", [(100, 4, False, True), (101, 4, True, True), (7, 8, False, True),

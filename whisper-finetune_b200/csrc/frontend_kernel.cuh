@@ -92,20 +92,23 @@ static_assert(kWinFloats % 4 == 0 && kTwFloats % 4 == 0 && WFT_MEL80_W_LEN % 4 =
 __device__ const uint32_t g_mel80_thread[kThreads] = WFT_MEL80_THREAD_INIT;
 __device__ const uint32_t g_mel128_thread[kThreads] = WFT_MEL128_THREAD_INIT;
 
-// mel plan (gen_tables.py): warp w owns a group of rows of similar tap count; its threads run T(w) taps over NF(w) frames each
+// mel plan (gen_tables.py): a thread owns one mel row x 8 frames per PASS (lane l: row slot l % 16, frames 8 * (l / 16) ..);
+// warp w runs one or two passes, pass k with T taps; its weights start at WBASE(w) (tap j of slot i at (taps before + j) * 16 + i)
+constexpr int kMelSlots = 16;
 template <int NM>
-__host__ __device__ constexpr int mel_warp_taps(int w) {
-  constexpr int a[kWarps] = WFT_MEL80_WARP_T, b[kWarps] = WFT_MEL128_WARP_T;
+__host__ __device__ constexpr int mel_warp_passes(int w) {
+  constexpr int a[kWarps] = WFT_MEL80_WARP_PASSES, b[kWarps] = WFT_MEL128_WARP_PASSES;
   return NM == 80 ? a[w] : b[w];
 }
 template <int NM>
-__host__ __device__ constexpr int mel_warp_frames(int w) {
-  constexpr int a[kWarps] = WFT_MEL80_WARP_NF, b[kWarps] = WFT_MEL128_WARP_NF;
-  return NM == 80 ? a[w] : b[w];
+__host__ __device__ constexpr int mel_warp_taps(int w, int pass) {
+  constexpr int a0[kWarps] = WFT_MEL80_WARP_T0, a1[kWarps] = WFT_MEL80_WARP_T1;
+  constexpr int b0[kWarps] = WFT_MEL128_WARP_T0, b1[kWarps] = WFT_MEL128_WARP_T1;
+  return NM == 80 ? (pass ? a1[w] : a0[w]) : (pass ? b1[w] : b0[w]);
 }
 template <int NM>
-__host__ __device__ constexpr int mel_warp_wstride(int w) {
-  constexpr int a[kWarps] = WFT_MEL80_WARP_WS, b[kWarps] = WFT_MEL128_WARP_WS;
+__host__ __device__ constexpr int mel_warp_wbase(int w) {
+  constexpr int a[kWarps] = WFT_MEL80_WARP_WBASE, b[kWarps] = WFT_MEL128_WARP_WBASE;
   return NM == 80 ? a[w] : b[w];
 }
 
@@ -459,42 +462,48 @@ template <int NM>
 __device__ __noinline__ void mel_edge(const float* __restrict__ sm_region, const float* __restrict__ sm_melw,
                                       const int* __restrict__ desc, uint32_t mel_desc, float* __restrict__ out, int n_frames,
                                       int n_frames_out, float mask_value, float* __restrict__ red) {
-  const int warp = static_cast<int>(threadIdx.x) >> 5;
-  int T = 0, NF = 0, WS = 0;
+  const int warp = static_cast<int>(threadIdx.x) >> 5, lane = static_cast<int>(threadIdx.x) & 31;
+  int passes = 1, T0 = 0, T1 = 0, wbase = 0;
 #pragma unroll
   for (int w = 0; w < kWarps; ++w)
     if (warp == w) {
-      T = mel_warp_taps<NM>(w);
-      NF = mel_warp_frames<NM>(w);
-      WS = mel_warp_wstride<NM>(w);
+      passes = mel_warp_passes<NM>(w);
+      T0 = mel_warp_taps<NM>(w, 0);
+      T1 = mel_warp_taps<NM>(w, 1);
+      wbase = mel_warp_wbase<NM>(w);
     }
-  const int row = static_cast<int>(mel_desc & 0xffu), f0 = static_cast<int>((mel_desc >> 16) & 0xfu);
-  const float* wp = sm_melw + (mel_desc >> 20);
-  const float* pk = sm_region + ((mel_desc >> 8) & 0xffu) * kPStride;
+  const int f0 = (lane >> 4) * 8;
   const int clip = desc[kDescClip], t0 = desc[kDescT0], keep = desc[kDescKeep];
-  const bool rowmask = row >= desc[kDescMask + 2] && row < desc[kDescMask + 3];
   const uint32_t live = frame_window(0, n_frames, t0), kept = frame_window(0, keep, t0),
                  store = frame_window(0, n_frames < n_frames_out ? n_frames : n_frames_out, t0),
                  tmask = frame_window(desc[kDescMask], desc[kDescMask + 1], t0);
-  float* dst = out + (static_cast<size_t>(clip) * NM + row) * n_frames_out + t0;
   float mx = -INFINITY, mn_kept = INFINITY, mn_live = INFINITY;
 #pragma unroll 1
-  for (int f = f0; f < f0 + NF; ++f) {
-    float a = 0.0f;
+  for (int ps = 0; ps < passes; ++ps) {
+    const int T = ps ? T1 : T0;
+    const int row = static_cast<int>((mel_desc >> (ps ? 15 : 0)) & 0x7fu);
+    const float* pk = sm_region + ((mel_desc >> (ps ? 22 : 7)) & 0xffu) * kPStride;
+    const float* wp = sm_melw + wbase + (ps ? T0 * kMelSlots : 0) + (lane & (kMelSlots - 1));
+    const bool rowmask = row >= desc[kDescMask + 2] && row < desc[kDescMask + 3];
+    float* dst = out + (static_cast<size_t>(clip) * NM + row) * n_frames_out + t0;
 #pragma unroll 1
-    for (int j = 0; j < T; ++j) a = fmaf(wp[j * WS], pk[j * kPStride + f], a);
-    const float l2 = fast_log2(fmaxf(a, 1e-10f));
-    if ((live >> f) & 1u) {
-      mx = fmaxf(mx, l2);
-      mn_live = fminf(mn_live, l2);
+    for (int f = f0; f < f0 + 8; ++f) {
+      float a = 0.0f;
+#pragma unroll 1
+      for (int j = 0; j < T; ++j) a = fmaf(wp[j * kMelSlots], pk[j * kPStride + f], a);
+      const float l2 = fast_log2(fmaxf(a, 1e-10f));
+      if ((live >> f) & 1u) {
+        mx = fmaxf(mx, l2);
+        mn_live = fminf(mn_live, l2);
+      }
+      if ((kept >> f) & 1u) mn_kept = fminf(mn_kept, l2);
+      if ((store >> f) & 1u) dst[f] = (rowmask || ((tmask >> f) & 1u)) ? mask_value : feature_of_l2(l2);
     }
-    if ((kept >> f) & 1u) mn_kept = fminf(mn_kept, l2);
-    if ((store >> f) & 1u) dst[f] = (rowmask || ((tmask >> f) & 1u)) ? mask_value : feature_of_l2(l2);
   }
   mx = warp_max(mx);
   mn_kept = warp_min(mn_kept);
   mn_live = warp_min(mn_live);
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     red[3 * warp] = mx;
     red[3 * warp + 1] = mn_kept;
     red[3 * warp + 2] = mn_live;
@@ -1006,22 +1015,33 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         if (flags & kFlagFast) {
           const int4 mk = *reinterpret_cast<const int4*>(desc + kDescMask);
           const int2 oo = *reinterpret_cast<const int2*>(desc + kDescOutLo);
-          const int mel_row = static_cast<int>(mel_desc & 0xffu);
-          const int mel_f0 = static_cast<int>((mel_desc >> 16) & 0xfu);
-          const float* mel_p = sm_region + ((mel_desc >> 8) & 0xffu) * kPStride + mel_f0;
-          const float* mel_w = sm_melw + (mel_desc >> 20);
-          const bool masked = (mel_row >= mk.z && mel_row < mk.w) || (flags & kFlagAllMasked) != 0;
-          const float sc = masked ? 0.0f : kFeatScale;            // masked cell: 0 * L2 + mask_value
-          const float of = masked ? p.mask_value : 1.0f;
           const long long out_off = (static_cast<long long>(oo.y) << 32) | static_cast<unsigned int>(oo.x);
-          float* dst = p.out + out_off + (mel_row * p.n_frames_out + mel_f0);
+          const int half8 = (lane >> 4) * 8;
           float mx = -INFINITY, mn = INFINITY;
-          // warp-uniform dispatch: one fully unrolled body per warp of the plan
-          if (warp == 0) mel_fast<mel_warp_taps<NM>(0), mel_warp_frames<NM>(0), mel_warp_wstride<NM>(0)>(mel_p, mel_w, sc, of, dst, mx, mn);
-          else if (warp == 1) mel_fast<mel_warp_taps<NM>(1), mel_warp_frames<NM>(1), mel_warp_wstride<NM>(1)>(mel_p, mel_w, sc, of, dst, mx, mn);
-          else if (warp == 2) mel_fast<mel_warp_taps<NM>(2), mel_warp_frames<NM>(2), mel_warp_wstride<NM>(2)>(mel_p, mel_w, sc, of, dst, mx, mn);
-          else if (warp == 3) mel_fast<mel_warp_taps<NM>(3), mel_warp_frames<NM>(3), mel_warp_wstride<NM>(3)>(mel_p, mel_w, sc, of, dst, mx, mn);
-          else mel_fast<mel_warp_taps<NM>(4), mel_warp_frames<NM>(4), mel_warp_wstride<NM>(4)>(mel_p, mel_w, sc, of, dst, mx, mn);
+          // one pass = this thread's row x 8 frames; warp-uniform dispatch, one fully unrolled body per (warp, pass) of the plan
+#define MEL_PASS(W, PS)                                                                                              \
+  do {                                                                                                               \
+    constexpr int T_ = mel_warp_taps<NM>(W, PS);                                                                     \
+    const int row_ = static_cast<int>((mel_desc >> ((PS) ? 15 : 0)) & 0x7fu);                                        \
+    const float* pk_ = sm_region + ((mel_desc >> ((PS) ? 22 : 7)) & 0xffu) * kPStride + half8;                       \
+    const float* wp_ = sm_melw + mel_warp_wbase<NM>(W) + ((PS) ? mel_warp_taps<NM>(W, 0) * kMelSlots : 0) + (lane & (kMelSlots - 1)); \
+    const bool masked_ = (row_ >= mk.z && row_ < mk.w) || (flags & kFlagAllMasked) != 0;                             \
+    const float sc_ = masked_ ? 0.0f : kFeatScale;            /* masked cell: 0 * L2 + mask_value */                  \
+    const float of_ = masked_ ? p.mask_value : 1.0f;                                                                 \
+    mel_fast<T_, 8, kMelSlots>(pk_, wp_, sc_, of_, p.out + out_off + (row_ * p.n_frames_out + half8), mx, mn);       \
+  } while (0)
+#define MEL_WARP(W)                                           \
+  do {                                                        \
+    MEL_PASS(W, 0);                                           \
+    if constexpr (mel_warp_passes<NM>(W) > 1) MEL_PASS(W, 1); \
+  } while (0)
+          if (warp == 0) MEL_WARP(0);
+          else if (warp == 1) MEL_WARP(1);
+          else if (warp == 2) MEL_WARP(2);
+          else if (warp == 3) MEL_WARP(3);
+          else MEL_WARP(4);
+#undef MEL_WARP
+#undef MEL_PASS
           mx = warp_max(mx);
           mn = warp_min(mn);
           if (lane == 0) {

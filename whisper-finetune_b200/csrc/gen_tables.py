@@ -98,14 +98,16 @@ def row_support(bank: np.ndarray):
 
 
 # ---- mel phase plan -------------------------------------------------------------------------------------------------
-# A thread owns ONE mel row for NF consecutive frames of the 16-frame tile, NF in {16, 8, 4} uniform over its warp (a row is
-# then shared by 16 / NF threads of that warp).  Rows are sorted by tap count and dealt to the five warps in consecutive
-# groups, so a warp's fully unrolled tap loop runs T = (largest tap count in the group) taps; the (NF per warp) assignment
-# is the one that minimises the slowest warp (every phase ends on a CTA barrier), found by enumeration.
-def _warp_cost(taps, nf):
-    """Issue-slot estimate of one thread: per tap NF/4 LDS.128 + NF/2 FFMA2 + 1 weight load; per frame clamp, lg2, fma and
-    its share of the running max / min; two stores and fixed overhead."""
-    return taps * (0.75 * nf + 1) + 4.0 * nf + 24
+# A thread owns ONE mel row for 8 consecutive frames of the 16-frame tile: lane l of a warp plays row slot l % 16 and frame
+# half l / 16, so lanes l and l + 16 write the two 32-byte halves of the SAME 64-byte row segment and a warp-wide 32-byte
+# store touches 16 lines instead of 32 (the L1 charges a store per line it touches: ncu counted 16 wavefronts for a store
+# whose lanes sit on 32 lines and 8 for one on 16).  The rows are sorted by tap count and cut into groups of 16; a warp
+# takes one or two groups (its "passes"), each with its own fully unrolled tap loop of T = (largest tap count in the group)
+# taps.  The assignment of groups to warps minimises the slowest warp (every phase ends on a CTA barrier).
+def _group_cost(taps):
+    """Issue-slot estimate of one pass of one thread: per tap 2 LDS.128 + 4 FFMA2 + 1 weight load; per frame clamp, lg2, fma and
+    its share of the running max / min; the store and fixed overhead."""
+    return taps * 7.0 + 4.0 * 8 + 24
 
 
 def _conflict_cost(lanes):
@@ -123,8 +125,9 @@ def _conflict_cost(lanes):
 
 
 def _lanes_of(order, start, nf):
-    """lane -> (row, f0) for a warp whose rows are `order` (32 * nf / 16 of them)."""
+    """lane -> (row, f0) for one pass: 16 rows, lane l plays row slot l % 16 and frames 8 * (l / 16) .."""
     n = len(order)
+    assert n == 16 and nf == 8
     return [(order[lane % n], nf * (lane // n)) for lane in range(32)]
 
 
@@ -182,56 +185,72 @@ def _order_rows(rows, start_range, nf):
 def mel_plan(bank: np.ndarray):
     """Thread-level plan of the mel phase.
 
-    -> dict(weights=[float32...], thread=[(row, start_bin, f0, w_ofs)] * 160, warp_t=[taps of warp w],
-            warp_nf=[frames per thread of warp w], warp_ws=[weight stride of warp w], conflicts=int)
+    -> dict(weights=[float32...], thread=[[(row, start_bin) per pass] * 160], warp_t=[[taps per pass] per warp],
+            warp_wbase=[weight offset of warp w], conflicts=int)
+    Weight of (warp w, pass p, tap j, row slot i) = weights[wbase[w] + (sum of the taps of the earlier passes + j) * 16 + i].
     """
     import itertools
 
     n_mels = bank.shape[0]
+    assert n_mels % 16 == 0
     supp = row_support(bank)
     ntaps = [supp[m][1] - supp[m][0] + 1 for m in range(n_mels)]
     by_taps = sorted(range(n_mels), key=lambda m: (ntaps[m], m))
+    groups = [by_taps[g : g + 16] for g in range(0, n_mels, 16)]
+    gt = [max(ntaps[m] for m in rows) for rows in groups]
+    n_groups = len(groups)
+    assert N_WARPS <= n_groups <= 2 * N_WARPS
+    # choose which groups share a warp: n_groups - N_WARPS warps take two groups
     best = None
-    for nfs in itertools.product((16, 8, 4), repeat=N_WARPS):
-        if list(nfs) != sorted(nfs, reverse=True):   # cheap rows first: they take the wide (16-frame) slots
+    n_double = n_groups - N_WARPS
+    idx = list(range(n_groups))
+    for pairs in itertools.combinations(itertools.combinations(idx, 2), n_double):
+        used = [g for pr in pairs for g in pr]
+        if len(set(used)) != len(used):
             continue
-        counts = [32 * nf // 16 for nf in nfs]
-        if sum(counts) != n_mels:
-            continue
-        pos, costs, groups = 0, [], []
-        for nf, c in zip(nfs, counts):
-            rows = by_taps[pos : pos + c]
-            pos += c
-            groups.append(rows)
-            costs.append(_warp_cost(max(ntaps[m] for m in rows), nf))
-        key = (max(costs), sum(costs))
+        singles = [g for g in idx if g not in used]
+        assign = [list(pr) for pr in pairs] + [[g] for g in singles]
+        costs = [sum(_group_cost(gt[g]) for g in a) for a in assign]
+        key = (max(costs), sum(c * c for c in costs))
         if best is None or key < best[0]:
-            best = (key, nfs, groups)
-    assert best is not None, "no (frames per thread) assignment covers all rows"
-    _, nfs, groups = best
-    weights, thread, warp_t, warp_ws = [], [], [], []
+            best = (key, assign)
+    _, assign = best
+    assign.sort(key=lambda a: (-len(a), a))   # two-pass warps first (warp-uniform dispatch in the kernel)
+    weights, thread, warp_t, warp_wbase = [], [], [], []
     conflicts = 0
-    for nf, rows in zip(nfs, groups):
-        taps = max(ntaps[m] for m in rows)
-        # the padded window [start, start + taps) must cover the support and stay on bins 1..199 (rewritten every
-        # tile, always finite); whatever freedom is left goes into avoiding bank conflicts
-        start_range = {m: (max(1, supp[m][1] - taps + 1), min(supp[m][0], 200 - taps)) for m in rows}
-        assert all(lo <= hi for lo, hi in start_range.values())
-        order, start_of, cost = _order_rows(rows, start_range, nf)
-        conflicts += cost
-        base = len(weights)
-        n = len(order)
-        for j in range(taps):
-            for m in order:
-                # 0.25 * bank weight: the packed two-frame FFT yields 4 |X|^2 (exact scaling)
-                weights.append(np.float32(bank[m, start_of[m] + j]) * np.float32(0.25))
-        for lane in range(32):
-            m = order[lane % n]
-            thread.append((m, start_of[m], nf * (lane // n), base + lane % n))
-        warp_t.append(taps)
-        warp_ws.append(n)
+    for a in assign:
+        warp_wbase.append(len(weights))
+        lanes = [[] for _ in range(32)]
+        taps_of = []
+        for g in a:
+            rows, taps = groups[g], gt[g]
+            # the padded window [start, start + taps) must cover the support and stay on bins 1..199 (rewritten every
+            # tile, always finite); whatever freedom is left goes into avoiding bank conflicts
+            # (a group whose rows leave no freedom may not be arrangeable without conflicts: one padded tap more buys it)
+            cands = []
+            for extra in (0, 1, 2):
+                t_try = taps + extra
+                start_range = {m: (max(1, supp[m][1] - t_try + 1), min(supp[m][0], 200 - t_try)) for m in rows}
+                assert all(lo <= hi for lo, hi in start_range.values())
+                order, start_of, cost = _order_rows(rows, start_range, 8)
+                # wavefronts per tile: every tap is 2 LDS.128 of 4 wavefronts, a conflict adds one to each of them
+                cands.append((2 * t_try * (4 + cost), t_try, order, start_of, cost))
+                if cost == 0:
+                    break
+            _, taps, order, start_of, cost = min(cands, key=lambda c: c[0])
+            conflicts += cost
+            for j in range(taps):
+                for m in order:
+                    # 0.25 * bank weight: the packed two-frame FFT yields 4 |X|^2 (exact scaling)
+                    weights.append(np.float32(bank[m, start_of[m] + j]) * np.float32(0.25))
+            for lane in range(32):
+                m = order[lane % 16]
+                lanes[lane].append((m, start_of[m]))
+            taps_of.append(taps)
+        thread.extend(lanes)
+        warp_t.append(taps_of)
     assert len(thread) == N_THREADS
-    return dict(weights=weights, thread=thread, warp_t=warp_t, warp_nf=list(nfs), warp_ws=warp_ws, conflicts=conflicts)
+    return dict(weights=weights, thread=thread, warp_t=warp_t, warp_wbase=warp_wbase, conflicts=conflicts)
 
 
 def simulate(bank: np.ndarray, plan):
@@ -240,16 +259,18 @@ def simulate(bank: np.ndarray, plan):
     P = rng.random((201, TILE_FRAMES))
     out = np.full((bank.shape[0], TILE_FRAMES), np.nan)
     w = np.asarray(plan["weights"], dtype=np.float64)
-    for t, (row, start, f0, w_ofs) in enumerate(plan["thread"]):
-        wi = t // 32
-        taps, nf, stride = plan["warp_t"][wi], plan["warp_nf"][wi], plan["warp_ws"][wi]
-        f1 = f0 + nf
-        assert 1 <= start and start + taps - 1 <= 199 and f1 <= TILE_FRAMES
-        acc = np.zeros(nf)
-        for j in range(taps):
-            acc += w[w_ofs + j * stride] * P[start + j, f0:f1]
-        assert np.isnan(out[row, f0:f1]).all(), "cell computed twice"
-        out[row, f0:f1] = acc
+    for t, passes in enumerate(plan["thread"]):
+        wi, lane = t // 32, t % 32
+        f0, f1 = 8 * (lane // 16), 8 * (lane // 16) + 8
+        ofs = plan["warp_wbase"][wi] + lane % 16
+        for (row, start), taps in zip(passes, plan["warp_t"][wi]):
+            assert 1 <= start and start + taps - 1 <= 199 and row < 128 and start < 256
+            acc = np.zeros(8)
+            for j in range(taps):
+                acc += w[ofs + j * 16] * P[start + j, f0:f1]
+            ofs += taps * 16
+            assert np.isnan(out[row, f0:f1]).all(), "cell computed twice"
+            out[row, f0:f1] = acc
     assert not np.isnan(out).any(), "cell never computed"
     ref = (bank.astype(np.float64) * 0.25) @ P
     assert np.allclose(out, ref, rtol=1e-12, atol=0), np.abs(out - ref).max()
@@ -287,19 +308,23 @@ def generate() -> str:
         while len(w) % 4:
             w.append(np.float32(0.0))
         assert len(w) < 4096
-        lines.append(f"// n_mels={n_mels}: per warp taps = {plan['warp_t']}, frames per thread = {plan['warp_nf']}, "
-                     f"weight stride = {plan['warp_ws']}, residual LDS.128 conflicts = {plan['conflicts']}")
-        lines.append(f"#define WFT_MEL{n_mels}_WARP_T {{" + ", ".join(str(v) for v in plan["warp_t"]) + "}")
-        lines.append(f"#define WFT_MEL{n_mels}_WARP_NF {{" + ", ".join(str(v) for v in plan["warp_nf"]) + "}")
-        lines.append(f"#define WFT_MEL{n_mels}_WARP_WS {{" + ", ".join(str(v) for v in plan["warp_ws"]) + "}")
+        lines.append(f"// n_mels={n_mels}: taps per warp and pass = {plan['warp_t']}, residual LDS.128 conflicts = {plan['conflicts']}")
+        lines.append(f"#define WFT_MEL{n_mels}_WARP_PASSES {{" + ", ".join(str(len(v)) for v in plan["warp_t"]) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_WARP_T0 {{" + ", ".join(str(v[0]) for v in plan["warp_t"]) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_WARP_T1 {{" + ", ".join(str(v[1] if len(v) > 1 else 0) for v in plan["warp_t"]) + "}")
+        lines.append(f"#define WFT_MEL{n_mels}_WARP_WBASE {{" + ", ".join(str(v) for v in plan["warp_wbase"]) + "}")
         lines.append(f"#define WFT_MEL{n_mels}_W_LEN {len(w)}")
         lines.append(f"#define WFT_MEL{n_mels}_W_INIT {{ \\")
         for r in range(0, len(w), 8):
             lines.append("  " + ", ".join(flit(v) for v in w[r : r + 8]) + ", \\")
         lines.append("}")
-        lines.append(f"// per thread: row | start_bin << 8 | first_frame << 16 | weight_offset << 20")
+        lines.append(f"// per thread: row0 | start_bin0 << 7 | row1 << 15 | start_bin1 << 22   (pass 0 / pass 1)")
         lines.append(f"#define WFT_MEL{n_mels}_THREAD_INIT {{ \\")
-        words = ["0x%08xu" % (row | (start << 8) | (f0 << 16) | (w_ofs << 20)) for row, start, f0, w_ofs in plan["thread"]]
+        words = []
+        for passes in plan["thread"]:
+            (r0, s0) = passes[0]
+            (r1, s1) = passes[1] if len(passes) > 1 else (0, 1)
+            words.append("0x%08xu" % (r0 | (s0 << 7) | (r1 << 15) | (s1 << 22)))
         for r in range(0, len(words), 8):
             lines.append("  " + ", ".join(words[r : r + 8]) + ", \\")
         lines.append("}")

@@ -327,15 +327,19 @@ constexpr int kAugThreads = 256;
 constexpr int kAugFramesPerThread = 4;
 constexpr int kAugRowsPerCta = 16;
 
-// grid = (frame blocks of 1024, row groups of 16, clips); a thread owns 4 consecutive output frames: it evaluates the source
-// coordinates once and walks the 16 rows of its group (bilinear taps mirror grid_sample's float32 arithmetic, zeros outside).
+// grid = (frame blocks of 1024, row groups of 16, clips); a thread owns 4 output frames, 256 apart (lane <-> consecutive frames:
+// a warp's store is one 128-byte line and the two source taps of a smooth, monotone map fall into one or two lines -- with 4
+// ADJACENT frames per thread every scalar load of a warp was spread over 4-8 lines and the kernel sat at 0.40 of the HBM peak
+// on the L1 data pipe); it evaluates the 4 source coordinates once and walks the 16 rows of its group with 8 independent
+// loads in flight per row (bilinear taps mirror grid_sample's float32 arithmetic, zeros outside).
 template <bool kF32>
 __global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                              int32_t R, int32_t T, const int32_t* __restrict__ warp_params,
                                                              const int32_t* __restrict__ mask_params,
                                                              const int32_t* __restrict__ extremes, float mask_value) {
   const int b = blockIdx.z;
-  const int tbase = (blockIdx.x * kAugThreads + threadIdx.x) * kAugFramesPerThread;
+  const int tbase = blockIdx.x * kAugThreads * kAugFramesPerThread + threadIdx.x;
+  constexpr int kStep = kAugThreads;   // frame k of this thread = tbase + k * kStep
   if (tbase >= T) return;
   int wp = -1, wd = 0;
   if (warp_params != nullptr) {
@@ -350,24 +354,31 @@ __global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __res
     lo_rows = e.x; hi_rows = e.y;
   }
   const bool warp = wp > 0 && wp < T - 1;          // anything else (the draw's "gate rejected" marker is -1) = no warp
-  int ix0[kAugFramesPerThread];
-  float wx0[kAugFramesPerThread], wx1[kAugFramesPerThread];
-  bool tmask[kAugFramesPerThread];
+  // per frame, once: the two source columns (clamped into the row so that every load is unconditional) and their weights
+  // (0 for a tap that falls outside: "zeros" padding -- 0 * finite contributes exactly nothing), and whether the cell is live
+  int oa[kAugFramesPerThread], oc[kAugFramesPerThread];
+  float wa[kAugFramesPerThread], wc[kAugFramesPerThread];
+  bool on[kAugFramesPerThread];
 #pragma unroll
   for (int k = 0; k < kAugFramesPerThread; ++k) {
-    const int t = tbase + k;
-    tmask[k] = t >= mk.x && t < mk.y;
-    ix0[k] = t; wx0[k] = 1.0f; wx1[k] = 0.0f;
+    const int t = tbase + k * kStep;
+    on[k] = t < T && !(t >= mk.x && t < mk.y);
+    int a = t < T ? t : T - 1;
+    float wx0 = 1.0f, wx1 = 0.0f;
     if (warp && t < T) {
       const float gx = warp_source_coord<kF32>(t, T, wp, wd);
       const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(T - 1);
       const float f = floorf(ix);
-      ix0[k] = static_cast<int>(f);
-      wx1[k] = ix - f;
-      wx0[k] = (f + 1.0f) - ix;
+      a = static_cast<int>(f);
+      wx1 = ix - f;
+      wx0 = (f + 1.0f) - ix;
     }
+    const int c = a + 1;
+    wa[k] = (a >= 0 && a < T) ? wx0 : 0.0f;
+    wc[k] = (c >= 0 && c < T) ? wx1 : 0.0f;
+    oa[k] = min(max(a, 0), T - 1);
+    oc[k] = min(max(c, 0), T - 1);
   }
-  const bool vec = (T & 3) == 0 && tbase + kAugFramesPerThread <= T;
   const float step = 2.0f / static_cast<float>(R - 1);  // torch.linspace(-1, 1, R)
   const size_t clip = static_cast<size_t>(b) * R * T;
   const int r_end = min(R, static_cast<int>(blockIdx.y + 1) * kAugRowsPerCta);
@@ -380,44 +391,56 @@ __global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __res
     } else if (!warp) {
       const float* row = in + clip + static_cast<size_t>(r) * T;
 #pragma unroll
-      for (int k = 0; k < kAugFramesPerThread; ++k) v[k] = (tmask[k] || tbase + k >= T) ? mask_value : __ldg(row + tbase + k);
+      for (int k = 0; k < kAugFramesPerThread; ++k) v[k] = on[k] ? __ldg(row + oa[k]) : mask_value;
     } else {
+      // source row(s): grid_sample's y coordinate of output row r (the identity up to float32 rounding, which can put a
+      // sliver of weight on the next row -- restated, not assumed)
       const float gy = (r < R / 2) ? (-1.0f + step * static_cast<float>(r)) : (1.0f - step * static_cast<float>(R - 1 - r));
       const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
       const float iy0f = floorf(iy);
       const int iy0 = static_cast<int>(iy0f), iy1 = iy0 + 1;
-      const float wy1 = iy - iy0f, wy0 = (iy0f + 1.0f) - iy;
-      const bool use0 = iy0 >= 0 && iy0 < R, use1 = iy1 >= 0 && iy1 < R && wy1 != 0.0f;
+      const float wy1r = iy - iy0f, wy0r = (iy0f + 1.0f) - iy;
+      const bool use0 = iy0 >= 0 && iy0 < R, use1 = iy1 >= 0 && iy1 < R && wy1r != 0.0f;
+      const float wy0 = use0 ? wy0r : 0.0f, wy1 = use1 ? wy1r : 0.0f;
       const float* row0 = in + clip + static_cast<size_t>(use0 ? iy0 : 0) * T;
-      const float* row1 = in + clip + static_cast<size_t>(use1 ? iy1 : 0) * T;
+      // every tap of the row is requested before the first one is used (8 independent loads in flight per thread)
+      float t0a[kAugFramesPerThread], t0c[kAugFramesPerThread];
 #pragma unroll
       for (int k = 0; k < kAugFramesPerThread; ++k) {
-        float acc = 0.0f;
-        if (!tmask[k] && tbase + k < T) {
-          const int a = ix0[k], c = a + 1;
-          const bool ca = a >= 0 && a < T, cc = c >= 0 && c < T;
-          if (use0) {
-            if (ca) acc += __ldg(row0 + a) * (wx0[k] * wy0);
-            if (cc) acc += __ldg(row0 + c) * (wx1[k] * wy0);
-          }
-          if (use1) {
-            if (ca) acc += __ldg(row1 + a) * (wx0[k] * wy1);
-            if (cc) acc += __ldg(row1 + c) * (wx1[k] * wy1);
-          }
-        } else {
-          acc = mask_value;
+        t0a[k] = __ldg(row0 + oa[k]);
+        t0c[k] = __ldg(row0 + oc[k]);
+      }
+      if (!use1) {      // warp-uniform (depends on r alone); taps accumulate in grid_sample's order
+#pragma unroll
+        for (int k = 0; k < kAugFramesPerThread; ++k) {
+          float acc = 0.0f;
+          acc += t0a[k] * (wa[k] * wy0);
+          acc += t0c[k] * (wc[k] * wy0);
+          v[k] = on[k] ? acc : mask_value;
         }
-        v[k] = acc;
+      } else {
+        const float* row1 = in + clip + static_cast<size_t>(iy1) * T;
+        float t1a[kAugFramesPerThread], t1c[kAugFramesPerThread];
+#pragma unroll
+        for (int k = 0; k < kAugFramesPerThread; ++k) {
+          t1a[k] = __ldg(row1 + oa[k]);
+          t1c[k] = __ldg(row1 + oc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kAugFramesPerThread; ++k) {
+          float acc = 0.0f;
+          acc += t0a[k] * (wa[k] * wy0);
+          acc += t0c[k] * (wc[k] * wy0);
+          acc += t1a[k] * (wa[k] * wy1);
+          acc += t1c[k] * (wc[k] * wy1);
+          v[k] = on[k] ? acc : mask_value;
+        }
       }
     }
     float* dst = out + clip + static_cast<size_t>(r) * T + tbase;
-    if (vec) {
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
 #pragma unroll
-      for (int k = 0; k < kAugFramesPerThread; ++k)
-        if (tbase + k < T) dst[k] = v[k];
-    }
+    for (int k = 0; k < kAugFramesPerThread; ++k)
+      if (tbase + k * kStep < T) dst[k * kStep] = v[k];
   }
 }
 
