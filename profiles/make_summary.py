@@ -46,8 +46,9 @@ def main():
             "steps, kernel-only loop, host pipeline).", "", "| kernel | launches | total µs | share of GPU time |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:10]:
         out.append(f"| `{k}` | {v[0]} | {v[1] / 1e3:.1f} | {100 * v[1] / tot:.1f} % |")
-    out += ["", "A timed step is exactly two launches of this library: `specaug_draw_kernel` (≈2 µs) and `frontend_kernel`; "
-            "synthetic PCM is generated on the host before timing, so no torch kernel runs inside the step.", ""]
+    out += ["", "A timed step is exactly two launches of this library: `frontend_kernel` and its `fixup_kernel` (the SpecAugment "
+            "intervals are drawn inside the front-end kernel); synthetic PCM is generated on the host before timing, so no torch "
+            "kernel runs inside the step.  `augment_kernel` / the draw kernels belong to the `value_with_time_warp` and epilogue loops.", ""]
 
     raw = ncu_csv(rep, "raw")
     d = dict(zip(raw[0], raw[2]))
@@ -128,9 +129,9 @@ def main():
     tot_e = sum(x["exec"] for x in regions)
     tot_s = sum(x["samp"] for x in regions) or 1.0
     out += ["", f"### Instructions per barrier-delimited region of the SASS ({len(data)} instructions = {len(data) * 16 / 1024:.0f} KB)",
-            "", "Regions in program order: 0-1 prologue / loop top / edge staging, 2 audio gather + window, 3 stage A DFT + twiddles + "
-            "exchange stores (+ describe_tile), 4 stage B row loads + DFT, 5 DFT tail + mirror shuffles + power tile, 6 mel phase, "
-            "8 ring check, 9 publication, 10-11 drain, 15-16 helper functions (bulk-copy issue, fix-up).", "", "| # | SASS instr | warp-instr / tile | share | stall-sample share | top opcodes (per tile) |", "|---|---|---|---|---|---|"]
+            "", "Regions in program order: 0-1 prologue / loop top / edge staging, 2 audio gather + window (+ first butterflies), 3 stage A "
+            "DFT + twiddles + exchange stores (+ describe_tile), 4 stage B row loads + DFT + mirror shuffles, 5 power tile, 6 mel "
+            "phase, 8-9 tile close + publication (red.max, tile minimum), 10+ helper functions (bulk-copy issue, edge mel, draw).", "", "| # | SASS instr | warp-instr / tile | share | stall-sample share | top opcodes (per tile) |", "|---|---|---|---|---|---|"]
     for i, x in enumerate(regions):
         if x["exec"] < 0.002 * tot_e:
             continue

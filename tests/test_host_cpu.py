@@ -38,7 +38,7 @@ def test_host_validation_without_gpu(wft):
     lib = wft._lib.load()
     need = ctypes.c_size_t(0)
     assert lib.wft_frontend_workspace_bytes(64, 480000, 3000, ctypes.byref(need)) == 0
-    assert need.value >= 16 + 16 * 64 + 4 * 64 * 94 and need.value % 256 == 0
+    assert need.value >= 16 + 8 * 64 + 4 * 64 * 188 and need.value % 256 == 0
     assert lib.wft_frontend_workspace_bytes(0, 480000, 3000, ctypes.byref(need)) == wft._lib.WFT_ERR_INVALID
     assert b"batch" in lib.wft_last_error()
     assert lib.wft_frontend_workspace_bytes(1, 200, 0, ctypes.byref(need)) == wft._lib.WFT_ERR_INVALID
@@ -46,6 +46,19 @@ def test_host_validation_without_gpu(wft):
     args.pcm = args.out = args.workspace = 1  # never dereferenced: validation fails first
     assert lib.wft_frontend_forward(ctypes.byref(args), None) == wft._lib.WFT_ERR_INVALID
     assert b"n_mels" in lib.wft_last_error()
+    # workspace modes / launch flags (include/wft.h): an overlapping launch needs the workspace ring, unknown modes are rejected
+    need16 = ctypes.c_size_t(0)
+    assert lib.wft_frontend_workspace_bytes(1, 16000, 0, ctypes.byref(need16)) == 0
+    ok = dict(n_mels=80, batch=1, n_samples=16000, clip_stride=16000, workspace_bytes=need16.value)
+    for mode, flags, word in ((wft._lib.WFT_WS_MEMSET, wft._lib.WFT_LAUNCH_OVERLAP, b"WFT_WS_RING"),
+                              (wft._lib.WFT_WS_PHASE_A, wft._lib.WFT_LAUNCH_OVERLAP, b"WFT_WS_RING"),
+                              (3, 0, b"workspace_mode"), (wft._lib.WFT_WS_RING + wft._lib.WFT_WS_PHASES, 0, b"workspace_mode")):
+        args = wft._lib.FrontendArgs(workspace_mode=mode, launch_flags=flags, **ok)
+        args.pcm = args.out = args.workspace = 16
+        assert lib.wft_frontend_forward(ctypes.byref(args), None) == wft._lib.WFT_ERR_INVALID
+        assert word in lib.wft_last_error(), lib.wft_last_error()
+    # the ring needs WFT_WS_PHASES copies of the counters and of the per-tile scratch
+    assert need16.value >= wft._lib.WFT_WS_PHASES * (16 + 8 * 1 + 4 * 7)
     with pytest.raises(ValueError):
         wft._lib.check(wft._lib.WFT_ERR_INVALID)
 

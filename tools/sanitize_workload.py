@@ -1,7 +1,8 @@
 """The workload run under compute-sanitizer (memcheck / synccheck / racecheck): every kernel of the library, and every path of
-the fused kernel -- ragged lengths (silent tiles), partial-segment cuts, masks, int16 / 80 mel, a capped grid (pending FIFO
-overflow -> parked chain -> drain fix-ups), one long clip whose floor binds, a config-3 style batch, the fused augmentation
-epilogue, the draws, pad_or_trim and the activation mask."""
+the fused kernel and its fix-up grid -- ragged lengths (silent tiles), partial-segment cuts, masks, int16 / 80 mel, capped
+grids, one long clip whose floor binds, a config-3 style batch, overlapping independent batches on the workspace ring
+(more than one trip round it), intervals drawn inside the kernel, the fused augmentation epilogue, the draws, pad_or_trim
+and the activation mask."""
 import os
 import sys
 
@@ -19,7 +20,7 @@ nv = torch.tensor([-1, 500, 100], dtype=torch.int32, device="cuda")
 masks = w.draw_mask_params(1, 0, 3, 128, 3000, 100, 27, 1.0)
 out = w.frontend_forward(pcm, 128, lengths=lengths, n_valid_frames=nv, mask_params=masks, n_frames_out=3000)
 out16 = w.frontend_forward((pcm * 32767).round().to(torch.int16), 80, lengths=lengths)
-# capped grid: 2 CTAs hold far more than 16 pending tiles of an incomplete clip -> parked chain + drain
+# capped grids: 2 CTAs walk every tile (front-end kernel) and every 32-tile group (fix-up kernel)
 lib.wft_debug_set_max_ctas(2)
 capped = w.frontend_forward(pcm, 128, lengths=lengths, n_valid_frames=nv, mask_params=masks, n_frames_out=3000)
 lib.wft_debug_set_max_ctas(0)
@@ -39,6 +40,20 @@ fe = w.FrontEnd(n_mels=128, spec_augment=True, seed=3,
                 spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "time_warp_w": 80, "p": 0.7})
 ext = torch.randint(0, 6, (B, 2), generator=g).to(torch.int32)
 x = fe(ragged.cuda(), lengths=rl, n_valid_frames=rv, clip_offset=100, extremes=ext)
+# independent batches overlapping on the 16-phase workspace ring (WFT_LAUNCH_OVERLAP), 20 calls = more than one trip
+old = w.set_overlap(True)
+bufs = [torch.empty(3, 128, 3000, device="cuda") for _ in range(3)]
+fe_plain = w.FrontEnd(n_mels=128)
+fe_draw = w.FrontEnd(n_mels=128, spec_augment=True, seed=9, spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "p": 1.0})
+lengths_d, nv_d = lengths, nv
+for i in range(20):
+    if i % 3 == 2:
+        fe_draw(pcm, lengths=lengths_d, n_valid_frames=nv_d, clip_offset=3 * i, out=bufs[i % 3])
+    else:
+        fe_plain(pcm, lengths=lengths_d if i % 3 else None, n_valid_frames=nv_d if i % 3 else None, out=bufs[i % 3])
+w.set_overlap(old)
+torch.cuda.synchronize()
+assert torch.equal(bufs[1], fe_plain(pcm, lengths=lengths_d, n_valid_frames=nv_d))
 wp = w.draw_warp_params(1, 0, 3, 3000, 80)
 tw = w.time_warp(out, wp)
 ep = w.augment_epilogue(out, wp, masks, None, spline="f32")
