@@ -167,6 +167,18 @@ def test_pad_or_trim_bit_exact(wft, cuda, shape, axis, length):
     assert same.data_ptr() == x.to(cuda).data_ptr() or torch.equal(same.cpu(), x)
 
 
+def test_pad_or_trim_nonfinite_minimum_like_torch_min(wft, cuda):
+    """torch.min propagates NaN and an all-(+inf) input has minimum +inf (data/utils.py:380-404 pads with array.min())."""
+    x = torch.randn(4, 10)
+    x[1, 3] = float("nan")
+    got = wft.pad_or_trim(x.to(cuda), 20, axis=1).cpu()
+    assert torch.isnan(got[:, 10:]).all()
+    assert torch.equal(got[:, :10].nan_to_num(7.0), x.nan_to_num(7.0))
+    y = torch.full((2, 5), float("inf"))
+    got = wft.pad_or_trim(y.to(cuda), 8, axis=1).cpu()
+    assert torch.isinf(got).all() and (got > 0).all()
+
+
 def test_pad_or_trim_empty_raises(wft, cuda):
     with pytest.raises(RuntimeError):
         wft.pad_or_trim(torch.zeros(80, 0, device=cuda), 3000)

@@ -138,14 +138,23 @@ size_t ws_body_bytes(int32_t /*batch*/, int64_t tiles) {
 
 // ---- small stand-alone kernels ---------------------------------------------------------------------------
 
+// scratch[0] = ~enc(min), scratch[1] = 1 if any element is NaN (torch.min propagates NaN; fminf would drop it)
 __global__ void min_reduce_kernel(const float* __restrict__ in, int64_t n, uint32_t* __restrict__ min_inv) {
   float mn = INFINITY;
+  bool nan = false;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
-       k += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    mn = fminf(mn, __ldg(in + k));
+       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = __ldg(in + k);
+    nan |= v != v;
+    mn = fminf(mn, v);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-  if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMax(min_inv, ~wft::enc_ordered(mn));
+  nan = __any_sync(0xffffffffu, nan);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(min_inv, ~wft::enc_ordered(mn));   // always published: an all-(+inf) input pads with +inf
+    if (nan) min_inv[1] = 1u;
+  }
 }
 
 // out[o, l, i] = l < len_in ? in[o, l, i] : min(in)      (data/utils.py:380-404)
@@ -153,7 +162,7 @@ __global__ void pad_or_trim_kernel(const float* __restrict__ in, float* __restri
                                    int64_t len_in, int64_t inner, int64_t len_out,
                                    const uint32_t* __restrict__ min_inv) {
   const int64_t n = outer * len_out * inner;
-  const float fill = (len_out > len_in) ? wft::dec_ordered(~(*min_inv)) : 0.0f;
+  const float fill = (len_out > len_in) ? (min_inv[1] != 0u ? __int_as_float(0x7fc00000) : wft::dec_ordered(~min_inv[0])) : 0.0f;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
        k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t i = k % inner;
