@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WFT_ABI_VERSION 7
+#define WFT_ABI_VERSION 8
 
 /* Front-end constants (whisper.audio: SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES;
  * imported by the reference at data_loader.py:13 and data/utils.py:10). */
@@ -182,6 +182,14 @@ int wft_time_warp_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32
  * in == out is allowed only without a warp. */
 int wft_augment_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
                     const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream);
+
+/* The same epilogue with the clip parameters drawn INSIDE the kernel: intervals = wft_specaug_draw(seed, clip_offset, batch,
+ * n_rows, n_frames, time_mask_param, freq_mask_param, p), warp points = wft_time_warp_draw(seed, clip_offset, batch, n_frames,
+ * time_warp_w, p) -- bit for bit the same draws, without the two launches in front (an augmented production batch is then
+ * front-end grid -> fix-up grid -> this grid).  time_warp_w == 0 = masks only (in == out allowed). */
+int wft_augment_drawn_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, uint64_t seed,
+                          uint64_t clip_offset, int32_t time_mask_param, int32_t freq_mask_param, int32_t time_warp_w, float p,
+                          const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream);
 
 /* Deep SpecAugment on encoder activations (model/model_utils.py:382-437: permute -> TimeMasking -> FrequencyMasking ->
  * permute on every hooked layer-norm output), without the permutes: x is [batch, seq, dim] contiguous with 16-bit (fp16 /

@@ -346,6 +346,40 @@ def test_overlapping_batches_equal_ordinary_launches(wft, cuda):
         assert torch.equal(outs[k], want_aug[k]), f"overlapped augmented batch {k}"
 
 
+def test_production_batch_with_drawn_epilogue_equals_explicit_composition(wft, cuda):
+    """FrontEnd with time_warp_w > 0 takes front-end grid -> fix-up grid -> ONE epilogue grid that draws the warp point and the
+    mask intervals itself (wft_augment_drawn_f32).  It must equal, bit for bit, the explicit composition draw -> draw ->
+    front end -> epilogue, also when consecutive batches overlap (scratch buffers alternate)."""
+    B = 6
+    g = torch.Generator().manual_seed(21)
+    sets = [(0.1 * torch.randn(B, 480000, generator=g)).clamp(-1, 1).to(cuda) for _ in range(3)]
+    lengths = torch.tensor([480000, 400000, 480000, 16000, 480000, 250000], dtype=torch.int32, device=cuda)
+    for x in sets:
+        x[torch.arange(480000, device=cuda)[None, :] >= lengths[:, None]] = 0.0
+    params = {"time_mask_param": 100, "freq_mask_param": 27, "time_warp_w": 80, "p": 0.6}
+    fe = wft.FrontEnd(n_mels=128, spec_augment=True, spec_augment_params=params, seed=17)
+    want = []
+    for k, x in enumerate(sets):
+        masks = wft.draw_mask_params(17, 1000 * k, B, 128, 3000, 100, 27, 0.6, cuda)
+        warps = wft.draw_warp_params(17, 1000 * k, B, 3000, 80, 0.6, cuda)
+        plain = wft.frontend_forward(x, 128, lengths=lengths)
+        want.append(wft.augment_epilogue(plain, warps, masks, None, 0.0))
+    torch.cuda.synchronize()
+    assert any(int(w[0]) > 0 for w in wft.draw_warp_params(17, 0, B, 3000, 80, 0.6, cuda).cpu()), "some clip must be warped"
+    outs = [torch.empty_like(want[0]) for _ in range(3)]
+    for overlap in (False, True):
+        old = wft.set_overlap(overlap)
+        try:
+            for i in range(9):
+                fe(sets[i % 3], lengths=lengths, clip_offset=1000 * (i % 3), out=outs[i % 3])
+            torch.cuda.synchronize()
+        finally:
+            wft.set_overlap(old)
+        for k in range(3):
+            assert torch.equal(outs[k], want[k]), f"batch {k}, overlap={overlap}"
+            outs[k].zero_()
+
+
 def _gold(name):
     import os
 

@@ -18,7 +18,7 @@ WFT_WS_PHASES = 16
 WFT_LAUNCH_PDL, WFT_LAUNCH_OVERLAP = 1, 2
 WFT_ERR_INVALID = -1
 WFT_ERR_CUDA = -2
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class FrontendArgs(Structure):
@@ -65,6 +65,8 @@ SIGNATURES = {
     "wft_time_warp_draw": (c_int, [c_uint64, c_uint64, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
     "wft_augment_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_int32,
                                 c_void_p]),
+    "wft_augment_drawn_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_uint64, c_uint64, c_int32, c_int32, c_int32,
+                                      c_float, c_void_p, c_float, c_int32, c_void_p]),
     "wft_mask_bsd": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                              c_uint32, c_void_p]),
     "wft_launch_count": (c_int64, [c_int]),

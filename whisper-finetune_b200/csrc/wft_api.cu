@@ -262,11 +262,7 @@ __global__ void specaug_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t
 
 // counter-based draw of (warp_p, warp_d): warp_p uniform in [W, T-W), warp_d uniform in [-W, W) (the reference's randint
 // ranges, data/utils.py:107-111), Philox block 2 of the clip's counter; (-1, 0) == "no warp" when the p gate rejects
-__global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t W,
-                                      float p, int32_t* __restrict__ out) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
-  const uint64_t idx = clip_offset + static_cast<uint64_t>(b);
+__device__ __noinline__ int2 draw_warp_point(uint64_t seed, uint64_t idx, int32_t n_frames, int32_t W, float p) {
   const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   const uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
   bool apply = p >= 1.0f;
@@ -282,8 +278,23 @@ __global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32
     w.x = W + static_cast<int>(__fmul_rn(wft::u01(r[0]), static_cast<float>(n_frames - 2 * W)));
     w.y = -W + static_cast<int>(__fmul_rn(wft::u01(r[1]), static_cast<float>(2 * W)));
   }
-  reinterpret_cast<int2*>(out)[b] = w;
+  return w;
 }
+
+__global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t W,
+                                      float p, int32_t* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  reinterpret_cast<int2*>(out)[b] = draw_warp_point(seed, clip_offset + static_cast<uint64_t>(b), n_frames, W, p);
+}
+
+// the augmentation epilogue may draw its clip's parameters itself (wft_augment_drawn_f32): same draws as wft_specaug_draw and
+// wft_time_warp_draw for (seed, clip_offset + b)
+struct AugDraw {
+  int32_t enabled, tparam, fparam, W;
+  float p;
+  uint64_t seed, clip_offset;
+};
 
 // ---- fused augmentation epilogue: time-warp -> time mask -> frequency mask -> extremes mask in ONE read + write of the
 // features (data_loader.py:284-290: time_warping, time_masking, freq_masking, extreme_freq_masking).  Every step after the
@@ -345,18 +356,36 @@ template <bool kF32>
 __global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                              int32_t R, int32_t T, const int32_t* __restrict__ warp_params,
                                                              const int32_t* __restrict__ mask_params,
-                                                             const int32_t* __restrict__ extremes, float mask_value) {
+                                                             const int32_t* __restrict__ extremes, float mask_value,
+                                                             const AugDraw draw) {
   const int b = blockIdx.z;
+  __shared__ int s_draw[8];
+  if (draw.enabled) {   // two threads draw the clip's intervals and warp point (before the features are needed)
+    if (threadIdx.x == 0) {
+      const int4 m = wft::draw_mask_intervals(draw.seed, draw.clip_offset + static_cast<uint64_t>(b), R, T, draw.tparam, draw.fparam, draw.p);
+      s_draw[0] = m.x; s_draw[1] = m.y; s_draw[2] = m.z; s_draw[3] = m.w;
+    } else if (threadIdx.x == 32) {
+      const int2 w = draw_warp_point(draw.seed, draw.clip_offset + static_cast<uint64_t>(b), T, draw.W, draw.p);
+      s_draw[4] = w.x; s_draw[5] = w.y;
+    }
+    __syncthreads();
+  }
+  // a programmatic dependent of whatever produced `in`: the grid behind this one may be scheduled, this one waits
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tbase = blockIdx.x * kAugThreads * kAugFramesPerThread + threadIdx.x;
   constexpr int kStep = kAugThreads;   // frame k of this thread = tbase + k * kStep
   if (tbase >= T) return;
   int wp = -1, wd = 0;
-  if (warp_params != nullptr) {
+  if (draw.enabled) {
+    wp = s_draw[4]; wd = s_draw[5];
+  } else if (warp_params != nullptr) {
     const int2 w = __ldg(reinterpret_cast<const int2*>(warp_params) + b);
     wp = w.x; wd = w.y;
   }
   int4 mk = make_int4(0, 0, 0, 0);
-  if (mask_params != nullptr) mk = __ldg(reinterpret_cast<const int4*>(mask_params) + b);
+  if (draw.enabled) mk = make_int4(s_draw[0], s_draw[1], s_draw[2], s_draw[3]);
+  else if (mask_params != nullptr) mk = __ldg(reinterpret_cast<const int4*>(mask_params) + b);
   int lo_rows = 0, hi_rows = 0;
   if (extremes != nullptr) {
     const int2 e = __ldg(reinterpret_cast<const int2*>(extremes) + b);
@@ -706,13 +735,13 @@ int wft_specaug_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t
   return WFT_OK;
 }
 
-int wft_augment_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
-                    const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int launch_augment(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
+                          const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32,
+                          const AugDraw& draw, cudaStream_t stream) {
   if (batch < 0 || n_rows < 0 || n_frames < 0) return fail(WFT_ERR_INVALID, "negative extent");
   if (static_cast<int64_t>(batch) * n_rows * n_frames == 0) return WFT_OK;
   if (in == nullptr || out == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
-  if (warp_params != nullptr) {
+  if (warp_params != nullptr || (draw.enabled && draw.W > 0)) {
     if (in == out) return fail(WFT_ERR_INVALID, "time warp cannot run in place");
     if (n_rows < 2 || n_frames < 3) return fail(WFT_ERR_INVALID, "time warp needs at least 2 rows and 3 frames");
     if ((reinterpret_cast<uintptr_t>(warp_params) & 7) != 0) return fail(WFT_ERR_INVALID, "warp_params must be 8-byte aligned");
@@ -725,14 +754,41 @@ int wft_augment_f32(const float* in, float* out, int32_t batch, int32_t n_rows, 
     return fail(WFT_ERR_INVALID, "in and out must be 16-byte aligned");
   if (batch > 65535) return fail(WFT_ERR_INVALID, "batch too large for one launch (max 65535)");
   const int per_cta = kAugThreads * kAugFramesPerThread;
-  dim3 grid((n_frames + per_cta - 1) / per_cta, (n_rows + kAugRowsPerCta - 1) / kAugRowsPerCta, batch);
+  // always a programmatic dependent: the kernel waits for its predecessor on the device (griddepcontrol.wait), so its
+  // launch latency and -- for the drawn variant -- its draws hide under the tail of the kernel that produces `in`
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((n_frames + per_cta - 1) / per_cta, (n_rows + kAugRowsPerCta - 1) / kAugRowsPerCta, batch);
+  cfg.blockDim = dim3(kAugThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (spline_f32)
-    augment_kernel<true><<<grid, kAugThreads, 0, stream>>>(in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value);
+    WFT_CUDA(cudaLaunchKernelEx(&cfg, augment_kernel<true>, in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, draw));
   else
-    augment_kernel<false><<<grid, kAugThreads, 0, stream>>>(in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value);
+    WFT_CUDA(cudaLaunchKernelEx(&cfg, augment_kernel<false>, in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, draw));
   ++g_launches;
-  WFT_CUDA(cudaGetLastError());
   return WFT_OK;
+}
+
+int wft_augment_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
+                    const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream_) {
+  return launch_augment(in, out, batch, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, spline_f32, AugDraw{},
+                        static_cast<cudaStream_t>(stream_));
+}
+
+int wft_augment_drawn_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, uint64_t seed,
+                          uint64_t clip_offset, int32_t time_mask_param, int32_t freq_mask_param, int32_t time_warp_w, float p,
+                          const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream_) {
+  if (!(p >= 0.0f && p <= 1.0f)) return fail(WFT_ERR_INVALID, "spec_augment p must be between 0 and 1");
+  if (time_warp_w < 0) return fail(WFT_ERR_INVALID, "time_warp_w must be >= 0");
+  AugDraw d{};
+  d.enabled = 1; d.tparam = time_mask_param; d.fparam = freq_mask_param; d.W = time_warp_w; d.p = p;
+  d.seed = seed; d.clip_offset = clip_offset;
+  return launch_augment(in, out, batch, n_rows, n_frames, nullptr, nullptr, extremes, mask_value, spline_f32, d,
+                        static_cast<cudaStream_t>(stream_));
 }
 
 int wft_time_warp_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames,

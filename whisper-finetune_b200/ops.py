@@ -118,12 +118,12 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
         ws = ent[0]
         flags = _lib.WFT_LAUNCH_PDL if _PDL["enabled"] else 0
         reads = [_span(t) for t in (pcm, lengths, n_valid_frames, mask_params)]
-        writes = _span(out)
+        writes = [_span(out)]
         prev = _LAST_CALL.get((dev.index, stream))
         if _OVERLAP["enabled"] and prev is not None:
             prev_reads, prev_writes = prev
-            if (_disjoint(writes, prev_writes) and all(_disjoint(writes, r) for r in prev_reads)
-                    and all(_disjoint(r, prev_writes) for r in reads)):
+            if (all(_disjoint(w, q) for w in writes for q in prev_writes + prev_reads)
+                    and all(_disjoint(r, q) for r in reads for q in prev_writes)):
                 flags |= _lib.WFT_LAUNCH_OVERLAP
         _LAST_CALL[(dev.index, stream)] = (reads, writes)
         args = _lib.FrontendArgs(
@@ -258,6 +258,44 @@ def _launch_augment(mel: Tensor, warp_params: Optional[Tensor], mask_params: Opt
     with torch.cuda.device(mel.device):
         _lib.check(lib.wft_augment_f32(mel.data_ptr(), out.data_ptr(), B, R, T, _ptr(warp_params), _ptr(mask_params),
                                        _ptr(extremes), float(mask_value), 1 if spline_f32 else 0, _stream(mel.device)))
+
+
+def _chain_stream(dev: torch.device, reads, writes) -> int:
+    """Stream handle for the epilogue of a front-end call: the call's recorded byte ranges grow by what the epilogue touches,
+    so that the NEXT front-end call may still be launched as an independent batch when it stays clear of all of them."""
+    st = torch.cuda.current_stream(dev).cuda_stream
+    prev = _LAST_CALL.get((dev.index, st))
+    if prev is not None:
+        _LAST_CALL[(dev.index, st)] = (prev[0] + [_span(t) for t in reads], prev[1] + [_span(t) for t in writes])
+    return st
+
+
+@torch.library.custom_op("wft::augment_drawn_out", mutates_args=("out",), device_types="cuda")
+def augment_drawn_out(mel: Tensor, seed: int, clip_offset: int, time_mask_param: int, freq_mask_param: int, time_warp_w: int,
+                      p: float, extremes: Optional[Tensor], mask_value: float, spline_f32: bool, out: Tensor) -> None:
+    """The augmentation epilogue with the clip parameters drawn inside the kernel (``wft_augment_drawn_f32``): the same draws as
+    ``wft::specaug_draw`` + ``wft::time_warp_draw`` for ``(seed, clip_offset + b)``, no launches in front."""
+    lib = _lib.load()
+    if mel.dim() != 3 or mel.dtype != torch.float32 or not mel.is_contiguous():
+        raise ValueError("mel must be a contiguous CUDA float32 tensor of shape [B, R, T]")
+    B, R, T = mel.shape
+    if extremes is not None and (extremes.dtype != torch.int32 or tuple(extremes.shape) != (B, 2) or not extremes.is_contiguous()
+                                 or extremes.device != mel.device):
+        raise ValueError(f"extremes must be a contiguous int32 tensor of shape {(B, 2)} on {mel.device}")
+    if out.dtype != torch.float32 or tuple(out.shape) != (B, R, T) or not out.is_contiguous() or out.device != mel.device:
+        raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {(B, R, T)}")
+    if not 0.0 <= p <= 1.0:
+        raise ValueError(f"spec_augment p must be between 0 and 1, got {p}")
+    with torch.cuda.device(mel.device):
+        _lib.check(lib.wft_augment_drawn_f32(mel.data_ptr(), out.data_ptr(), B, R, T, seed & (2**64 - 1), clip_offset & (2**64 - 1),
+                                             int(time_mask_param), int(freq_mask_param), int(time_warp_w), float(p), _ptr(extremes),
+                                             float(mask_value), 1 if spline_f32 else 0,
+                                             _chain_stream(mel.device, [mel, extremes], [out])))
+
+
+@augment_drawn_out.register_fake
+def _(mel, seed, clip_offset, time_mask_param, freq_mask_param, time_warp_w, p, extremes, mask_value, spline_f32, out):
+    return None
 
 
 @torch.library.custom_op("wft::augment", mutates_args=(), device_types="cuda")
