@@ -526,8 +526,8 @@ def run_ours(args):
         epi_bytes = 2 * 4 * N_MELS * N_FRAMES * BATCH
         line["value_with_time_warp"] = {
             "value": value_warp, "unit": UNIT, "ms_per_step": warp_block_ms / args.steps, "gpu_launches_per_step": warp_launches / args.steps,
-            "what": "mask + warp draws, fused front-end kernel, ONE fused epilogue pass (time-warp W=80 -> time mask -> frequency mask), "
-                    "device-resident PCM, same blocks / streams as `value`",
+            "what": "front-end grid, fix-up grid, ONE fused epilogue grid (time-warp W=80 -> time mask -> frequency mask) that draws "
+                    "the clip's warp point and mask intervals itself; device-resident PCM, same blocks / stream as `value`",
             "epilogue_roofline": {"bound": "hbm", "kernel": "augment_kernel<false>", "kernel_ms": epi_ms,
                                   "algorithmic_bytes_per_launch": epi_bytes, "achieved": epi_bytes / (epi_ms * 1e-3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": epi_bytes / (epi_ms * 1e-3) / 1e9 / peak}}
