@@ -551,28 +551,25 @@ constexpr int kFixThreads = 128;
 constexpr int kFixWarps = kFixThreads / 32;
 constexpr int kFixTiles = 32;   // tiles per CTA: one per lane of the scan
 
+// what a lane found out about ITS tile during the scan; broadcast to the warp when the tile is rewritten
+struct FixTile {
+  int clip, t0, keep;
+  float floorn, padv;
+  int mt0, mt1, mf0, mf1;
+};
+
 // one warp finishes one tile; `constant` = nothing was written yet (silent or pad-only tile): every kept cell is the clamp value
-template <int NM>
-__device__ __forceinline__ void fixup_tile(const FixupParams& p, int clip, int t0, bool constant, int lane) {
+template <int NM, int kBatch>
+__device__ __forceinline__ void fixup_tile(const FixupParams& p, const FixTile& ft, bool constant, int lane) {
   const float vsilent = feature_of_l2(silent_l2());
-  const ClipStat st = p.stats[clip];
-  const float floorn = floor_feature(dec_ordered(st.max_enc));
-  const float padv = fmaxf(feature_of_l2(dec_ordered(~st.min_inv)), floorn);
-  const int keep = kept_frames(p.n_valid, clip, p.n_frames);
-  int mt0 = 0, mt1 = 0, mf0 = 0, mf1 = 0;
-  if (p.masks != nullptr || p.draw) {
-    const int4 mk = p.masks != nullptr ? __ldg(reinterpret_cast<const int4*>(p.masks) + clip)
-                                       : draw_mask_intervals(p.draw_seed, p.draw_clip_offset + static_cast<uint64_t>(clip), NM,
-                                                             p.n_frames_out, p.draw_tparam, p.draw_fparam, p.draw_p);
-    mt0 = mk.x; mt1 = mk.y; mf0 = mk.z; mf1 = mk.w;
-  }
-  const float mv = p.mask_value;
+  const float floorn = ft.floorn, padv = ft.padv, mv = p.mask_value;
+  const int keep = ft.keep, t0 = ft.t0, mt0 = ft.mt0, mt1 = ft.mt1, mf0 = ft.mf0, mf1 = ft.mf1;
   const int pitch = p.n_frames_out;
-  float* base = p.out + static_cast<size_t>(clip) * NM * pitch;
+  float* base = p.out + static_cast<size_t>(ft.clip) * NM * pitch;
   if ((pitch & 3) == 0) {
     constexpr int kGroups = kTileFrames / 4;        // float4 groups per row (4)
     constexpr int kRowsPerPass = 32 / kGroups;      // 8 rows per warp-wide access
-    constexpr int kBatch = 2;                       // rows in flight per lane (the kernel has to stay within 32 registers)
+    // kBatch = rows in flight per lane (2 in the lean instance, which has to stay within 32 registers)
     static_assert(NM % (kRowsPerPass * kBatch) == 0, "row loop");
     const int f = t0 + ((lane & (kGroups - 1)) << 2);
     if (f >= pitch) return;
@@ -619,39 +616,55 @@ __device__ __forceinline__ void fixup_tile(const FixupParams& p, int clip, int t
 
 __device__ __forceinline__ bool tile_is_silent(int t0, int len, int n_total);
 
-template <int NM>
-__global__ void __launch_bounds__(kFixThreads, 16) fixup_kernel(const FixupParams p) {   // <= 32 registers: see launch_frontend
+// kLean: the instance launched behind batches that hardly ever need a fix-up (full-length clips) -- <= 32 registers, one CTA
+// per SM, so that it fits next to six front-end CTAs.  The other instance serves ragged batches, where a third or more of
+// all tiles are constant fills: more registers, more CTAs.
+template <int NM, bool kLean>
+__global__ void __launch_bounds__(kFixThreads, kLean ? 16 : 4) fixup_kernel(const FixupParams p) {
   // the kernel behind this one may be scheduled now (it decides itself what it has to wait for); this grid needs the
   // front-end grid complete: its features, the clip statistics and the per-tile minima
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = static_cast<int>(threadIdx.x) & 31, warp = static_cast<int>(threadIdx.x) >> 5;
-  // a WARP owns groups of 32 consecutive tiles (lane <-> tile), grid-stride: no shared memory, no barrier
+  // a WARP owns groups of 32 consecutive tiles (lane <-> tile), grid-stride: no shared memory, no barrier.  Every lane
+  // gathers everything its own tile's rewrite needs (clip statistics, kept frames, mask intervals) -- 32 tiles' worth of
+  // dependent loads in parallel -- and the warp then rewrites the flagged tiles one after the other from broadcast values.
   for (int base = (static_cast<int>(blockIdx.x) * kFixWarps + warp) * kFixTiles; base < p.total_tiles;
        base += static_cast<int>(gridDim.x) * kFixWarps * kFixTiles) {
     const int tile = base + lane;
     bool needs = false, constant = false;
-    int clip = 0, t0 = 0;
+    FixTile ft{};
     if (tile < p.total_tiles) {
-      clip = tile / p.tiles_per_clip;
-      t0 = (tile - clip * p.tiles_per_clip) * kTileFrames;
-      if (t0 < p.n_frames_out) {
-        if (t0 >= p.n_frames) {            // pad-only tile (n_frames_out > n_frames)
+      ft.clip = tile / p.tiles_per_clip;
+      ft.t0 = (tile - ft.clip * p.tiles_per_clip) * kTileFrames;
+      if (ft.t0 < p.n_frames_out) {
+        ft.keep = kept_frames(p.n_valid, ft.clip, p.n_frames);
+        const uint32_t max_enc = __ldcg(&p.stats[ft.clip].max_enc);
+        ft.floorn = floor_feature(dec_ordered(max_enc));
+        if (ft.t0 >= p.n_frames) {            // pad-only tile (n_frames_out > n_frames)
           needs = constant = true;
         } else {
           int len = p.n_samples;
           if (p.lengths != nullptr) {
-            const int l = __ldg(p.lengths + clip);
+            const int l = __ldg(p.lengths + ft.clip);
             len = l < 0 ? 0 : (l < len ? l : len);
           }
-          if (tile_is_silent(t0, len, p.n_total)) {
+          if (tile_is_silent(ft.t0, len, p.n_total)) {
             needs = constant = true;
           } else {
-            const int keep = kept_frames(p.n_valid, clip, p.n_frames);
-            const int hi = t0 + kTileFrames < p.n_frames_out ? t0 + kTileFrames : p.n_frames_out;
-            const bool has_pad = (t0 > keep ? t0 : keep) < hi;
-            const bool floor_binds = feature_of_l2(__ldcg(p.tile_min + tile)) < floor_feature(dec_ordered(__ldcg(&p.stats[clip].max_enc)));
+            const int hi = ft.t0 + kTileFrames < p.n_frames_out ? ft.t0 + kTileFrames : p.n_frames_out;
+            const bool has_pad = (ft.t0 > ft.keep ? ft.t0 : ft.keep) < hi;
+            const bool floor_binds = feature_of_l2(__ldcg(p.tile_min + tile)) < ft.floorn;
             needs = has_pad || floor_binds;
+          }
+        }
+        if (needs) {
+          ft.padv = fmaxf(feature_of_l2(dec_ordered(~__ldcg(&p.stats[ft.clip].min_inv))), ft.floorn);
+          if (p.masks != nullptr || p.draw) {
+            const int4 mk = p.masks != nullptr ? __ldg(reinterpret_cast<const int4*>(p.masks) + ft.clip)
+                                               : draw_mask_intervals(p.draw_seed, p.draw_clip_offset + static_cast<uint64_t>(ft.clip),
+                                                                     NM, p.n_frames_out, p.draw_tparam, p.draw_fparam, p.draw_p);
+            ft.mt0 = mk.x; ft.mt1 = mk.y; ft.mf0 = mk.z; ft.mf1 = mk.w;
           }
         }
       }
@@ -661,7 +674,13 @@ __global__ void __launch_bounds__(kFixThreads, 16) fixup_kernel(const FixupParam
     while (todo != 0u) {
       const int l = __ffs(todo) - 1;
       todo &= todo - 1u;
-      fixup_tile<NM>(p, __shfl_sync(0xffffffffu, clip, l), __shfl_sync(0xffffffffu, t0, l), ((cst >> l) & 1u) != 0u, lane);
+      FixTile b;
+      b.clip = __shfl_sync(0xffffffffu, ft.clip, l); b.t0 = __shfl_sync(0xffffffffu, ft.t0, l);
+      b.keep = __shfl_sync(0xffffffffu, ft.keep, l);
+      b.floorn = __shfl_sync(0xffffffffu, ft.floorn, l); b.padv = __shfl_sync(0xffffffffu, ft.padv, l);
+      b.mt0 = __shfl_sync(0xffffffffu, ft.mt0, l); b.mt1 = __shfl_sync(0xffffffffu, ft.mt1, l);
+      b.mf0 = __shfl_sync(0xffffffffu, ft.mf0, l); b.mf1 = __shfl_sync(0xffffffffu, ft.mf1, l);
+      fixup_tile<NM, 2>(p, b, ((cst >> l) & 1u) != 0u, lane);   // (8 rows in flight in the heavy instance: 113 registers, same time)
     }
   }
 }

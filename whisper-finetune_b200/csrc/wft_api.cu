@@ -105,7 +105,7 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launc
   const int groups = (p.total_tiles + wft::kFixTiles * wft::kFixWarps - 1) / (wft::kFixTiles * wft::kFixWarps);
   // ragged inputs (lengths / cuts / output longer than the clip) mean many constant-fill tiles: more CTAs per SM
   const bool heavy = p.lengths != nullptr || p.n_valid != nullptr || p.n_frames_out > p.n_frames;
-  int fix_ctas = (ctas_full / 6) * (heavy ? 4 : 1);
+  int fix_ctas = (ctas_full / 6) * (heavy ? 8 : 1);
   if (fix_ctas > groups) fix_ctas = groups;
   if (g_debug_max_ctas > 0 && fix_ctas > g_debug_max_ctas) fix_ctas = g_debug_max_ctas;
   cudaLaunchConfig_t fcfg{};
@@ -115,7 +115,8 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launc
   fcfg.stream = stream;
   fcfg.attrs = attr;
   fcfg.numAttrs = 1;
-  WFT_CUDA(cudaLaunchKernelEx(&fcfg, wft::fixup_kernel<NM>, f));
+  if (heavy) WFT_CUDA(cudaLaunchKernelEx(&fcfg, wft::fixup_kernel<NM, false>, f));
+  else WFT_CUDA(cudaLaunchKernelEx(&fcfg, wft::fixup_kernel<NM, true>, f));
   ++g_launches;
   return WFT_OK;
 }
