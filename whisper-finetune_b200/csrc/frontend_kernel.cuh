@@ -75,7 +75,8 @@ constexpr int kTwFloats = WFT_TWIDDLE_TABLE_LEN;                 // 880
 constexpr int kTwRow = WFT_TWIDDLE_ROW;                          // 44
 constexpr int kMelWFloats = ((WFT_MEL80_W_LEN > WFT_MEL128_W_LEN ? WFT_MEL80_W_LEN : WFT_MEL128_W_LEN) + 3) & ~3;
 constexpr int kCtlInts = 64;
-constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats + kMelWFloats) * 4 + kCtlInts * 4;
+constexpr int kDrawCache = 64;    // clips whose drawn SpecAugment intervals a CTA keeps in shared memory (batches up to this size)
+constexpr int kSmemBytes = (kRegionFloats + kWinFloats + kTwFloats + kMelWFloats) * 4 + kCtlInts * 4 + kDrawCache * 16;
 
 static_assert(kPFloats <= kAudioBase, "power tile and prefetched audio tile must not overlap");
 static_assert((kAudioBase & 3) == 0 && ((kSkewBlock + Skew<float>::value) * 4) % 16 == 0 &&
@@ -736,7 +737,8 @@ __device__ __forceinline__ TileGeom tile_geom(const FrontendParams& q) {
 // mask intervals are loaded once per clip and memoised in shared memory -- consecutive tiles mostly share the clip)
 // (forced inline: as a real call this sat on thread 0's critical path before a CTA barrier and cost 2.5 % overall)
 template <int NM, typename PcmT>
-__device__ __forceinline__ void describe_tile(const TileGeom p, int t, int* __restrict__ slot, int* __restrict__ memo) {
+__device__ __forceinline__ void describe_tile(const TileGeom p, int t, int* __restrict__ slot, int* __restrict__ memo,
+                                              const int4* __restrict__ draw_cache) {
   int clip = 0, t0 = 0, kind = kTileEdge, flags = 0, keep = 0;
   long long off = 0, out_off = 0;
   int4 mk = make_int4(0, 0, 0, 0);
@@ -757,8 +759,9 @@ __device__ __forceinline__ void describe_tile(const TileGeom p, int t, int* __re
       }
       int4 m = make_int4(0, 0, 0, 0);
       if (p.masks != nullptr) m = __ldg(reinterpret_cast<const int4*>(p.masks) + clip);
-      else if (p.draw) m = draw_mask_intervals(p.draw_seed, p.draw_clip_offset + static_cast<uint64_t>(clip), NM, p.n_frames_out,
-                                               p.draw_tparam, p.draw_fparam, p.draw_p);
+      else if (p.draw) m = draw_cache != nullptr ? draw_cache[clip]
+                                                 : draw_mask_intervals(p.draw_seed, p.draw_clip_offset + static_cast<uint64_t>(clip), NM,
+                                                                       p.n_frames_out, p.draw_tparam, p.draw_fparam, p.draw_p);
       memo[0] = clip; memo[1] = len; memo[2] = kp;
       *reinterpret_cast<int4*>(memo + 4) = m;
     }
@@ -815,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   float* sm_tw = sm_win + kWinFloats;
   float* sm_melw = sm_tw + kTwFloats;
   int* sm_ctl = reinterpret_cast<int*>(sm_melw + kMelWFloats);
+  int4* sm_draw = reinterpret_cast<int4*>(sm_ctl + kCtlInts);
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
@@ -846,6 +850,13 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       if (k < kVecAll) reinterpret_cast<float4*>(sm_win)[k] = v[i];
     }
   }
+  // Intervals drawn in here (draw_masks): a small batch is drawn once per CTA, one clip per thread, into shared memory -- with
+  // 13 tiles per CTA nearly every tile belongs to another clip, and ~150 instructions of Philox on thread 0 per tile held up
+  // every barrier behind it (3 % of the launch).  Larger batches draw on demand (consecutive tiles mostly share the clip).
+  const int4* draw_cache = (p.draw && p.batch <= kDrawCache) ? sm_draw : nullptr;
+  if (draw_cache != nullptr && tid < p.batch)
+    sm_draw[tid] = draw_mask_intervals(p.draw_seed, p.draw_clip_offset + static_cast<uint64_t>(tid), NM, p.n_frames_out,
+                                       p.draw_tparam, p.draw_fparam, p.draw_p);
   uint64_t* audio_bar = reinterpret_cast<uint64_t*>(sm_ctl + kCtlMbar);  // completion of the audio tile's bulk copies
   // Programmatic dependent launch: everything above (7.4 KB of tables into shared memory) may overlap the tail of the
   // previous kernel on the stream; its results and the workspace may only be touched from here on.
@@ -857,13 +868,14 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   // one AFTER it (not started: it waits for this grid): zeroing them here needs no fence and replaces a memset per call
   if (blockIdx.x == 0)
     for (int i = tid; i < p.clean_vec; i += kThreads) p.clean[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (draw_cache != nullptr) __syncthreads();   // the first describe_tile below reads the drawn intervals
   if (tid == 0) {
     sm_ctl[kCtlMemo] = -1;
     mbar_init(audio_bar, kWarps);   // one arrive.expect_tx per warp and tile (prefetch_audio_part)
     const int first = static_cast<int>(atomicAdd(p.tile_counter, static_cast<uint32_t>(p.chunk)));
     sm_ctl[kCtlChunkNext] = first + 1;
     sm_ctl[kCtlChunkLeft] = p.chunk - 1;
-    describe_tile<NM, PcmT>(tile_geom(p), first, sm_ctl + kCtlDesc, sm_ctl + kCtlMemo);
+    describe_tile<NM, PcmT>(tile_geom(p), first, sm_ctl + kCtlDesc, sm_ctl + kCtlMemo, draw_cache);
   }
   __syncthreads();
   // a tile of kind kTileInterior always arrives by TMA: the first one is sent here, every later one under the tile before it
@@ -896,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
     const int t_ = left_ == 0 ? nxt_claim : sm_ctl[kCtlChunkNext];                                   \
     sm_ctl[kCtlChunkLeft] = left_ == 0 ? p.chunk - 1 : left_ - 1;                                    \
     sm_ctl[kCtlChunkNext] = t_ + 1;                                                                  \
-    describe_tile<NM, PcmT>(tile_geom(p), t_, NDESC, sm_ctl + kCtlMemo);                             \
+    describe_tile<NM, PcmT>(tile_geom(p), t_, NDESC, sm_ctl + kCtlMemo, draw_cache);                 \
   } while (0)
     const int4 d_top = DESC4;
     if (d_top.x >= p.total_tiles) break;
