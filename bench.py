@@ -8,8 +8,8 @@
 Workload (BASELINE.json configs[1] with the metric's SpecAugment masks on): n_mels=128, 64 synthetic 30-s clips of
 float32 PCM per GPU per step.  A "step" is one pass of the hot path over one batch:
 
-    mask draw (Philox, device) -> fused kernel: zero pad, STFT, |X|^2, mel, log10, per-clip max-8 floor, (x+4)/4,
-    time + frequency masks -> x[64, 128, 3000]
+    front-end grid: zero pad, STFT, |X|^2, mel, log10, (x+4)/4, time + frequency masks (intervals drawn in the kernel: Philox)
+    -> fix-up grid: per-clip max-8 floor where it binds, min-value pad -> x[64, 128, 3000]
 
 `value`  : clips/s with the PCM already resident in HBM (CUDA events, max over ranks, whole job).
 `e2e`    : clips/s through the public API with HOST buffers: pinned PCM -> H2D -> kernels -> D2H pinned features.

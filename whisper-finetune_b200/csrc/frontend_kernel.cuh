@@ -1,4 +1,5 @@
-// Fused Whisper audio front end for sm_100a: PCM -> log-mel (+ cut / min-pad / SpecAugment masks), one launch.
+// Fused Whisper audio front end for sm_100a: PCM -> log-mel (+ cut / min-pad / SpecAugment masks): the front-end grid and the
+// lean fix-up grid that runs behind it.
 //
 // Replaces, for a whole batch, the per-clip CPU path of the reference
 //   np.pad -> whisper.audio.log_mel_spectrogram -> mel[:, :T'] -> pad_or_trim -> time/freq masks -> collate
@@ -14,11 +15,12 @@
 //                        upper half of the mirror row 20 - k1 by warp shuffle (both rows sit in one warp);
 //               power  : thread (q, j) pairs Z[j + 20 m] with its mirror Z[400 - j - 20 m] and separates the two real
 //                        spectra: 4|Xa|^2 = |Z[k] + conj Z[400-k]|^2, 4|Xb|^2 = |Z[k] - conj Z[400-k]|^2.
-//   mel phase = thread <-> one mel row x 16 (or 8) consecutive frames: the power tile is stored [bin][frame], so one tap of
+//   mel phase = thread <-> one mel row x 8 consecutive frames per pass: the power tile is stored [bin][frame], so one tap of
 //               the sparse triangular filter is LDS.128 + 2 FFMA2 per 4 frames with the weight held in a register; rows
-//               are banded over the warps by tap count (wft_tables.inc) and each band's tap loop is fully unrolled;
-//               log10 via MUFU.LG2; the FINAL feature (L + 4) / 4 with the SpecAugment masks applied is written once to
-//               `out` as 32-byte stores (STG.256).
+//               are dealt to the warps in groups of 16 by tap count (wft_tables.inc: one or two passes per warp) and each
+//               pass's tap loop is fully unrolled; log10 via MUFU.LG2; the FINAL feature (L + 4) / 4 with the SpecAugment
+//               masks applied is written once to `out` as 32-byte stores (STG.256).  The intervals of the masks may be
+//               drawn in here (Philox keyed by the global clip index), so an augmented batch needs no launch in front.
 //   per-clip max / min = ordered-int red.max into the workspace (fire and forget), plus the tile's own minimum in a
 //               per-tile slot.  The few cells that can only be finished once the WHOLE clip is known -- the max-8 floor
 //               where it binds, the min-value pad of the frames beyond the kept part, silent (all-zero PCM) tiles that
@@ -34,10 +36,11 @@
 //
 // Shared memory per CTA: one 28.8 KB region time-multiplexed as
 //   [audio tile at the top] -> stage A->B exchange -> [power tile at the bottom | next audio tile at the top],
-// plus ~7.8 KB of window / twiddle / mel-weight tables and control words.  The thread order and every stride in here
-// were chosen against measured shared-memory wavefront costs (tools/micro/smem_wavefronts.cu,
-// profiles/r01_smem_wavefront_probe.md): the data pipe, not HBM, is what bounds this kernel.  The hot loop is one DFT20
-// copy per stage and ~2.4 k SASS instructions so that it stays resident in the SM's instruction cache.
+// plus ~8.4 KB of window / twiddle / mel-weight tables, drawn intervals and control words.  The thread order and every stride
+// in here were chosen against measured shared-memory wavefront costs (tools/micro/smem_wavefronts.cu,
+// profiles/r01_smem_wavefront_probe.md): the SM (L1 data pipe 84 %, FMA pipe 51 %, issue 2.3 of 4), not HBM, is what bounds
+// this kernel (profiles/r02_ncu_summary.md, profiles/r02_ab_experiments.md).  The hot loop is one DFT20 copy per stage and
+// ~2.8 k SASS instructions so that it stays resident in the SM's instruction cache.
 #pragma once
 
 #include <cuda_runtime.h>
