@@ -344,6 +344,34 @@ __device__ __forceinline__ float warp_source_coord(int t, int T, int warp_p, int
   }
 }
 
+// The float64 spline once per CTA instead of once per frame: the source map is a cubic in u = (t - xa) / dx on each of its two
+// segments, g(u) = A h00 + B h10 + C h01 + D h11 with A = ya, B = ma dx, C = yb, D = mb dx, i.e.
+//   g(u) = A + B u + (-3A - 2B + 3C - D) u^2 + (2A + B - 2C + D) u^3.
+// One thread derives {xa, 1 / dx, c0 .. c3} for both segments (the three float64 divisions of the knot slopes live here: with
+// every thread evaluating its own frames they were half of the kernel's instructions), every frame is then 1 multiply + 3 FMAs.
+__device__ __forceinline__ void spline_segments(int T, int warp_p, int warp_d, double* __restrict__ seg /* [2][6] */) {
+  const double x1 = static_cast<double>(warp_p), x2 = static_cast<double>(T - 1);
+  const double y0 = -1.0, y1 = static_cast<double>(warp_p - warp_d) * 2.0 / (T - 1.0) - 1.0, y2 = 1.0;
+  const double s0 = (y1 - y0) / x1, s1 = (y2 - y1) / (x2 - x1);
+  const double m0 = s0, m1 = 0.5 * (s0 + s1), m2 = s1;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double xa = k ? x1 : 0.0, dx = k ? (x2 - x1) : x1;
+    const double A = k ? y1 : y0, C = k ? y2 : y1, B = (k ? m1 : m0) * dx, D = (k ? m2 : m1) * dx;
+    seg[6 * k + 0] = xa;
+    seg[6 * k + 1] = 1.0 / dx;
+    seg[6 * k + 2] = A;
+    seg[6 * k + 3] = B;
+    seg[6 * k + 4] = -3.0 * A - 2.0 * B + 3.0 * C - D;
+    seg[6 * k + 5] = 2.0 * A + B - 2.0 * C + D;
+  }
+}
+__device__ __forceinline__ float spline_eval(int t, int warp_p, const double* __restrict__ seg) {
+  const double* c = seg + (t > warp_p ? 6 : 0);
+  const double u = (static_cast<double>(t) - c[0]) * c[1];
+  return static_cast<float>(fma(fma(fma(c[5], u, c[4]), u, c[3]), u, c[2]));
+}
+
 constexpr int kAugThreads = 256;
 constexpr int kAugFramesPerThread = 4;
 constexpr int kAugRowsPerCta = 16;
@@ -354,39 +382,62 @@ constexpr int kAugRowsPerCta = 16;
 // on the L1 data pipe); it evaluates the 4 source coordinates once and walks the 16 rows of its group with 8 independent
 // loads in flight per row (bilinear taps mirror grid_sample's float32 arithmetic, zeros outside).
 template <bool kF32>
-__global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __restrict__ in, float* __restrict__ out,
+__global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                              int32_t R, int32_t T, const int32_t* __restrict__ warp_params,
                                                              const int32_t* __restrict__ mask_params,
                                                              const int32_t* __restrict__ extremes, float mask_value,
                                                              const AugDraw draw) {
   const int b = blockIdx.z;
   __shared__ int s_draw[8];
-  if (draw.enabled) {   // two threads draw the clip's intervals and warp point (before the features are needed)
+  __shared__ double s_seg[12];
+  __shared__ int4 s_row[kAugRowsPerCta];   // per output row of this CTA: source row, its weight, the next row's weight (bits), -
+  // source row(s) of every output row of the group: grid_sample's y coordinate of row r (the identity up to float32 rounding,
+  // which can put a sliver of weight on the next row -- restated, not assumed), once per CTA instead of once per thread and row
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kAugRowsPerCta) {
+    const int r = blockIdx.y * kAugRowsPerCta + (threadIdx.x - 64);
+    const float step = 2.0f / static_cast<float>(R - 1);  // torch.linspace(-1, 1, R)
+    const float gy = (r < R / 2) ? (-1.0f + step * static_cast<float>(r)) : (1.0f - step * static_cast<float>(R - 1 - r));
+    const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
+    const float iy0f = floorf(iy);
+    const int iy0 = static_cast<int>(iy0f), iy1 = iy0 + 1;
+    const float wy1r = iy - iy0f, wy0r = (iy0f + 1.0f) - iy;
+    const bool use0 = iy0 >= 0 && iy0 < R, use1 = iy1 >= 0 && iy1 < R && wy1r != 0.0f;
+    s_row[threadIdx.x - 64] = make_int4(use0 ? iy0 : 0, __float_as_int(use0 ? wy0r : 0.0f), __float_as_int(use1 ? wy1r : 0.0f),
+                                        use1 ? iy1 : -1);
+  }
+  // clip parameters -> shared memory: thread 0 the mask intervals, thread 32 the warp point and the spline's segment
+  // coefficients.  Drawn parameters depend on nothing a grid in front produced: they are ready before this grid's wait.
+  if (draw.enabled) {
     if (threadIdx.x == 0) {
       const int4 m = wft::draw_mask_intervals(draw.seed, draw.clip_offset + static_cast<uint64_t>(b), R, T, draw.tparam, draw.fparam, draw.p);
       s_draw[0] = m.x; s_draw[1] = m.y; s_draw[2] = m.z; s_draw[3] = m.w;
     } else if (threadIdx.x == 32) {
       const int2 w = draw_warp_point(draw.seed, draw.clip_offset + static_cast<uint64_t>(b), T, draw.W, draw.p);
       s_draw[4] = w.x; s_draw[5] = w.y;
+      if (!kF32 && w.x > 0 && w.x < T - 1) spline_segments(T, w.x, w.y, s_seg);
     }
-    __syncthreads();
   }
   // a programmatic dependent of whatever produced `in`: the grid behind this one may be scheduled, this one waits
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!draw.enabled) {
+    if (threadIdx.x == 0) {
+      int4 m = make_int4(0, 0, 0, 0);
+      if (mask_params != nullptr) m = __ldg(reinterpret_cast<const int4*>(mask_params) + b);
+      s_draw[0] = m.x; s_draw[1] = m.y; s_draw[2] = m.z; s_draw[3] = m.w;
+    } else if (threadIdx.x == 32) {
+      int2 w = make_int2(-1, 0);
+      if (warp_params != nullptr) w = __ldg(reinterpret_cast<const int2*>(warp_params) + b);
+      s_draw[4] = w.x; s_draw[5] = w.y;
+      if (!kF32 && w.x > 0 && w.x < T - 1) spline_segments(T, w.x, w.y, s_seg);
+    }
+  }
+  __syncthreads();
   const int tbase = blockIdx.x * kAugThreads * kAugFramesPerThread + threadIdx.x;
   constexpr int kStep = kAugThreads;   // frame k of this thread = tbase + k * kStep
   if (tbase >= T) return;
-  int wp = -1, wd = 0;
-  if (draw.enabled) {
-    wp = s_draw[4]; wd = s_draw[5];
-  } else if (warp_params != nullptr) {
-    const int2 w = __ldg(reinterpret_cast<const int2*>(warp_params) + b);
-    wp = w.x; wd = w.y;
-  }
-  int4 mk = make_int4(0, 0, 0, 0);
-  if (draw.enabled) mk = make_int4(s_draw[0], s_draw[1], s_draw[2], s_draw[3]);
-  else if (mask_params != nullptr) mk = __ldg(reinterpret_cast<const int4*>(mask_params) + b);
+  const int wp = s_draw[4], wd = s_draw[5];
+  const int4 mk = make_int4(s_draw[0], s_draw[1], s_draw[2], s_draw[3]);
   int lo_rows = 0, hi_rows = 0;
   if (extremes != nullptr) {
     const int2 e = __ldg(reinterpret_cast<const int2*>(extremes) + b);
@@ -405,7 +456,7 @@ __global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __res
     int a = t < T ? t : T - 1;
     float wx0 = 1.0f, wx1 = 0.0f;
     if (warp && t < T) {
-      const float gx = warp_source_coord<kF32>(t, T, wp, wd);
+      const float gx = kF32 ? warp_source_coord<true>(t, T, wp, wd) : spline_eval(t, wp, s_seg);
       const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(T - 1);
       const float f = floorf(ix);
       a = static_cast<int>(f);
@@ -418,7 +469,6 @@ __global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __res
     oa[k] = min(max(a, 0), T - 1);
     oc[k] = min(max(c, 0), T - 1);
   }
-  const float step = 2.0f / static_cast<float>(R - 1);  // torch.linspace(-1, 1, R)
   const size_t clip = static_cast<size_t>(b) * R * T;
   const int r_end = min(R, static_cast<int>(blockIdx.y + 1) * kAugRowsPerCta);
   for (int r = blockIdx.y * kAugRowsPerCta; r < r_end; ++r) {
@@ -432,16 +482,11 @@ __global__ void __launch_bounds__(kAugThreads) augment_kernel(const float* __res
 #pragma unroll
       for (int k = 0; k < kAugFramesPerThread; ++k) v[k] = on[k] ? __ldg(row + oa[k]) : mask_value;
     } else {
-      // source row(s): grid_sample's y coordinate of output row r (the identity up to float32 rounding, which can put a
-      // sliver of weight on the next row -- restated, not assumed)
-      const float gy = (r < R / 2) ? (-1.0f + step * static_cast<float>(r)) : (1.0f - step * static_cast<float>(R - 1 - r));
-      const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
-      const float iy0f = floorf(iy);
-      const int iy0 = static_cast<int>(iy0f), iy1 = iy0 + 1;
-      const float wy1r = iy - iy0f, wy0r = (iy0f + 1.0f) - iy;
-      const bool use0 = iy0 >= 0 && iy0 < R, use1 = iy1 >= 0 && iy1 < R && wy1r != 0.0f;
-      const float wy0 = use0 ? wy0r : 0.0f, wy1 = use1 ? wy1r : 0.0f;
-      const float* row0 = in + clip + static_cast<size_t>(use0 ? iy0 : 0) * T;
+      const int4 rr = s_row[r - blockIdx.y * kAugRowsPerCta];
+      const float wy0 = __int_as_float(rr.y), wy1 = __int_as_float(rr.z);
+      const bool use1 = rr.w >= 0;
+      const int iy1 = rr.w;
+      const float* row0 = in + clip + static_cast<size_t>(rr.x) * T;
       // every tap of the row is requested before the first one is used (8 independent loads in flight per thread)
       float t0a[kAugFramesPerThread], t0c[kAugFramesPerThread];
 #pragma unroll
