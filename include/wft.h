@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WFT_ABI_VERSION 8
+#define WFT_ABI_VERSION 9
 
 /* Front-end constants (whisper.audio: SAMPLE_RATE, N_FFT, HOP_LENGTH, CHUNK_LENGTH, N_SAMPLES, N_FRAMES;
  * imported by the reference at data_loader.py:13 and data/utils.py:10). */
@@ -191,6 +191,33 @@ int wft_augment_drawn_f32(const float* in, float* out, int32_t batch, int32_t n_
                           uint64_t clip_offset, int32_t time_mask_param, int32_t freq_mask_param, int32_t time_warp_w, float p,
                           const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream);
 
+/* A production batch as ONE call and TWO grids (every reference config time-warps: configs/config_turbo_best.yaml:97,
+ * config_large_v3_best_muon_ddp4.yaml:120; data_loader.py:273-292 in order): the front-end grid of wft_frontend_forward writes
+ * the un-augmented features into `fe->out` (scratch of the output's shape), and the augmentation epilogue right behind it
+ * finishes every cell as it loads it -- the max-8 floor, the clamp value of tiles that were never computed, the min-value
+ * pad beyond the kept frames: what the fix-up grid of wft_frontend_forward would have rewritten in place -- and writes
+ * warp -> time mask -> frequency mask -> extremes mask of it to `aug->out`.  Bit-identical to wft_frontend_forward followed by
+ * wft_augment_f32 / wft_augment_drawn_f32, one grid and one host call fewer.  `fe->out` holds unspecified values afterwards.
+ * `fe` as for wft_frontend_forward with mask_params == NULL and draw_masks == 0 (the masks belong to `aug`); workspace modes
+ * and launch flags mean the same (WFT_LAUNCH_OVERLAP: independent of the front-end / front-end + augmentation call in front). */
+typedef struct wft_augment_args {
+  float* out;                 /* device [B, n_mels, n_frames_out] contiguous, != fe->out                                   */
+  const int32_t* warp_params; /* device [B,2] or NULL, as for wft_augment_f32                                             */
+  const int32_t* mask_params; /* device [B,4] or NULL                                                                     */
+  const int32_t* extremes;    /* device [B,2] or NULL                                                                     */
+  float mask_value;
+  int32_t spline_f32;
+  int32_t draw;               /* != 0: warp points and intervals drawn inside the kernel (wft_augment_drawn_f32's draws);
+                                 warp_params and mask_params must be NULL                                                 */
+  int32_t draw_time_mask_param;
+  int32_t draw_freq_mask_param;
+  int32_t draw_time_warp_w;
+  float draw_p;
+  uint64_t draw_seed;
+  uint64_t draw_clip_offset;
+} wft_augment_args;
+int wft_frontend_augment_forward(const wft_frontend_args* fe, const wft_augment_args* aug, void* stream);
+
 /* Deep SpecAugment on encoder activations (model/model_utils.py:382-437: permute -> TimeMasking -> FrequencyMasking ->
  * permute on every hooked layer-norm output), without the permutes: x is [batch, seq, dim] contiguous with 16-bit (fp16 /
  * bf16) or 32-bit elements, out[b, s, d] = (t0 <= s < t1 || f0 <= d < f1) ? fill : x[b, s, d].  ONE mask for the whole batch,
@@ -208,6 +235,9 @@ int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t*
 /* Test hook: cap the persistent grids of wft_frontend_forward (front-end and fix-up kernel) at `max_ctas` CTAs (0 = no cap, the
  * default).  Results must not depend on the grid. */
 int wft_debug_set_max_ctas(int32_t max_ctas);
+/* Development hook (tools/cosched_probe.py): pad the front-end CTA's dynamic shared memory by `bytes`, i.e. lower its CTAs per
+ * SM (0 = the default, 6 per SM on B200). */
+int wft_debug_set_extra_smem(int32_t bytes);
 
 #ifdef __cplusplus
 }

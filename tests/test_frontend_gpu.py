@@ -380,6 +380,104 @@ def test_production_batch_with_drawn_epilogue_equals_explicit_composition(wft, c
             outs[k].zero_()
 
 
+@pytest.mark.parametrize("n_mels,dtype,spline", [(128, "f32", "f64"), (80, "i16", "f32")])
+def test_fused_production_call_finishes_cells_like_the_fixup_grid(wft, cuda, n_mels, dtype, spline):
+    """wft_frontend_augment_forward (front-end grid -> epilogue that finishes every cell as it loads it) against
+    wft_frontend_forward (front-end grid + fix-up grid) followed by wft_augment_drawn_f32, bit for bit, on a batch that needs
+    every kind of fix-up: a quiet clip and a clip with exact zeros (the max-8 floor binds), short clips (silent tiles that were
+    never computed), partial-segment cuts (min-value pad), plus the full-length batch without `lengths` (floor-only instance)."""
+    B = 8
+    g = torch.Generator().manual_seed(33)
+    x = (0.1 * torch.randn(B, 480000, generator=g)).clamp(-1, 1)
+    x[0] *= 1e-4
+    x[1, 150000:] = 0.0
+    x[2, :240000] *= 1e-3                      # the floor binds on the first half only
+    lengths = torch.tensor([480000, 480000, 480000, 16000, 300001, 479999, 1000, 480000], dtype=torch.int32)
+    n_valid = torch.tensor([-1, 1200, -1, 90, 3000, 1, -1, 2999], dtype=torch.int32)
+    x[torch.arange(480000)[None, :] >= lengths[:, None]] = 0.0
+    if dtype == "i16":
+        x = (x * 32767).round().to(torch.int16)
+    x, lengths, n_valid = x.to(cuda), lengths.to(cuda), n_valid.to(cuda)
+    ext = torch.tensor([[0, 0], [3, 0], [0, 5], [2, 2], [0, 0], [0, 0], [1, 0], [0, 0]], dtype=torch.int32, device=cuda)
+    for ragged in (True, False):
+        L, NV = (lengths, n_valid) if ragged else (None, None)
+        plain = wft.frontend_forward(x, n_mels, lengths=L, n_valid_frames=NV)
+        want = torch.empty_like(plain)
+        torch.ops.wft.augment_drawn_out(plain, 9, 500, 100, 27, 80, 0.7, ext, 0.0, spline == "f32", want)
+        scratch = torch.full_like(plain, float("nan"))      # whatever the scratch held must not matter
+        got = torch.empty_like(plain)
+        torch.ops.wft.frontend_augment_drawn_out(x, n_mels, 0, L, 3000, NV, 9, 500, 100, 27, 80, 0.7, ext, 0.0, spline == "f32",
+                                                 scratch, got)
+        torch.cuda.synchronize()
+        assert torch.isfinite(got).all()
+        assert torch.equal(got, want), f"ragged={ragged}: {(got != want).sum().item()} cells differ"
+    # the floor really bound somewhere and the pad really was a pad (the test would be vacuous otherwise)
+    assert (plain[0] == plain[0].min()).float().mean().item() > 0.5
+
+
+def test_small_batches_in_flight_never_share_a_scratch_buffer(wft, cuda):
+    """B = 1: whole calls fit on the GPU side by side, so an independent launch may run while calls further back than its
+    predecessor are still in flight.  The launch bookkeeping (ops._LAST_CALL) must keep every buffer of every call since the
+    last waiting launch apart: 50 production calls and 50 masks-only calls on rotating outputs equal the ordinary launches."""
+    params = {"time_mask_param": 100, "freq_mask_param": 27, "time_warp_w": 80, "p": 1.0}
+    fe = wft.FrontEnd(n_mels=128, spec_augment=True, spec_augment_params=params, seed=3)
+    fe_plain = wft.FrontEnd(n_mels=128)
+    g = torch.Generator().manual_seed(5)
+    clips = [(0.1 * torch.randn(1, 480000, generator=g)).clamp(-1, 1).to(cuda) for _ in range(5)]
+    want = [fe(c, clip_offset=k).clone() for k, c in enumerate(clips)]
+    want_plain = [fe_plain(c).clone() for c in clips]
+    torch.cuda.synchronize()
+    outs = [torch.empty_like(want[0]) for _ in range(5)]
+    old = wft.set_overlap(True)
+    try:
+        for i in range(50):
+            fe(clips[i % 5], clip_offset=i % 5, out=outs[i % 5])
+        torch.cuda.synchronize()
+        for k in range(5):
+            assert torch.equal(outs[k], want[k]), f"production call {k}"
+        for i in range(50):
+            fe_plain(clips[i % 5], out=outs[i % 5])
+        torch.cuda.synchronize()
+        for k in range(5):
+            assert torch.equal(outs[k], want_plain[k]), f"plain call {k}"
+    finally:
+        wft.set_overlap(old)
+
+
+def test_front_end_calls_survive_cuda_graph_capture_and_replay(wft, cuda):
+    """A captured front-end step is replayed verbatim: the call must not bake a host-side ring position or an overlap decision
+    into the graph (ops._launch_frontend switches to a private workspace that is zeroed by a memset node of the graph).
+    Replays with new PCM in the captured input buffer equal eager calls, for the masks-only and the production (time-warp) path."""
+    B = 4
+    g = torch.Generator().manual_seed(8)
+    batches = [(0.1 * torch.randn(B, 480000, generator=g)).clamp(-1, 1).to(cuda) for _ in range(3)]
+    p_masks = {"time_mask_param": 100, "freq_mask_param": 43, "p": 1.0}
+    p_warp = dict(p_masks, time_warp_w=80)
+    old = wft.set_overlap(True)    # must be ignored while capturing
+    try:
+        for params in (p_masks, p_warp):
+            fe = wft.FrontEnd(n_mels=128, spec_augment=True, spec_augment_params=params, seed=12)
+            want = [fe(x, clip_offset=40).clone() for x in batches]
+            static_in = batches[0].clone()
+            static_out = torch.empty_like(want[0])
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fe(static_in, clip_offset=40, out=static_out)      # warm-up outside the capture
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fe(static_in, clip_offset=40, out=static_out)
+                fe(static_in, clip_offset=40, out=static_out)      # twice: two calls of one graph must not share counters either
+            for k in (1, 2, 0, 1):
+                static_in.copy_(batches[k])
+                graph.replay()
+                torch.cuda.synchronize()
+                assert torch.equal(static_out, want[k]), f"replay of batch {k} ({'warp' if 'time_warp_w' in params else 'masks'})"
+    finally:
+        wft.set_overlap(old)
+
+
 def _gold(name):
     import os
 
@@ -602,6 +700,9 @@ def test_torch_custom_ops_pass_opcheck(wft, cuda):
     opcheck(torch.ops.wft.frontend_forward_out, (pcm, 80, 0, None, 300, None, masks, 0.0, torch.empty(3, 80, 300, device=cuda)))
     opcheck(torch.ops.wft.frontend_forward_drawn_out,
             (pcm, 80, 0, lengths, 300, nv, 42, 7, 100, 27, 0.5, 0.0, torch.empty(3, 80, 300, device=cuda)))
+    opcheck(torch.ops.wft.frontend_augment_drawn_out,
+            (pcm, 80, 0, lengths, 300, nv, 42, 7, 100, 27, 20, 0.5, None, 0.0, False, torch.empty(3, 80, 300, device=cuda),
+             torch.empty(3, 80, 300, device=cuda)))
     drawn = torch.empty(3, 80, 300, device=cuda)
     torch.ops.wft.frontend_forward_drawn_out(pcm, 80, 0, lengths, 300, nv, 42, 7, 100, 27, 1.0, 0.0, drawn)
     assert torch.equal(drawn, torch.ops.wft.frontend_forward(pcm, 80, 0, lengths, 300, nv,

@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol(wft):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/wft.h but not exported"
     assert sorted(wft._lib.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert wft._lib.load().wft_abi_version() == wft._lib.ABI_VERSION == 8
+    assert wft._lib.load().wft_abi_version() == wft._lib.ABI_VERSION == 9
 
 
 def test_host_validation_without_gpu(wft):

@@ -2,7 +2,7 @@
 """Does the production batch (front end -> fix-up -> augmentation epilogue) gain from running the epilogue of batch k NEXT TO
 the front-end grid of batch k + 1?  The front-end grid is bound by the SM (HBM 40 % busy), the epilogue by memory latency /
 bandwidth; on one stream they only overlap in each other's tails, because six front-end CTAs leave no registers for an
-epilogue CTA.  Here the front-end grid is capped to `cap` CTAs (5, 4, 3 per SM) and the epilogue runs on a second stream.
+epilogue CTA.  Here the front-end CTA's shared memory is padded so that only 5, 4 or 3 fit per SM and the epilogue runs on a second stream.
 
     python tools/cosched_probe.py [steps] -> one JSON object on stdout (profiles/r02_cosched_probe.json)
 """
@@ -29,9 +29,9 @@ def main():
     pcm = [(0.1 * torch.randn(B, 480000, generator=g)).clamp_(-1, 1).to(dev) for _ in range(n_sets)]
     plain = [torch.empty(B, NM, T, device=dev) for _ in range(n_sets)]
     outs = [torch.empty(B, NM, T, device=dev) for _ in range(n_sets)]
-    sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1)
     res = {"batch": B, "steps": steps, "what": "ms per production batch (front end + fix-up + drawn augmentation epilogue), B = 64, "
-           "4 rotating buffer sets; cap = CTAs of the front-end grid (888 = 6 per SM)"}
+           "4 rotating buffer sets; caps = front-end CTAs per SM"}
 
     def timed(body):
         body(0, 8)
@@ -58,6 +58,17 @@ def main():
 
     wft.set_overlap(True)
     res["one_stream_ms"] = timed(one_stream)
+
+    # 1b. the same batch cut into sub-batches whose un-warped features fit in the L2 (ncu: at B = 64 the epilogue re-reads 83 %
+    # of the 98 MB the front end wrote from DRAM)
+    def chunked(c):
+        def body(first, n):
+            for i in range(first, first + n):
+                for a in range(0, B, c):
+                    fe(pcm[i % n_sets][a:a + c], clip_offset=i * B + a, out=outs[i % n_sets][a:a + c])
+        return body
+
+    res["one_stream_chunked_ms"] = {str(c): timed(chunked(c)) for c in (32, 16, 8)}
 
     # 2. front end alone / epilogue alone at the same caps (what each costs when it has the GPU to itself)
     def fe_only(first, n):
@@ -94,21 +105,23 @@ def main():
         cur.wait_stream(sa)
         cur.wait_stream(sb)
 
+    # the cap that matters is CTAs PER SM (independent batches overlap, so a smaller grid alone just lets the next batch's CTAs
+    # in): pad the front-end CTA's shared memory so that only 5 / 4 / 3 fit
     res["caps"] = {}
-    for cap in (888, 740, 592, 444):
-        lib.wft_debug_set_max_ctas(cap)
-        r = {"front_end_alone_ms": timed(fe_only), "two_streams_ms": timed(two_streams)}
-        res["caps"][str(cap)] = r
-    lib.wft_debug_set_max_ctas(0)
+    for per_sm, extra in ((6, 0), (5, 6 * 1024), (4, 16 * 1024), (3, 34 * 1024)):
+        lib.wft_debug_set_extra_smem(extra)
+        r = {"front_end_alone_ms": timed(fe_only), "two_streams_ms": timed(two_streams), "one_stream_ms": timed(one_stream)}
+        res["caps"][str(per_sm)] = r
+    lib.wft_debug_set_extra_smem(0)
     wft.set_overlap(False)
     # the two-stream result must equal the one-stream result
     torch.cuda.synchronize()
     ref = fe(pcm[0], clip_offset=0).clone()
-    lib.wft_debug_set_max_ctas(740)
+    lib.wft_debug_set_extra_smem(6 * 1024)
     wft.set_overlap(True)
     two_streams(0, 4)
     torch.cuda.synchronize()
-    lib.wft_debug_set_max_ctas(0)
+    lib.wft_debug_set_extra_smem(0)
     res["two_streams_equal_one_stream"] = bool(torch.equal(ref, outs[0]))
     res["clips_per_s"] = {"one_stream": B / res["one_stream_ms"] * 1e3,
                           **{f"two_streams_cap_{k}": B / v["two_streams_ms"] * 1e3 for k, v in res["caps"].items()}}

@@ -18,7 +18,7 @@ WFT_WS_PHASES = 16
 WFT_LAUNCH_PDL, WFT_LAUNCH_OVERLAP = 1, 2
 WFT_ERR_INVALID = -1
 WFT_ERR_CUDA = -2
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class FrontendArgs(Structure):
@@ -51,12 +51,33 @@ class FrontendArgs(Structure):
     ]
 
 
+class AugmentArgs(Structure):
+    """Mirror of ``struct wft_augment_args`` (include/wft.h)."""
+
+    _fields_ = [
+        ("out", c_void_p),
+        ("warp_params", c_void_p),
+        ("mask_params", c_void_p),
+        ("extremes", c_void_p),
+        ("mask_value", c_float),
+        ("spline_f32", c_int32),
+        ("draw", c_int32),
+        ("draw_time_mask_param", c_int32),
+        ("draw_freq_mask_param", c_int32),
+        ("draw_time_warp_w", c_int32),
+        ("draw_p", c_float),
+        ("draw_seed", c_uint64),
+        ("draw_clip_offset", c_uint64),
+    ]
+
+
 # name -> (restype, argtypes); tests check that the library exports exactly these (and the header declares them)
 SIGNATURES = {
     "wft_abi_version": (c_int, []),
     "wft_last_error": (c_char_p, []),
     "wft_frontend_workspace_bytes": (c_int, [c_int32, c_int32, c_int32, POINTER(c_size_t)]),
     "wft_frontend_forward": (c_int, [POINTER(FrontendArgs), c_void_p]),
+    "wft_frontend_augment_forward": (c_int, [POINTER(FrontendArgs), POINTER(AugmentArgs), c_void_p]),
     "wft_pad_or_trim_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "wft_specaug_apply_f32": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_float, c_void_p]),
     "wft_specaug_draw": (c_int, [c_uint64, c_uint64, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
@@ -72,6 +93,7 @@ SIGNATURES = {
     "wft_launch_count": (c_int64, [c_int]),
     "wft_frontend_grid": (c_int, [c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "wft_debug_set_max_ctas": (c_int, [c_int32]),
+    "wft_debug_set_extra_smem": (c_int, [c_int32]),
 }
 
 _lib = None

@@ -17,6 +17,7 @@ thread_local std::string g_last_error;
 thread_local int64_t g_launches = 0;
 int g_debug_chunk = 0;      // WFT_DEBUG_CHUNK (development): force the tiles-per-claim of the fused kernel
 int g_debug_max_ctas = 0;   // wft_debug_set_max_ctas: caps the persistent grids (results must not depend on the grid)
+int g_debug_extra_smem = 0; // wft_debug_set_extra_smem: pads the front-end CTA's shared memory, i.e. lowers its CTAs per SM
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -60,7 +61,7 @@ int grid_for(KernelT kernel, GridInfo* cache, int* ctas) {
 }
 
 template <int NM, typename PcmT>
-int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launch_flags) {
+int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launch_flags, bool with_fixup) {
   static GridInfo cache[64];
   static const bool env_read = [] {
     if (const char* e = getenv("WFT_DEBUG_CHUNK")) g_debug_chunk = atoi(e);
@@ -70,6 +71,14 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launc
   int ctas = 0;
   int rc = grid_for(wft::frontend_kernel<NM, PcmT>, cache, &ctas);
   if (rc != WFT_OK) return rc;
+  if (g_debug_extra_smem > 0) {   // fewer front-end CTAs per SM: the rest of the SM is left to whatever runs next to this grid
+    int per_sm = 0, sms = 0, dev = 0;
+    WFT_CUDA(cudaGetDevice(&dev));
+    WFT_CUDA(cudaFuncSetAttribute(wft::frontend_kernel<NM, PcmT>, cudaFuncAttributeMaxDynamicSharedMemorySize, wft::kSmemBytes + g_debug_extra_smem));
+    WFT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wft::frontend_kernel<NM, PcmT>, wft::kThreads, wft::kSmemBytes + g_debug_extra_smem));
+    WFT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (per_sm >= 1) ctas = per_sm * sms;
+  }
   const int ctas_full = ctas;
   if (ctas > p.total_tiles) ctas = p.total_tiles;
   if (g_debug_max_ctas > 0 && ctas > g_debug_max_ctas) ctas = g_debug_max_ctas;
@@ -83,7 +92,7 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launc
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(wft::kThreads);
-  cfg.dynamicSmemBytes = wft::kSmemBytes;
+  cfg.dynamicSmemBytes = wft::kSmemBytes + (g_debug_extra_smem > 0 ? g_debug_extra_smem : 0);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -92,6 +101,7 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launc
   cfg.numAttrs = (launch_flags & (WFT_LAUNCH_PDL | WFT_LAUNCH_OVERLAP)) ? 1 : 0;
   WFT_CUDA(cudaLaunchKernelEx(&cfg, wft::frontend_kernel<NM, PcmT>, q));
   ++g_launches;
+  if (!with_fixup) return WFT_OK;   // wft_frontend_augment_forward: the epilogue grid behind this one finishes the cells on load
 
   // the fix-up grid right behind it: always a programmatic dependent (it waits for the front-end grid on the device), one
   // lean CTA per SM -- 128 threads x 32 registers and no shared memory fit NEXT TO six front-end CTAs, so the blocks that
@@ -376,19 +386,42 @@ constexpr int kAugThreads = 256;
 constexpr int kAugFramesPerThread = 4;
 constexpr int kAugRowsPerCta = 16;
 
+// kFix instances of the epilogue run directly behind a front-end grid that was launched WITHOUT its fix-up grid
+// (wft_frontend_augment_forward): `in` then holds what the front-end kernel wrote -- final features except for what can only
+// be finished once the whole clip is known -- and every tap is finished on load exactly like wft::fixup_tile would have
+// rewritten it: max(v, floor) for the kept frames, the clamp value for tiles that were never computed (silent / pad-only),
+// the min-value pad beyond the kept frames (data/utils.py:380-404).
+struct AugFix {
+  const wft::ClipStat* stats;    // this call's clip statistics (complete once the front-end grid is)
+  const int32_t* lengths;
+  const int32_t* n_valid;
+  int32_t n_samples, n_total, n_frames;   // of the front-end call (frames the clip really has; T is n_frames_out)
+};
+
 // grid = (frame blocks of 1024, row groups of 16, clips); a thread owns 4 output frames, 256 apart (lane <-> consecutive frames:
 // a warp's store is one 128-byte line and the two source taps of a smooth, monotone map fall into one or two lines -- with 4
 // ADJACENT frames per thread every scalar load of a warp was spread over 4-8 lines and the kernel sat at 0.40 of the HBM peak
 // on the L1 data pipe); it evaluates the 4 source coordinates once and walks the 16 rows of its group with 8 independent
 // loads in flight per row (bilinear taps mirror grid_sample's float32 arithmetic, zeros outside).
-template <bool kF32>
-__global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __restrict__ in, float* __restrict__ out,
+// the value fixup_tile would have left in a cell the front-end kernel wrote as v (kind: 0 = computed, 1 = never computed, 2 = pad)
+// (s_fix: floor feature, pad value, kept frames, clip length, clamp feature; the last two values a ragged clip needs are read
+// from shared memory where they are used -- a register each would spill the float64-spline instance)
+__device__ __forceinline__ float aug_finish(float v, uint32_t kind, bool ragged, float floorn, const int* __restrict__ s_fix) {
+  if (!ragged) return fmaxf(v, floorn);
+  return kind == 2u ? __int_as_float(s_fix[1]) : fmaxf(kind == 1u ? __int_as_float(s_fix[4]) : v, floorn);
+}
+
+// kFix: 0 = `in` holds finished features; 1 = finish on load, full-length clips without a cut (the floor is all there is);
+// 2 = finish on load, ragged batch (lengths / cuts / output longer than the clip: per-tap kinds; 64 registers, 4 CTAs per SM)
+template <bool kF32, int kFix>
+__global__ void __launch_bounds__(kAugThreads, kFix == 2 ? 4 : 5) augment_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                              int32_t R, int32_t T, const int32_t* __restrict__ warp_params,
                                                              const int32_t* __restrict__ mask_params,
                                                              const int32_t* __restrict__ extremes, float mask_value,
-                                                             const AugDraw draw) {
+                                                             const AugDraw draw, const AugFix fix) {
   const int b = blockIdx.z;
   __shared__ int s_draw[8];
+  __shared__ int s_fix[5];    // kFix: floor feature, pad value (float bits), kept frames, clip length in samples, clamp feature
   __shared__ double s_seg[12];
   __shared__ int4 s_row[kAugRowsPerCta];   // per output row of this CTA: source row, its weight, the next row's weight (bits), -
   // source row(s) of every output row of the group: grid_sample's y coordinate of row r (the identity up to float32 rounding,
@@ -432,6 +465,20 @@ __global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __
       if (!kF32 && w.x > 0 && w.x < T - 1) spline_segments(T, w.x, w.y, s_seg);
     }
   }
+  if (kFix != 0 && threadIdx.x == 96) {   // the front-end grid is complete (griddepcontrol.wait above): its statistics are final
+    const float floorn = wft::floor_feature(wft::dec_ordered(__ldcg(&fix.stats[b].max_enc)));
+    const float padv = fmaxf(wft::feature_of_l2(wft::dec_ordered(~__ldcg(&fix.stats[b].min_inv))), floorn);
+    int len = fix.n_samples;
+    if (fix.lengths != nullptr) {
+      const int l = __ldg(fix.lengths + b);
+      len = l < 0 ? 0 : (l < len ? l : len);
+    }
+    s_fix[0] = __float_as_int(floorn);
+    s_fix[1] = __float_as_int(padv);
+    s_fix[2] = wft::kept_frames(fix.n_valid, b, fix.n_frames);
+    s_fix[3] = len;
+    s_fix[4] = __float_as_int(wft::feature_of_l2(wft::silent_l2()));
+  }
   __syncthreads();
   const int tbase = blockIdx.x * kAugThreads * kAugFramesPerThread + threadIdx.x;
   constexpr int kStep = kAugThreads;   // frame k of this thread = tbase + k * kStep
@@ -446,7 +493,8 @@ __global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __
   const bool warp = wp > 0 && wp < T - 1;          // anything else (the draw's "gate rejected" marker is -1) = no warp
   // per frame, once: the two source columns (clamped into the row so that every load is unconditional) and their weights
   // (0 for a tap that falls outside: "zeros" padding -- 0 * finite contributes exactly nothing), and whether the cell is live
-  int oa[kAugFramesPerThread], oc[kAugFramesPerThread];
+  int oa[kAugFramesPerThread];
+  uint32_t cstep = 0;   // bit k: the second tap of frame k sits one column right of the first (0 where both clamp to one column)
   float wa[kAugFramesPerThread], wc[kAugFramesPerThread];
   bool on[kAugFramesPerThread];
 #pragma unroll
@@ -467,8 +515,28 @@ __global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __
     wa[k] = (a >= 0 && a < T) ? wx0 : 0.0f;
     wc[k] = (c >= 0 && c < T) ? wx1 : 0.0f;
     oa[k] = min(max(a, 0), T - 1);
-    oc[k] = min(max(c, 0), T - 1);
+    cstep |= static_cast<uint32_t>(min(max(c, 0), T - 1) - oa[k]) << k;
   }
+  // kFix: what a tap at source column oa[k] / oc[k] still needs (per frame, once): 0 = floor only, 1 = never computed (the
+  // clamp value, then the floor), 2 = beyond the kept frames (the pad value).  Full-length clips without a cut need no table.
+  float floorn = 0.0f;
+  bool ragged = false;
+  uint32_t kinds = 0;   // 2 bits per tap: tap a of frame k at bit 4k, tap c at bit 4k + 2
+  if constexpr (kFix != 0) floorn = __int_as_float(s_fix[0]);
+  if constexpr (kFix == 2) {
+    const int keep = s_fix[2], len = s_fix[3];
+    ragged = keep < T || len < fix.n_samples || fix.n_frames < T;
+    if (ragged) {
+#pragma unroll
+      for (int k = 0; k < kAugFramesPerThread; ++k) {
+        const int a = oa[k], c = oa[k] + static_cast<int>((cstep >> k) & 1u);
+        const uint32_t ka = a >= keep ? 2u : (wft::tile_is_silent(a & ~(wft::kTileFrames - 1), len, fix.n_total) ? 1u : 0u);
+        const uint32_t kc = c >= keep ? 2u : (wft::tile_is_silent(c & ~(wft::kTileFrames - 1), len, fix.n_total) ? 1u : 0u);
+        kinds |= (ka | (kc << 2)) << (4 * k);
+      }
+    }
+  }
+#define AUG_FINISH(v, k, tap) aug_finish(v, (kinds >> (4 * (k) + 2 * (tap))) & 3u, ragged, floorn, s_fix)
   const size_t clip = static_cast<size_t>(b) * R * T;
   const int r_end = min(R, static_cast<int>(blockIdx.y + 1) * kAugRowsPerCta);
   for (int r = blockIdx.y * kAugRowsPerCta; r < r_end; ++r) {
@@ -480,7 +548,10 @@ __global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __
     } else if (!warp) {
       const float* row = in + clip + static_cast<size_t>(r) * T;
 #pragma unroll
-      for (int k = 0; k < kAugFramesPerThread; ++k) v[k] = on[k] ? __ldg(row + oa[k]) : mask_value;
+      for (int k = 0; k < kAugFramesPerThread; ++k) {
+        if constexpr (kFix != 0) v[k] = on[k] ? AUG_FINISH(__ldg(row + oa[k]), k, 0) : mask_value;
+        else v[k] = on[k] ? __ldg(row + oa[k]) : mask_value;
+      }
     } else {
       const int4 rr = s_row[r - blockIdx.y * kAugRowsPerCta];
       const float wy0 = __int_as_float(rr.y), wy1 = __int_as_float(rr.z);
@@ -492,7 +563,14 @@ __global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __
 #pragma unroll
       for (int k = 0; k < kAugFramesPerThread; ++k) {
         t0a[k] = __ldg(row0 + oa[k]);
-        t0c[k] = __ldg(row0 + oc[k]);
+        t0c[k] = __ldg(row0 + oa[k] + ((cstep >> k) & 1u));
+      }
+      if constexpr (kFix != 0) {
+#pragma unroll
+        for (int k = 0; k < kAugFramesPerThread; ++k) {
+          t0a[k] = AUG_FINISH(t0a[k], k, 0);
+          t0c[k] = AUG_FINISH(t0c[k], k, 1);
+        }
       }
       if (!use1) {      // warp-uniform (depends on r alone); taps accumulate in grid_sample's order
 #pragma unroll
@@ -508,7 +586,14 @@ __global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __
 #pragma unroll
         for (int k = 0; k < kAugFramesPerThread; ++k) {
           t1a[k] = __ldg(row1 + oa[k]);
-          t1c[k] = __ldg(row1 + oc[k]);
+          t1c[k] = __ldg(row1 + oa[k] + ((cstep >> k) & 1u));
+        }
+        if constexpr (kFix != 0) {
+#pragma unroll
+          for (int k = 0; k < kAugFramesPerThread; ++k) {
+            t1a[k] = AUG_FINISH(t1a[k], k, 0);
+            t1c[k] = AUG_FINISH(t1c[k], k, 1);
+          }
         }
 #pragma unroll
         for (int k = 0; k < kAugFramesPerThread; ++k) {
@@ -527,6 +612,8 @@ __global__ void __launch_bounds__(kAugThreads, 5) augment_kernel(const float* __
       if (tbase + k * kStep < T) dst[k * kStep] = v[k];
   }
 }
+
+#undef AUG_FINISH
 
 int grid_1d(int64_t n, int threads) {
   int64_t g = (n + threads - 1) / threads;
@@ -557,6 +644,11 @@ int wft_debug_set_max_ctas(int32_t max_ctas) {
   return WFT_OK;
 }
 
+int wft_debug_set_extra_smem(int32_t bytes) {
+  g_debug_extra_smem = bytes > 0 ? bytes : 0;
+  return WFT_OK;
+}
+
 int64_t wft_launch_count(int reset) {
   const int64_t v = g_launches;
   if (reset) g_launches = 0;
@@ -577,9 +669,9 @@ int wft_frontend_workspace_bytes(int32_t batch, int32_t n_samples_total, int32_t
   return WFT_OK;
 }
 
-int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
+// validate, lay out the workspace, launch the front-end grid (and, with_fixup, its fix-up grid); *used = what was launched
+static int frontend_forward_impl(const wft_frontend_args* a, cudaStream_t stream, bool with_fixup, wft::FrontendParams* used) {
   if (a == nullptr) return fail(WFT_ERR_INVALID, "args is NULL");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (a->pcm == nullptr || a->out == nullptr || a->workspace == nullptr)
     return fail(WFT_ERR_INVALID, "pcm, out and workspace must be non-NULL device pointers");
   if (a->n_mels != 80 && a->n_mels != 128) return fail(WFT_ERR_INVALID, "Unsupported n_mels: " + std::to_string(a->n_mels));
@@ -665,12 +757,17 @@ int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
     p.draw_fparam = a->draw_freq_mask_param;
     p.draw_p = a->draw_p;
   }
+  if (used != nullptr) *used = p;
   if (a->n_mels == 128) {
-    return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<128, float>(p, stream, launch_flags)
-                                       : launch_frontend<128, int16_t>(p, stream, launch_flags);
+    return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<128, float>(p, stream, launch_flags, with_fixup)
+                                       : launch_frontend<128, int16_t>(p, stream, launch_flags, with_fixup);
   }
-  return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<80, float>(p, stream, launch_flags)
-                                     : launch_frontend<80, int16_t>(p, stream, launch_flags);
+  return a->pcm_dtype == WFT_PCM_F32 ? launch_frontend<80, float>(p, stream, launch_flags, with_fixup)
+                                     : launch_frontend<80, int16_t>(p, stream, launch_flags, with_fixup);
+}
+
+int wft_frontend_forward(const wft_frontend_args* a, void* stream_) {
+  return frontend_forward_impl(a, static_cast<cudaStream_t>(stream_), true, nullptr);
 }
 
 int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t* threads, int32_t* smem_bytes) {
@@ -783,7 +880,7 @@ int wft_specaug_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t
 
 static int launch_augment(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
                           const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32,
-                          const AugDraw& draw, cudaStream_t stream) {
+                          const AugDraw& draw, cudaStream_t stream, const AugFix* fix = nullptr) {
   if (batch < 0 || n_rows < 0 || n_frames < 0) return fail(WFT_ERR_INVALID, "negative extent");
   if (static_cast<int64_t>(batch) * n_rows * n_frames == 0) return WFT_OK;
   if (in == nullptr || out == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
@@ -811,10 +908,19 @@ static int launch_augment(const float* in, float* out, int32_t batch, int32_t n_
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (spline_f32)
-    WFT_CUDA(cudaLaunchKernelEx(&cfg, augment_kernel<true>, in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, draw));
-  else
-    WFT_CUDA(cudaLaunchKernelEx(&cfg, augment_kernel<false>, in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, draw));
+  const AugFix fx = fix != nullptr ? *fix : AugFix{};
+  // (same rule as the fix-up grid's heavy instance: lengths / cuts / an output longer than the clip)
+  const bool ragged = fix != nullptr && (fix->lengths != nullptr || fix->n_valid != nullptr || n_frames > fix->n_frames);
+#define WFT_AUG_LAUNCH(F32, FIX) \
+  WFT_CUDA(cudaLaunchKernelEx(&cfg, augment_kernel<F32, FIX>, in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, draw, fx))
+  if (fix == nullptr) {
+    if (spline_f32) WFT_AUG_LAUNCH(true, 0); else WFT_AUG_LAUNCH(false, 0);
+  } else if (!ragged) {
+    if (spline_f32) WFT_AUG_LAUNCH(true, 1); else WFT_AUG_LAUNCH(false, 1);
+  } else {
+    if (spline_f32) WFT_AUG_LAUNCH(true, 2); else WFT_AUG_LAUNCH(false, 2);
+  }
+#undef WFT_AUG_LAUNCH
   ++g_launches;
   return WFT_OK;
 }
@@ -835,6 +941,31 @@ int wft_augment_drawn_f32(const float* in, float* out, int32_t batch, int32_t n_
   d.seed = seed; d.clip_offset = clip_offset;
   return launch_augment(in, out, batch, n_rows, n_frames, nullptr, nullptr, extremes, mask_value, spline_f32, d,
                         static_cast<cudaStream_t>(stream_));
+}
+
+int wft_frontend_augment_forward(const wft_frontend_args* a, const wft_augment_args* g, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (a == nullptr || g == nullptr) return fail(WFT_ERR_INVALID, "args is NULL");
+  if (g->out == nullptr) return fail(WFT_ERR_INVALID, "augment out is NULL");
+  if (a->mask_params != nullptr || a->draw_masks != 0)
+    return fail(WFT_ERR_INVALID, "the masks of a front-end + augmentation call belong to the augmentation arguments");
+  if (g->out == a->out) return fail(WFT_ERR_INVALID, "the un-augmented features (scratch) and the output must be different buffers");
+  AugDraw d{};
+  if (g->draw != 0) {
+    if (g->warp_params != nullptr || g->mask_params != nullptr) return fail(WFT_ERR_INVALID, "draw and explicit parameters are mutually exclusive");
+    if (!(g->draw_p >= 0.0f && g->draw_p <= 1.0f)) return fail(WFT_ERR_INVALID, "spec_augment p must be between 0 and 1");
+    if (g->draw_time_warp_w < 0) return fail(WFT_ERR_INVALID, "time_warp_w must be >= 0");
+    d.enabled = 1; d.tparam = g->draw_time_mask_param; d.fparam = g->draw_freq_mask_param; d.W = g->draw_time_warp_w; d.p = g->draw_p;
+    d.seed = g->draw_seed; d.clip_offset = g->draw_clip_offset;
+  }
+  wft::FrontendParams used{};
+  int rc = frontend_forward_impl(a, stream, false, &used);
+  if (rc != WFT_OK) return rc;
+  AugFix fix{};
+  fix.stats = used.stats; fix.lengths = used.lengths; fix.n_valid = used.n_valid;
+  fix.n_samples = used.n_samples; fix.n_total = used.n_total; fix.n_frames = used.n_frames;
+  return launch_augment(a->out, g->out, a->batch, a->n_mels, used.n_frames_out, g->warp_params, g->mask_params, g->extremes,
+                        g->mask_value, g->spline_f32, d, stream, &fix);
 }
 
 int wft_time_warp_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames,

@@ -50,7 +50,7 @@ class FrontEnd:
             self.freq_mask_param = int(params["freq_mask_param"])
             if params.get("time_warp", True):
                 self.time_warp_w = int(params.get("time_warp_w", 0))
-        self._scratch = {}        # (stream, batch, turn & 1) -> un-warped features of a time-warped batch
+        self._scratch = {}        # (stream, batch, turn % K) -> un-warped features of a time-warped batch
         self._scratch_turn = {}
 
     def __call__(self, pcm: torch.Tensor, lengths=None, n_valid_frames=None, clip_offset: int = 0,
@@ -85,28 +85,34 @@ class FrontEnd:
             return out
         if (mask_params is None and augment is None and self.spec_augment and self.spec_augment_p > 0.0 and self.time_warp_w > 0
                 and pcm.dtype in (torch.float32, torch.int16) and pcm.stride(1) == 1):
-            # the production batch (configs/*: time_warp_w = 80): front-end grid -> fix-up grid -> ONE epilogue grid that draws the
-            # clip's warp point and mask intervals itself.  The un-warped features go through one of two alternating scratch
-            # buffers, so that the next batch's front-end grid may already run under this batch's epilogue (wft.set_overlap)
+            # the production batch (configs/*: time_warp_w = 80) as ONE call: front-end grid -> ONE epilogue grid that finishes the
+            # cells as it loads them (floor / pad / silent tiles) and draws the clip's warp point and mask intervals itself.  The
+            # un-warped features go through a rotation of scratch buffers (up to 1 GiB of them, 2 .. 16), so that the following
+            # batches' front-end grids may run under this batch's epilogue (wft.set_overlap: an independent launch has to stay
+            # clear of every call that may still be in flight, see ops._LAST_CALL)
             from .audio import as_i32_on
 
-            st = torch.cuda.current_stream(self.device).cuda_stream      # scratch is per stream: stream order protects it
-            turn = self._scratch_turn.get(st, 0)
-            self._scratch_turn[st] = turn + 1
-            key = (st, B, turn & 1)
-            plain = self._scratch.get(key)
-            if plain is None:
-                for k in [k for k in self._scratch if k[0] == st and k[1] != B]:   # batch size changed on this stream
-                    del self._scratch[k]
-                plain = self._scratch[key] = torch.empty((B, self.n_mels, self.n_frames), dtype=torch.float32, device=self.device)
+            if torch.cuda.is_current_stream_capturing():
+                plain = torch.empty((B, self.n_mels, self.n_frames), dtype=torch.float32, device=self.device)   # the graph's own
+            else:
+                st = torch.cuda.current_stream(self.device).cuda_stream      # scratch is per stream: stream order protects it
+                turn = self._scratch_turn.get(st, 0)
+                self._scratch_turn[st] = turn + 1
+                nbytes = B * self.n_mels * self.n_frames * 4
+                key = (st, B, turn % max(2, min(16, (1 << 30) // nbytes)))
+                plain = self._scratch.get(key)
+                if plain is None:
+                    for k in [k for k in self._scratch if k[0] == st and k[1] != B]:   # batch size changed on this stream
+                        del self._scratch[k]
+                    plain = self._scratch[key] = torch.empty((B, self.n_mels, self.n_frames), dtype=torch.float32, device=self.device)
             if out is None:
                 out = torch.empty((B, self.n_mels, self.n_frames), dtype=torch.float32, device=self.device)
-            torch.ops.wft.frontend_forward_out(pcm, self.n_mels, self.n_samples - N, as_i32_on(lengths, self.device, (B,), "lengths"),
-                                               self.n_frames, as_i32_on(n_valid_frames, self.device, (B,), "n_valid_frames"),
-                                               None, 0.0, plain)
             ext = None if extremes is None else torch.as_tensor(extremes, dtype=torch.int32).to(self.device).contiguous()
-            torch.ops.wft.augment_drawn_out(plain, self.seed, int(clip_offset), self.time_mask_param, self.freq_mask_param,
-                                            self.time_warp_w, self.spec_augment_p, ext, 0.0, self.warp_spline == "f32", out)
+            torch.ops.wft.frontend_augment_drawn_out(pcm, self.n_mels, self.n_samples - N, as_i32_on(lengths, self.device, (B,), "lengths"),
+                                                     self.n_frames, as_i32_on(n_valid_frames, self.device, (B,), "n_valid_frames"),
+                                                     self.seed, int(clip_offset), self.time_mask_param, self.freq_mask_param,
+                                                     self.time_warp_w, self.spec_augment_p, ext, 0.0, self.warp_spline == "f32",
+                                                     plain, out)
             return out
         gate = None
         p_draw = self.spec_augment_p

@@ -30,7 +30,13 @@ from torch import Tensor
 from . import _lib
 
 HOP_LENGTH = 160
-_LAST_CALL = {}   # (device, stream) -> byte ranges the last front-end call enqueued there reads / writes
+# (device, stream) -> [(reads, writes), ...]: byte ranges of every front-end call enqueued there since the last launch that WAITED
+# for everything in front of it (an ordinary launch, the memset of a wrapping workspace ring, any other op of this package).
+# An independent launch (WFT_LAUNCH_OVERLAP) never waits, so grids of ALL of these calls may still be running next to it --
+# with small batches several whole calls are resident at once -- and it has to stay clear of every one of them, not just of
+# the call directly in front.  (Grids of a stream complete in order, so a launch that waits for its predecessor has waited for
+# all of them.)
+_LAST_CALL = {}
 _ELEM_BYTES = {torch.float32: 4, torch.float16: 2, torch.bfloat16: 2}
 
 
@@ -105,8 +111,10 @@ def _disjoint(a, b) -> bool:
 
 def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[Tensor], n_frames_out: int,
                      n_valid_frames: Optional[Tensor], mask_params: Optional[Tensor], mask_value: float, out: Tensor,
-                     draw=None) -> None:
-    """``draw`` = (seed, clip_offset, time_mask_param, freq_mask_param, p): the intervals are drawn inside the call."""
+                     draw=None, aug=None) -> None:
+    """``draw`` = (seed, clip_offset, time_mask_param, freq_mask_param, p): the intervals are drawn inside the call.
+    ``aug`` = ``_lib.AugmentArgs`` + the tensors it points to: the call is ``wft_frontend_augment_forward`` (front-end grid ->
+    augmentation epilogue that finishes the cells on load; ``out`` is then the scratch of the un-augmented features)."""
     lib = _lib.load()
     B, N = pcm.shape
     dev = pcm.device
@@ -114,18 +122,30 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
         need = ctypes.c_size_t(0)
         _lib.check(lib.wft_frontend_workspace_bytes(B, N + padding, out.shape[2], ctypes.byref(need)))
         stream = torch.cuda.current_stream(dev).cuda_stream
-        key, ent, mode = _workspace(dev, stream, B, need.value)
-        ws = ent[0]
         flags = _lib.WFT_LAUNCH_PDL if _PDL["enabled"] else 0
-        reads = [_span(t) for t in (pcm, lengths, n_valid_frames, mask_params)]
-        writes = [_span(out)]
-        prev = _LAST_CALL.get((dev.index, stream))
-        if _OVERLAP["enabled"] and prev is not None:
-            prev_reads, prev_writes = prev
-            if (all(_disjoint(w, q) for w in writes for q in prev_writes + prev_reads)
-                    and all(_disjoint(r, q) for r in reads for q in prev_writes)):
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA graph capture: what is recorded now is replayed verbatim, so neither the ring position (a host-side count)
+            # nor the overlap decision may be baked in.  The call gets a workspace of its own from the graph's pool and the
+            # mode whose zeroing is part of the call itself (a memset node in front of the kernels).
+            key, mode = None, _lib.WFT_WS_MEMSET
+            ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            _LAST_CALL.pop((dev.index, stream), None)
+        else:
+            key, ent, mode = _workspace(dev, stream, B, need.value)
+            ws = ent[0]
+            reads = [_span(t) for t in (pcm, lengths, n_valid_frames, mask_params)]
+            writes = [_span(out)]
+            if aug is not None:
+                reads += [_span(t) for t in aug[1]]
+                writes += [_span(aug[2])]
+            hist = _LAST_CALL.get((dev.index, stream))
+            if (_OVERLAP["enabled"] and hist and mode != _lib.WFT_WS_RING       # (ring position 0: the memset waits anyway)
+                    and all(_disjoint(w, q) for prev_reads, prev_writes in hist for w in writes for q in prev_writes + prev_reads)
+                    and all(_disjoint(r, q) for _, prev_writes in hist for r in reads for q in prev_writes)):
                 flags |= _lib.WFT_LAUNCH_OVERLAP
-        _LAST_CALL[(dev.index, stream)] = (reads, writes)
+                hist.append((reads, writes))
+            else:
+                _LAST_CALL[(dev.index, stream)] = [(reads, writes)]
         args = _lib.FrontendArgs(
             pcm=pcm.data_ptr(),
             pcm_dtype=_lib.WFT_PCM_F32 if pcm.dtype == torch.float32 else _lib.WFT_PCM_I16,
@@ -150,8 +170,11 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
             args.draw_seed = draw[0] & (2**64 - 1)
             args.draw_clip_offset = draw[1] & (2**64 - 1)
             args.draw_time_mask_param, args.draw_freq_mask_param, args.draw_p = int(draw[2]), int(draw[3]), float(draw[4])
-        rc = lib.wft_frontend_forward(ctypes.byref(args), stream)
-        if rc != 0:
+        if aug is not None:
+            rc = lib.wft_frontend_augment_forward(ctypes.byref(args), ctypes.byref(aug[0]), stream)
+        else:
+            rc = lib.wft_frontend_forward(ctypes.byref(args), stream)
+        if rc != 0 and key is not None:
             _WORKSPACES.pop(key, None)   # a launch that did not happen leaves the ring bookkeeping undefined
         _lib.check(rc)
 
@@ -222,6 +245,42 @@ def _(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, seed, clip_of
     return None
 
 
+@torch.library.custom_op("wft::frontend_augment_drawn_out", mutates_args=("scratch", "out"), device_types="cuda")
+def frontend_augment_drawn_out(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[Tensor], n_frames_out: int,
+                               n_valid_frames: Optional[Tensor], seed: int, clip_offset: int, time_mask_param: int,
+                               freq_mask_param: int, time_warp_w: int, p: float, extremes: Optional[Tensor], mask_value: float,
+                               spline_f32: bool, scratch: Tensor, out: Tensor) -> None:
+    """A production batch (every reference config time-warps) as ONE call and TWO grids: the front-end grid writes the
+    un-augmented features to ``scratch``, the augmentation epilogue behind it finishes every cell as it loads it (floor, pad,
+    silent tiles: what the fix-up grid would have rewritten) and writes warp -> masks -> extremes mask to ``out``; warp point
+    and intervals are drawn inside the kernel for ``(seed, clip_offset + b)``.  Bit-identical to ``frontend_forward_out`` +
+    ``augment_drawn_out``."""
+    _check_frontend_inputs(pcm, n_mels, lengths, n_valid_frames, None)
+    if not 0.0 <= p <= 1.0:
+        raise ValueError(f"spec_augment p must be between 0 and 1, got {p}")
+    B = pcm.shape[0]
+    want = (B, n_mels, _frames(pcm, padding, n_frames_out))
+    for t, name in ((scratch, "scratch"), (out, "out")):
+        if t.dtype != torch.float32 or tuple(t.shape) != want or not t.is_contiguous() or t.device != pcm.device:
+            raise ValueError(f"{name} must be a contiguous CUDA float32 tensor of shape {want}")
+    if extremes is not None and (extremes.dtype != torch.int32 or tuple(extremes.shape) != (B, 2) or not extremes.is_contiguous()
+                                 or extremes.device != pcm.device):
+        raise ValueError(f"extremes must be a contiguous int32 tensor of shape {(B, 2)} on {pcm.device}")
+    g = _lib.AugmentArgs(out=out.data_ptr(), warp_params=None, mask_params=None, extremes=_ptr(extremes),
+                         mask_value=float(mask_value), spline_f32=1 if spline_f32 else 0, draw=1,
+                         draw_time_mask_param=int(time_mask_param), draw_freq_mask_param=int(freq_mask_param),
+                         draw_time_warp_w=int(time_warp_w), draw_p=float(p), draw_seed=seed & (2**64 - 1),
+                         draw_clip_offset=clip_offset & (2**64 - 1))
+    _launch_frontend(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, None, mask_value, scratch,
+                     aug=(g, [extremes], out))
+
+
+@frontend_augment_drawn_out.register_fake
+def _(pcm, n_mels, padding, lengths, n_frames_out, n_valid_frames, seed, clip_offset, time_mask_param, freq_mask_param,
+      time_warp_w, p, extremes, mask_value, spline_f32, scratch, out):
+    return None
+
+
 @torch.library.custom_op("wft::pad_or_trim", mutates_args=(), device_types="cuda")
 def pad_or_trim(x: Tensor, length: int) -> Tensor:
     """``x`` is ``[outer, len_in, inner]`` float32 contiguous -> ``[outer, length, inner]`` (min-value pad or trim)."""
@@ -264,9 +323,9 @@ def _chain_stream(dev: torch.device, reads, writes) -> int:
     """Stream handle for the epilogue of a front-end call: the call's recorded byte ranges grow by what the epilogue touches,
     so that the NEXT front-end call may still be launched as an independent batch when it stays clear of all of them."""
     st = torch.cuda.current_stream(dev).cuda_stream
-    prev = _LAST_CALL.get((dev.index, st))
-    if prev is not None:
-        _LAST_CALL[(dev.index, st)] = (prev[0] + [_span(t) for t in reads], prev[1] + [_span(t) for t in writes])
+    hist = _LAST_CALL.get((dev.index, st))
+    if hist:
+        hist[-1] = (hist[-1][0] + [_span(t) for t in reads], hist[-1][1] + [_span(t) for t in writes])
     return st
 
 
