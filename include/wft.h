@@ -235,6 +235,9 @@ int wft_frontend_grid(int32_t n_mels, int32_t pcm_dtype, int32_t* ctas, int32_t*
 /* Test hook: cap the persistent grids of wft_frontend_forward (front-end and fix-up kernel) at `max_ctas` CTAs (0 = no cap, the
  * default).  Results must not depend on the grid. */
 int wft_debug_set_max_ctas(int32_t max_ctas);
+/* Test hook: != 0 makes the augmentation epilogue use its generic kernel (taps straight from global memory) even where the staged
+ * one (source windows by bulk copy through shared memory; n_frames % 4 == 0) applies.  Both must agree bit for bit. */
+int wft_debug_set_augment_generic(int32_t on);
 /* Development hook (tools/cosched_probe.py): pad the front-end CTA's dynamic shared memory by `bytes`, i.e. lower its CTAs per
  * SM (0 = the default, 6 per SM on B200). */
 int wft_debug_set_extra_smem(int32_t bytes);

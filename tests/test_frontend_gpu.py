@@ -411,8 +411,58 @@ def test_fused_production_call_finishes_cells_like_the_fixup_grid(wft, cuda, n_m
         torch.cuda.synchronize()
         assert torch.isfinite(got).all()
         assert torch.equal(got, want), f"ragged={ragged}: {(got != want).sum().item()} cells differ"
-    # the floor really bound somewhere and the pad really was a pad (the test would be vacuous otherwise)
-    assert (plain[0] == plain[0].min()).float().mean().item() > 0.5
+        wft._lib.load().wft_debug_set_augment_generic(1)      # and the generic instance of the finishing epilogue
+        try:
+            got2 = torch.empty_like(plain)
+            torch.ops.wft.frontend_augment_drawn_out(x, n_mels, 0, L, 3000, NV, 9, 500, 100, 27, 80, 0.7, ext, 0.0, spline == "f32",
+                                                     scratch.fill_(float("nan")), got2)
+            torch.cuda.synchronize()
+        finally:
+            wft._lib.load().wft_debug_set_augment_generic(0)
+        assert torch.equal(got2, want), f"generic instance, ragged={ragged}"
+    # the floor really bound somewhere (the test would be vacuous otherwise): clip 1 is exact zeros after sample 150000
+    assert (plain[1] == plain[1].min()).float().mean().item() > 0.5
+
+
+@pytest.mark.parametrize("R,T", [(128, 3000), (80, 3000), (128, 1500), (5, 40), (33, 516)])
+def test_staged_and_generic_epilogue_agree_bit_for_bit(wft, cuda, R, T):
+    """The epilogue has two kernels: the staged one (source windows by bulk copy through shared memory, n_frames % 4 == 0) and
+    the generic one (taps straight from global memory).  Same arithmetic in the same order: equal bit for bit, for explicit and
+    drawn parameters, both splines, steep warps (windows wider than the staging buffer fall back inside the staged kernel),
+    clips without a warp, masks at the edges, extremes masks."""
+    lib = wft._lib.load()
+    B = 9
+    g = torch.Generator().manual_seed(R * 10000 + T)
+    mel = torch.randn(B, R, T, generator=g).to(cuda)
+    W = min(80, (T - 1) // 2 - 1)
+    # steepest maps the draw can produce (warp point next to an edge, full displacement), the identity, a rejected clip
+    wp = [W, W, T - W - 1, T - W - 1, T // 2, T // 3, -1, 1, T - 2]
+    wd = [W - 1, -W, W - 1, -W, 0, W // 2, 0, -W, W - 1]
+    warps = torch.tensor(list(zip(wp, wd)), dtype=torch.int32, device=cuda)
+    masks = torch.tensor([[0, 0, 0, 0], [0, min(100, T), 0, 1], [T - 7, T, R - 2, R], [T // 2, T // 2 + 50, 1, 3], [0, 0, 0, R],
+                          [3, 4, 0, 0], [10, 20, 1, 2], [0, T, 0, 0], [5, 5, 2, 2]], dtype=torch.int32, device=cuda)
+    ext = torch.tensor([[0, 0], [1, 0], [0, 2], [1, 1], [0, 0], [0, 0], [2, 0], [0, 0], [0, 1]], dtype=torch.int32, device=cuda)
+
+    def run():
+        outs = []
+        for f32 in (False, True):
+            outs.append(torch.ops.wft.augment(mel, warps, masks, ext, 0.25, f32))
+            outs.append(torch.ops.wft.augment(mel, warps, None, None, 0.0, f32))
+            o = torch.empty_like(mel)
+            torch.ops.wft.augment_drawn_out(mel, 77, 123, min(100, T // 4), min(27, R // 2), W, 0.8, ext, 0.0, f32, o)
+            outs.append(o)
+        outs.append(torch.ops.wft.augment(mel, None, masks, ext, -1.0, False))
+        torch.cuda.synchronize()
+        return outs
+
+    staged = run()
+    lib.wft_debug_set_augment_generic(1)
+    try:
+        generic = run()
+    finally:
+        lib.wft_debug_set_augment_generic(0)
+    for k, (a, b) in enumerate(zip(staged, generic)):
+        assert torch.equal(a, b), f"variant {k}: {(a != b).sum().item()} cells differ"
 
 
 def test_small_batches_in_flight_never_share_a_scratch_buffer(wft, cuda):

@@ -28,7 +28,8 @@ def main():
     n_sets = 4
     pcm = [(0.1 * torch.randn(B, 480000, generator=g)).clamp_(-1, 1).to(dev) for _ in range(n_sets)]
     plain = [torch.empty(B, NM, T, device=dev) for _ in range(n_sets)]
-    outs = [torch.empty(B, NM, T, device=dev) for _ in range(n_sets)]
+    n_out = 16   # an independent launch stays clear of every call since the last one that waited (ops._LAST_CALL)
+    outs = [torch.empty(B, NM, T, device=dev) for _ in range(n_out)]
     sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1)
     res = {"batch": B, "steps": steps, "what": "ms per production batch (front end + fix-up + drawn augmentation epilogue), B = 64, "
            "4 rotating buffer sets; caps = front-end CTAs per SM"}
@@ -54,7 +55,7 @@ def main():
 
     def one_stream(first, n):
         for i in range(first, first + n):
-            fe(pcm[i % n_sets], clip_offset=i * B, out=outs[i % n_sets])
+            fe(pcm[i % n_sets], clip_offset=i * B, out=outs[i % n_out])
 
     wft.set_overlap(True)
     res["one_stream_ms"] = timed(one_stream)
@@ -65,10 +66,20 @@ def main():
         def body(first, n):
             for i in range(first, first + n):
                 for a in range(0, B, c):
-                    fe(pcm[i % n_sets][a:a + c], clip_offset=i * B + a, out=outs[i % n_sets][a:a + c])
+                    fe(pcm[i % n_sets][a:a + c], clip_offset=i * B + a, out=outs[i % n_out][a:a + c])
         return body
 
-    res["one_stream_chunked_ms"] = {str(c): timed(chunked(c)) for c in (32, 16, 8)}
+    res["one_stream_chunked_ms"] = {str(c): timed(chunked(c)) for c in (32,)}
+
+    # 1c. the three-grid composition the fused call replaced (front end + fix-up grid, then the epilogue on finished features)
+    plain3 = [torch.empty(B, NM, T, device=dev) for _ in range(n_out)]
+
+    def three_grids(first, n):
+        for i in range(first, first + n):
+            wft.frontend_forward(pcm[i % n_sets], NM, out=plain3[i % n_out])
+            torch.ops.wft.augment_drawn_out(plain3[i % n_out], SEED, i * B, TM, FM, W, 1.0, None, 0.0, False, outs[i % n_out])
+
+    res["one_stream_three_grids_ms"] = timed(three_grids)
 
     # 2. front end alone / epilogue alone at the same caps (what each costs when it has the GPU to itself)
     def fe_only(first, n):
@@ -77,7 +88,7 @@ def main():
 
     def aug_only(first, n):
         for i in range(first, first + n):
-            torch.ops.wft.augment_drawn_out(plain[i % n_sets], SEED, i * B, TM, FM, W, 1.0, None, 0.0, False, outs[i % n_sets])
+            torch.ops.wft.augment_drawn_out(plain[i % n_sets], SEED, i * B, TM, FM, W, 1.0, None, 0.0, False, outs[i % n_out])
 
     res["epilogue_alone_ms"] = timed(aug_only)
 
@@ -98,7 +109,7 @@ def main():
                 done_a[i] = ev
             with torch.cuda.stream(sb):
                 sb.wait_event(done_a[i])
-                torch.ops.wft.augment_drawn_out(plain[s], SEED, i * B, TM, FM, W, 1.0, None, 0.0, False, outs[s])
+                torch.ops.wft.augment_drawn_out(plain[s], SEED, i * B, TM, FM, W, 1.0, None, 0.0, False, outs[i % n_out])
                 ev = torch.cuda.Event()
                 ev.record(sb)
                 done_b[i] = ev
@@ -108,7 +119,7 @@ def main():
     # the cap that matters is CTAs PER SM (independent batches overlap, so a smaller grid alone just lets the next batch's CTAs
     # in): pad the front-end CTA's shared memory so that only 5 / 4 / 3 fit
     res["caps"] = {}
-    for per_sm, extra in ((6, 0), (5, 6 * 1024), (4, 16 * 1024), (3, 34 * 1024)):
+    for per_sm, extra in ((6, 0), (4, 16 * 1024)):
         lib.wft_debug_set_extra_smem(extra)
         r = {"front_end_alone_ms": timed(fe_only), "two_streams_ms": timed(two_streams), "one_stream_ms": timed(one_stream)}
         res["caps"][str(per_sm)] = r

@@ -93,6 +93,7 @@ SIGNATURES = {
     "wft_launch_count": (c_int64, [c_int]),
     "wft_frontend_grid": (c_int, [c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "wft_debug_set_max_ctas": (c_int, [c_int32]),
+    "wft_debug_set_augment_generic": (c_int, [c_int32]),
     "wft_debug_set_extra_smem": (c_int, [c_int32]),
 }
 

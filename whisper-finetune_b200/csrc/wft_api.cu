@@ -10,6 +10,7 @@
 
 #include "../../include/wft.h"
 #include "frontend_kernel.cuh"
+#include "augment_kernel.cuh"
 
 namespace {
 
@@ -17,6 +18,7 @@ thread_local std::string g_last_error;
 thread_local int64_t g_launches = 0;
 int g_debug_chunk = 0;      // WFT_DEBUG_CHUNK (development): force the tiles-per-claim of the fused kernel
 int g_debug_max_ctas = 0;   // wft_debug_set_max_ctas: caps the persistent grids (results must not depend on the grid)
+int g_debug_aug_generic = 0;   // wft_debug_set_augment_generic: the epilogue's generic instance even where the staged one applies
 int g_debug_extra_smem = 0; // wft_debug_set_extra_smem: pads the front-end CTA's shared memory, i.e. lowers its CTAs per SM
 
 int fail(int code, const std::string& msg) {
@@ -271,349 +273,6 @@ __global__ void specaug_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t
 }
 
 
-// counter-based draw of (warp_p, warp_d): warp_p uniform in [W, T-W), warp_d uniform in [-W, W) (the reference's randint
-// ranges, data/utils.py:107-111), Philox block 2 of the clip's counter; (-1, 0) == "no warp" when the p gate rejects
-__device__ __noinline__ int2 draw_warp_point(uint64_t seed, uint64_t idx, int32_t n_frames, int32_t W, float p) {
-  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
-  const uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
-  bool apply = p >= 1.0f;
-  if (!apply && p > 0.0f) {
-    uint32_t g[4];
-    wft::philox4x32_10(lo, hi, 1u, 0u, k0, k1, g);
-    apply = wft::u01(g[0]) < p;
-  }
-  int2 w = make_int2(-1, 0);   // "no warp": the warp kernels copy such a clip
-  if (apply && W > 0 && n_frames > 2 * W) {
-    uint32_t r[4];
-    wft::philox4x32_10(lo, hi, 2u, 0u, k0, k1, r);
-    w.x = W + static_cast<int>(__fmul_rn(wft::u01(r[0]), static_cast<float>(n_frames - 2 * W)));
-    w.y = -W + static_cast<int>(__fmul_rn(wft::u01(r[1]), static_cast<float>(2 * W)));
-  }
-  return w;
-}
-
-__global__ void time_warp_draw_kernel(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t n_frames, int32_t W,
-                                      float p, int32_t* __restrict__ out) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
-  reinterpret_cast<int2*>(out)[b] = draw_warp_point(seed, clip_offset + static_cast<uint64_t>(b), n_frames, W, p);
-}
-
-// the augmentation epilogue may draw its clip's parameters itself (wft_augment_drawn_f32): same draws as wft_specaug_draw and
-// wft_time_warp_draw for (seed, clip_offset + b)
-struct AugDraw {
-  int32_t enabled, tparam, fparam, W;
-  float p;
-  uint64_t seed, clip_offset;
-};
-
-// ---- fused augmentation epilogue: time-warp -> time mask -> frequency mask -> extremes mask in ONE read + write of the
-// features (data_loader.py:284-290: time_warping, time_masking, freq_masking, extreme_freq_masking).  Every step after the
-// warp only overwrites cells with the mask value, so out[b, r, t] = masked(b, r, t) ? mask_value : warp(in[b])[r, t].
-//
-// Source coordinate of output frame t (normalised, align_corners): the reference's 3-knot cubic Hermite spline
-// (data/utils.py:65-93).  kF32 = false evaluates it in float64 and rounds once; kF32 = true restates the reference's own
-// float32 evaluation order (knot slopes, (xs - x0) / dx, powers of t, the 4x4 basis product as a k-ascending FMA chain, the
-// four products summed left to right) so that the coordinate lands on the reference's float32 value wherever torch's pow
-// returns the correctly rounded power.
-template <bool kF32>
-__device__ __forceinline__ float warp_source_coord(int t, int T, int warp_p, int warp_d) {
-  if (kF32) {
-    const float y0 = -1.0f, y2 = 1.0f;
-    const float y1 = __fsub_rn(__fdiv_rn(static_cast<float>((warp_p - warp_d) * 2), static_cast<float>(T - 1)), 1.0f);
-    const float dxa = static_cast<float>(warp_p), dxb = static_cast<float>(T - 1 - warp_p);
-    const float s0 = __fdiv_rn(__fsub_rn(y1, y0), dxa), s1 = __fdiv_rn(__fsub_rn(y2, y1), dxb);
-    const float mm = __fdiv_rn(__fadd_rn(s1, s0), 2.0f);
-    const bool second = t > warp_p;
-    const float xa = second ? static_cast<float>(warp_p) : 0.0f, dx = second ? dxb : dxa;
-    const float ya = second ? y1 : y0, yb = second ? y2 : y1, ma = second ? mm : s0, mb = second ? s1 : mm;
-    const float u = __fdiv_rn(__fsub_rn(static_cast<float>(t), xa), dx);
-    const float u2 = __fmul_rn(u, u);
-    const float u3 = static_cast<float>(static_cast<double>(u) * static_cast<double>(u) * static_cast<double>(u));
-    // A @ [1, u, u2, u3]^T, rows of A = (1,0,-3,2), (0,1,-2,1), (0,0,3,-2), (0,0,-1,1)
-    const float h0 = __fmaf_rn(2.0f, u3, __fmaf_rn(-3.0f, u2, 1.0f));
-    const float h1 = __fmaf_rn(1.0f, u3, __fmaf_rn(-2.0f, u2, u));
-    const float h2 = __fmaf_rn(-2.0f, u3, __fmul_rn(3.0f, u2));
-    const float h3 = __fmaf_rn(1.0f, u3, __fmul_rn(-1.0f, u2));
-    float g = __fmul_rn(h0, ya);
-    g = __fadd_rn(g, __fmul_rn(__fmul_rn(h1, ma), dx));
-    g = __fadd_rn(g, __fmul_rn(h2, yb));
-    g = __fadd_rn(g, __fmul_rn(__fmul_rn(h3, mb), dx));
-    return g;
-  } else {
-    const double x1 = static_cast<double>(warp_p), x2 = static_cast<double>(T - 1);
-    const double y0 = -1.0, y1 = static_cast<double>(warp_p - warp_d) * 2.0 / (T - 1.0) - 1.0, y2 = 1.0;
-    const double s0 = (y1 - y0) / x1, s1 = (y2 - y1) / (x2 - x1);
-    const double m0 = s0, m1 = 0.5 * (s0 + s1), m2 = s1;
-    const bool second = static_cast<double>(t) > x1;
-    const double xa = second ? x1 : 0.0, dx = second ? (x2 - x1) : x1;
-    const double ya = second ? y1 : y0, yb = second ? y2 : y1, ma = second ? m1 : m0, mb = second ? m2 : m1;
-    const double u = (static_cast<double>(t) - xa) / dx, u2 = u * u, u3 = u2 * u;
-    return static_cast<float>((1.0 - 3.0 * u2 + 2.0 * u3) * ya + (u - 2.0 * u2 + u3) * ma * dx + (3.0 * u2 - 2.0 * u3) * yb +
-                              (-u2 + u3) * mb * dx);
-  }
-}
-
-// The float64 spline once per CTA instead of once per frame: the source map is a cubic in u = (t - xa) / dx on each of its two
-// segments, g(u) = A h00 + B h10 + C h01 + D h11 with A = ya, B = ma dx, C = yb, D = mb dx, i.e.
-//   g(u) = A + B u + (-3A - 2B + 3C - D) u^2 + (2A + B - 2C + D) u^3.
-// One thread derives {xa, 1 / dx, c0 .. c3} for both segments (the three float64 divisions of the knot slopes live here: with
-// every thread evaluating its own frames they were half of the kernel's instructions), every frame is then 1 multiply + 3 FMAs.
-__device__ __forceinline__ void spline_segments(int T, int warp_p, int warp_d, double* __restrict__ seg /* [2][6] */) {
-  const double x1 = static_cast<double>(warp_p), x2 = static_cast<double>(T - 1);
-  const double y0 = -1.0, y1 = static_cast<double>(warp_p - warp_d) * 2.0 / (T - 1.0) - 1.0, y2 = 1.0;
-  const double s0 = (y1 - y0) / x1, s1 = (y2 - y1) / (x2 - x1);
-  const double m0 = s0, m1 = 0.5 * (s0 + s1), m2 = s1;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const double xa = k ? x1 : 0.0, dx = k ? (x2 - x1) : x1;
-    const double A = k ? y1 : y0, C = k ? y2 : y1, B = (k ? m1 : m0) * dx, D = (k ? m2 : m1) * dx;
-    seg[6 * k + 0] = xa;
-    seg[6 * k + 1] = 1.0 / dx;
-    seg[6 * k + 2] = A;
-    seg[6 * k + 3] = B;
-    seg[6 * k + 4] = -3.0 * A - 2.0 * B + 3.0 * C - D;
-    seg[6 * k + 5] = 2.0 * A + B - 2.0 * C + D;
-  }
-}
-__device__ __forceinline__ float spline_eval(int t, int warp_p, const double* __restrict__ seg) {
-  const double* c = seg + (t > warp_p ? 6 : 0);
-  const double u = (static_cast<double>(t) - c[0]) * c[1];
-  return static_cast<float>(fma(fma(fma(c[5], u, c[4]), u, c[3]), u, c[2]));
-}
-
-constexpr int kAugThreads = 256;
-constexpr int kAugFramesPerThread = 4;
-constexpr int kAugRowsPerCta = 16;
-
-// kFix instances of the epilogue run directly behind a front-end grid that was launched WITHOUT its fix-up grid
-// (wft_frontend_augment_forward): `in` then holds what the front-end kernel wrote -- final features except for what can only
-// be finished once the whole clip is known -- and every tap is finished on load exactly like wft::fixup_tile would have
-// rewritten it: max(v, floor) for the kept frames, the clamp value for tiles that were never computed (silent / pad-only),
-// the min-value pad beyond the kept frames (data/utils.py:380-404).
-struct AugFix {
-  const wft::ClipStat* stats;    // this call's clip statistics (complete once the front-end grid is)
-  const int32_t* lengths;
-  const int32_t* n_valid;
-  int32_t n_samples, n_total, n_frames;   // of the front-end call (frames the clip really has; T is n_frames_out)
-};
-
-// grid = (frame blocks of 1024, row groups of 16, clips); a thread owns 4 output frames, 256 apart (lane <-> consecutive frames:
-// a warp's store is one 128-byte line and the two source taps of a smooth, monotone map fall into one or two lines -- with 4
-// ADJACENT frames per thread every scalar load of a warp was spread over 4-8 lines and the kernel sat at 0.40 of the HBM peak
-// on the L1 data pipe); it evaluates the 4 source coordinates once and walks the 16 rows of its group with 8 independent
-// loads in flight per row (bilinear taps mirror grid_sample's float32 arithmetic, zeros outside).
-// the value fixup_tile would have left in a cell the front-end kernel wrote as v (kind: 0 = computed, 1 = never computed, 2 = pad)
-// (s_fix: floor feature, pad value, kept frames, clip length, clamp feature; the last two values a ragged clip needs are read
-// from shared memory where they are used -- a register each would spill the float64-spline instance)
-__device__ __forceinline__ float aug_finish(float v, uint32_t kind, bool ragged, float floorn, const int* __restrict__ s_fix) {
-  if (!ragged) return fmaxf(v, floorn);
-  return kind == 2u ? __int_as_float(s_fix[1]) : fmaxf(kind == 1u ? __int_as_float(s_fix[4]) : v, floorn);
-}
-
-// kFix: 0 = `in` holds finished features; 1 = finish on load, full-length clips without a cut (the floor is all there is);
-// 2 = finish on load, ragged batch (lengths / cuts / output longer than the clip: per-tap kinds; 64 registers, 4 CTAs per SM)
-template <bool kF32, int kFix>
-__global__ void __launch_bounds__(kAugThreads, kFix == 2 ? 4 : 5) augment_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                             int32_t R, int32_t T, const int32_t* __restrict__ warp_params,
-                                                             const int32_t* __restrict__ mask_params,
-                                                             const int32_t* __restrict__ extremes, float mask_value,
-                                                             const AugDraw draw, const AugFix fix) {
-  const int b = blockIdx.z;
-  __shared__ int s_draw[8];
-  __shared__ int s_fix[5];    // kFix: floor feature, pad value (float bits), kept frames, clip length in samples, clamp feature
-  __shared__ double s_seg[12];
-  __shared__ int4 s_row[kAugRowsPerCta];   // per output row of this CTA: source row, its weight, the next row's weight (bits), -
-  // source row(s) of every output row of the group: grid_sample's y coordinate of row r (the identity up to float32 rounding,
-  // which can put a sliver of weight on the next row -- restated, not assumed), once per CTA instead of once per thread and row
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + kAugRowsPerCta) {
-    const int r = blockIdx.y * kAugRowsPerCta + (threadIdx.x - 64);
-    const float step = 2.0f / static_cast<float>(R - 1);  // torch.linspace(-1, 1, R)
-    const float gy = (r < R / 2) ? (-1.0f + step * static_cast<float>(r)) : (1.0f - step * static_cast<float>(R - 1 - r));
-    const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
-    const float iy0f = floorf(iy);
-    const int iy0 = static_cast<int>(iy0f), iy1 = iy0 + 1;
-    const float wy1r = iy - iy0f, wy0r = (iy0f + 1.0f) - iy;
-    const bool use0 = iy0 >= 0 && iy0 < R, use1 = iy1 >= 0 && iy1 < R && wy1r != 0.0f;
-    s_row[threadIdx.x - 64] = make_int4(use0 ? iy0 : 0, __float_as_int(use0 ? wy0r : 0.0f), __float_as_int(use1 ? wy1r : 0.0f),
-                                        use1 ? iy1 : -1);
-  }
-  // clip parameters -> shared memory: thread 0 the mask intervals, thread 32 the warp point and the spline's segment
-  // coefficients.  Drawn parameters depend on nothing a grid in front produced: they are ready before this grid's wait.
-  if (draw.enabled) {
-    if (threadIdx.x == 0) {
-      const int4 m = wft::draw_mask_intervals(draw.seed, draw.clip_offset + static_cast<uint64_t>(b), R, T, draw.tparam, draw.fparam, draw.p);
-      s_draw[0] = m.x; s_draw[1] = m.y; s_draw[2] = m.z; s_draw[3] = m.w;
-    } else if (threadIdx.x == 32) {
-      const int2 w = draw_warp_point(draw.seed, draw.clip_offset + static_cast<uint64_t>(b), T, draw.W, draw.p);
-      s_draw[4] = w.x; s_draw[5] = w.y;
-      if (!kF32 && w.x > 0 && w.x < T - 1) spline_segments(T, w.x, w.y, s_seg);
-    }
-  }
-  // a programmatic dependent of whatever produced `in`: the grid behind this one may be scheduled, this one waits
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (!draw.enabled) {
-    if (threadIdx.x == 0) {
-      int4 m = make_int4(0, 0, 0, 0);
-      if (mask_params != nullptr) m = __ldg(reinterpret_cast<const int4*>(mask_params) + b);
-      s_draw[0] = m.x; s_draw[1] = m.y; s_draw[2] = m.z; s_draw[3] = m.w;
-    } else if (threadIdx.x == 32) {
-      int2 w = make_int2(-1, 0);
-      if (warp_params != nullptr) w = __ldg(reinterpret_cast<const int2*>(warp_params) + b);
-      s_draw[4] = w.x; s_draw[5] = w.y;
-      if (!kF32 && w.x > 0 && w.x < T - 1) spline_segments(T, w.x, w.y, s_seg);
-    }
-  }
-  if (kFix != 0 && threadIdx.x == 96) {   // the front-end grid is complete (griddepcontrol.wait above): its statistics are final
-    const float floorn = wft::floor_feature(wft::dec_ordered(__ldcg(&fix.stats[b].max_enc)));
-    const float padv = fmaxf(wft::feature_of_l2(wft::dec_ordered(~__ldcg(&fix.stats[b].min_inv))), floorn);
-    int len = fix.n_samples;
-    if (fix.lengths != nullptr) {
-      const int l = __ldg(fix.lengths + b);
-      len = l < 0 ? 0 : (l < len ? l : len);
-    }
-    s_fix[0] = __float_as_int(floorn);
-    s_fix[1] = __float_as_int(padv);
-    s_fix[2] = wft::kept_frames(fix.n_valid, b, fix.n_frames);
-    s_fix[3] = len;
-    s_fix[4] = __float_as_int(wft::feature_of_l2(wft::silent_l2()));
-  }
-  __syncthreads();
-  const int tbase = blockIdx.x * kAugThreads * kAugFramesPerThread + threadIdx.x;
-  constexpr int kStep = kAugThreads;   // frame k of this thread = tbase + k * kStep
-  if (tbase >= T) return;
-  const int wp = s_draw[4], wd = s_draw[5];
-  const int4 mk = make_int4(s_draw[0], s_draw[1], s_draw[2], s_draw[3]);
-  int lo_rows = 0, hi_rows = 0;
-  if (extremes != nullptr) {
-    const int2 e = __ldg(reinterpret_cast<const int2*>(extremes) + b);
-    lo_rows = e.x; hi_rows = e.y;
-  }
-  const bool warp = wp > 0 && wp < T - 1;          // anything else (the draw's "gate rejected" marker is -1) = no warp
-  // per frame, once: the two source columns (clamped into the row so that every load is unconditional) and their weights
-  // (0 for a tap that falls outside: "zeros" padding -- 0 * finite contributes exactly nothing), and whether the cell is live
-  int oa[kAugFramesPerThread];
-  uint32_t cstep = 0;   // bit k: the second tap of frame k sits one column right of the first (0 where both clamp to one column)
-  float wa[kAugFramesPerThread], wc[kAugFramesPerThread];
-  bool on[kAugFramesPerThread];
-#pragma unroll
-  for (int k = 0; k < kAugFramesPerThread; ++k) {
-    const int t = tbase + k * kStep;
-    on[k] = t < T && !(t >= mk.x && t < mk.y);
-    int a = t < T ? t : T - 1;
-    float wx0 = 1.0f, wx1 = 0.0f;
-    if (warp && t < T) {
-      const float gx = kF32 ? warp_source_coord<true>(t, T, wp, wd) : spline_eval(t, wp, s_seg);
-      const float ix = ((gx + 1.0f) / 2.0f) * static_cast<float>(T - 1);
-      const float f = floorf(ix);
-      a = static_cast<int>(f);
-      wx1 = ix - f;
-      wx0 = (f + 1.0f) - ix;
-    }
-    const int c = a + 1;
-    wa[k] = (a >= 0 && a < T) ? wx0 : 0.0f;
-    wc[k] = (c >= 0 && c < T) ? wx1 : 0.0f;
-    oa[k] = min(max(a, 0), T - 1);
-    cstep |= static_cast<uint32_t>(min(max(c, 0), T - 1) - oa[k]) << k;
-  }
-  // kFix: what a tap at source column oa[k] / oc[k] still needs (per frame, once): 0 = floor only, 1 = never computed (the
-  // clamp value, then the floor), 2 = beyond the kept frames (the pad value).  Full-length clips without a cut need no table.
-  float floorn = 0.0f;
-  bool ragged = false;
-  uint32_t kinds = 0;   // 2 bits per tap: tap a of frame k at bit 4k, tap c at bit 4k + 2
-  if constexpr (kFix != 0) floorn = __int_as_float(s_fix[0]);
-  if constexpr (kFix == 2) {
-    const int keep = s_fix[2], len = s_fix[3];
-    ragged = keep < T || len < fix.n_samples || fix.n_frames < T;
-    if (ragged) {
-#pragma unroll
-      for (int k = 0; k < kAugFramesPerThread; ++k) {
-        const int a = oa[k], c = oa[k] + static_cast<int>((cstep >> k) & 1u);
-        const uint32_t ka = a >= keep ? 2u : (wft::tile_is_silent(a & ~(wft::kTileFrames - 1), len, fix.n_total) ? 1u : 0u);
-        const uint32_t kc = c >= keep ? 2u : (wft::tile_is_silent(c & ~(wft::kTileFrames - 1), len, fix.n_total) ? 1u : 0u);
-        kinds |= (ka | (kc << 2)) << (4 * k);
-      }
-    }
-  }
-#define AUG_FINISH(v, k, tap) aug_finish(v, (kinds >> (4 * (k) + 2 * (tap))) & 3u, ragged, floorn, s_fix)
-  const size_t clip = static_cast<size_t>(b) * R * T;
-  const int r_end = min(R, static_cast<int>(blockIdx.y + 1) * kAugRowsPerCta);
-  for (int r = blockIdx.y * kAugRowsPerCta; r < r_end; ++r) {
-    float v[kAugFramesPerThread];
-    const bool rowmask = (r >= mk.z && r < mk.w) || r < lo_rows || r >= R - hi_rows;
-    if (rowmask) {
-#pragma unroll
-      for (int k = 0; k < kAugFramesPerThread; ++k) v[k] = mask_value;
-    } else if (!warp) {
-      const float* row = in + clip + static_cast<size_t>(r) * T;
-#pragma unroll
-      for (int k = 0; k < kAugFramesPerThread; ++k) {
-        if constexpr (kFix != 0) v[k] = on[k] ? AUG_FINISH(__ldg(row + oa[k]), k, 0) : mask_value;
-        else v[k] = on[k] ? __ldg(row + oa[k]) : mask_value;
-      }
-    } else {
-      const int4 rr = s_row[r - blockIdx.y * kAugRowsPerCta];
-      const float wy0 = __int_as_float(rr.y), wy1 = __int_as_float(rr.z);
-      const bool use1 = rr.w >= 0;
-      const int iy1 = rr.w;
-      const float* row0 = in + clip + static_cast<size_t>(rr.x) * T;
-      // every tap of the row is requested before the first one is used (8 independent loads in flight per thread)
-      float t0a[kAugFramesPerThread], t0c[kAugFramesPerThread];
-#pragma unroll
-      for (int k = 0; k < kAugFramesPerThread; ++k) {
-        t0a[k] = __ldg(row0 + oa[k]);
-        t0c[k] = __ldg(row0 + oa[k] + ((cstep >> k) & 1u));
-      }
-      if constexpr (kFix != 0) {
-#pragma unroll
-        for (int k = 0; k < kAugFramesPerThread; ++k) {
-          t0a[k] = AUG_FINISH(t0a[k], k, 0);
-          t0c[k] = AUG_FINISH(t0c[k], k, 1);
-        }
-      }
-      if (!use1) {      // warp-uniform (depends on r alone); taps accumulate in grid_sample's order
-#pragma unroll
-        for (int k = 0; k < kAugFramesPerThread; ++k) {
-          float acc = 0.0f;
-          acc += t0a[k] * (wa[k] * wy0);
-          acc += t0c[k] * (wc[k] * wy0);
-          v[k] = on[k] ? acc : mask_value;
-        }
-      } else {
-        const float* row1 = in + clip + static_cast<size_t>(iy1) * T;
-        float t1a[kAugFramesPerThread], t1c[kAugFramesPerThread];
-#pragma unroll
-        for (int k = 0; k < kAugFramesPerThread; ++k) {
-          t1a[k] = __ldg(row1 + oa[k]);
-          t1c[k] = __ldg(row1 + oa[k] + ((cstep >> k) & 1u));
-        }
-        if constexpr (kFix != 0) {
-#pragma unroll
-          for (int k = 0; k < kAugFramesPerThread; ++k) {
-            t1a[k] = AUG_FINISH(t1a[k], k, 0);
-            t1c[k] = AUG_FINISH(t1c[k], k, 1);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < kAugFramesPerThread; ++k) {
-          float acc = 0.0f;
-          acc += t0a[k] * (wa[k] * wy0);
-          acc += t0c[k] * (wc[k] * wy0);
-          acc += t1a[k] * (wa[k] * wy1);
-          acc += t1c[k] * (wc[k] * wy1);
-          v[k] = on[k] ? acc : mask_value;
-        }
-      }
-    }
-    float* dst = out + clip + static_cast<size_t>(r) * T + tbase;
-#pragma unroll
-    for (int k = 0; k < kAugFramesPerThread; ++k)
-      if (tbase + k * kStep < T) dst[k * kStep] = v[k];
-  }
-}
-
-#undef AUG_FINISH
 
 int grid_1d(int64_t n, int threads) {
   int64_t g = (n + threads - 1) / threads;
@@ -641,6 +300,11 @@ int wft_debug_timeline(uint32_t* host_out, int32_t* dims) {
 
 int wft_debug_set_max_ctas(int32_t max_ctas) {
   g_debug_max_ctas = max_ctas > 0 ? max_ctas : 0;
+  return WFT_OK;
+}
+
+int wft_debug_set_augment_generic(int32_t on) {
+  g_debug_aug_generic = on != 0;
   return WFT_OK;
 }
 
@@ -880,7 +544,7 @@ int wft_specaug_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32_t
 
 static int launch_augment(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
                           const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32,
-                          const AugDraw& draw, cudaStream_t stream, const AugFix* fix = nullptr) {
+                          const wft::AugDraw& draw, cudaStream_t stream, const wft::AugFix* fix = nullptr) {
   if (batch < 0 || n_rows < 0 || n_frames < 0) return fail(WFT_ERR_INVALID, "negative extent");
   if (static_cast<int64_t>(batch) * n_rows * n_frames == 0) return WFT_OK;
   if (in == nullptr || out == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
@@ -896,26 +560,51 @@ static int launch_augment(const float* in, float* out, int32_t batch, int32_t n_
   if ((n_frames & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0)
     return fail(WFT_ERR_INVALID, "in and out must be 16-byte aligned");
   if (batch > 65535) return fail(WFT_ERR_INVALID, "batch too large for one launch (max 65535)");
-  const int per_cta = kAugThreads * kAugFramesPerThread;
+  const int per_cta = wft::kAugThreads * wft::kAugFramesPerThread;
   // always a programmatic dependent: the kernel waits for its predecessor on the device (griddepcontrol.wait), so its
   // launch latency and -- for the drawn variant -- its draws hide under the tail of the kernel that produces `in`
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((n_frames + per_cta - 1) / per_cta, (n_rows + kAugRowsPerCta - 1) / kAugRowsPerCta, batch);
-  cfg.blockDim = dim3(kAugThreads);
+  cfg.gridDim = dim3((n_frames + per_cta - 1) / per_cta, (n_rows + wft::kAugRowsPerCta - 1) / wft::kAugRowsPerCta, batch);
+  cfg.blockDim = dim3(wft::kAugThreads);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const AugFix fx = fix != nullptr ? *fix : AugFix{};
+  const wft::AugFix fx = fix != nullptr ? *fix : wft::AugFix{};
   // (same rule as the fix-up grid's heavy instance: lengths / cuts / an output longer than the clip)
   const bool ragged = fix != nullptr && (fix->lengths != nullptr || fix->n_valid != nullptr || n_frames > fix->n_frames);
-#define WFT_AUG_LAUNCH(F32, FIX) \
-  WFT_CUDA(cudaLaunchKernelEx(&cfg, augment_kernel<F32, FIX>, in, out, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, draw, fx))
-  if (fix == nullptr) {
+  const int fixmode = fix == nullptr ? 0 : (ragged ? 2 : 1);
+  // the staged instance (source windows by bulk copy through shared memory) needs 16-byte rows; g_debug_aug_generic forces the
+  // generic instance (tests compare the two bit for bit)
+  const bool stage = (n_frames & 3) == 0 && n_frames >= 8 && !g_debug_aug_generic;
+  if (stage) {
+    cfg.gridDim = dim3((n_frames + wft::kStgBlock - 1) / wft::kStgBlock, (n_rows + wft::kAugRowsPerCta - 1) / wft::kAugRowsPerCta, batch);
+    cfg.blockDim = dim3(wft::kStgThreads);
+    cfg.dynamicSmemBytes = wft::kStgSmemBytes;
+  }
+#define WFT_AUG_LAUNCH(F32, FIX)                                                                                              \
+  do {                                                                                                                        \
+    if (stage) {                                                                                                              \
+      static bool attr_set[64] = {};                                                                                          \
+      int dev_ = 0;                                                                                                           \
+      WFT_CUDA(cudaGetDevice(&dev_));                                                                                         \
+      if (dev_ >= 0 && dev_ < 64 && !attr_set[dev_]) {                                                                        \
+        WFT_CUDA(cudaFuncSetAttribute(wft::augment_staged_kernel<F32, FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                      wft::kStgSmemBytes));                                                                   \
+        attr_set[dev_] = true;                                                                                                \
+      }                                                                                                                       \
+      WFT_CUDA(cudaLaunchKernelEx(&cfg, wft::augment_staged_kernel<F32, FIX>, in, out, n_rows, n_frames, warp_params,         \
+                                  mask_params, extremes, mask_value, draw, fx));                                             \
+    } else {                                                                                                                  \
+      WFT_CUDA(cudaLaunchKernelEx(&cfg, wft::augment_kernel<F32, FIX>, in, out, n_rows, n_frames, warp_params, mask_params,   \
+                                  extremes, mask_value, draw, fx));                                                           \
+    }                                                                                                                         \
+  } while (0)
+  if (fixmode == 0) {
     if (spline_f32) WFT_AUG_LAUNCH(true, 0); else WFT_AUG_LAUNCH(false, 0);
-  } else if (!ragged) {
+  } else if (fixmode == 1) {
     if (spline_f32) WFT_AUG_LAUNCH(true, 1); else WFT_AUG_LAUNCH(false, 1);
   } else {
     if (spline_f32) WFT_AUG_LAUNCH(true, 2); else WFT_AUG_LAUNCH(false, 2);
@@ -927,7 +616,7 @@ static int launch_augment(const float* in, float* out, int32_t batch, int32_t n_
 
 int wft_augment_f32(const float* in, float* out, int32_t batch, int32_t n_rows, int32_t n_frames, const int32_t* warp_params,
                     const int32_t* mask_params, const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream_) {
-  return launch_augment(in, out, batch, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, spline_f32, AugDraw{},
+  return launch_augment(in, out, batch, n_rows, n_frames, warp_params, mask_params, extremes, mask_value, spline_f32, wft::AugDraw{},
                         static_cast<cudaStream_t>(stream_));
 }
 
@@ -936,7 +625,7 @@ int wft_augment_drawn_f32(const float* in, float* out, int32_t batch, int32_t n_
                           const int32_t* extremes, float mask_value, int32_t spline_f32, void* stream_) {
   if (!(p >= 0.0f && p <= 1.0f)) return fail(WFT_ERR_INVALID, "spec_augment p must be between 0 and 1");
   if (time_warp_w < 0) return fail(WFT_ERR_INVALID, "time_warp_w must be >= 0");
-  AugDraw d{};
+  wft::AugDraw d{};
   d.enabled = 1; d.tparam = time_mask_param; d.fparam = freq_mask_param; d.W = time_warp_w; d.p = p;
   d.seed = seed; d.clip_offset = clip_offset;
   return launch_augment(in, out, batch, n_rows, n_frames, nullptr, nullptr, extremes, mask_value, spline_f32, d,
@@ -950,7 +639,7 @@ int wft_frontend_augment_forward(const wft_frontend_args* a, const wft_augment_a
   if (a->mask_params != nullptr || a->draw_masks != 0)
     return fail(WFT_ERR_INVALID, "the masks of a front-end + augmentation call belong to the augmentation arguments");
   if (g->out == a->out) return fail(WFT_ERR_INVALID, "the un-augmented features (scratch) and the output must be different buffers");
-  AugDraw d{};
+  wft::AugDraw d{};
   if (g->draw != 0) {
     if (g->warp_params != nullptr || g->mask_params != nullptr) return fail(WFT_ERR_INVALID, "draw and explicit parameters are mutually exclusive");
     if (!(g->draw_p >= 0.0f && g->draw_p <= 1.0f)) return fail(WFT_ERR_INVALID, "spec_augment p must be between 0 and 1");
@@ -961,7 +650,7 @@ int wft_frontend_augment_forward(const wft_frontend_args* a, const wft_augment_a
   wft::FrontendParams used{};
   int rc = frontend_forward_impl(a, stream, false, &used);
   if (rc != WFT_OK) return rc;
-  AugFix fix{};
+  wft::AugFix fix{};
   fix.stats = used.stats; fix.lengths = used.lengths; fix.n_valid = used.n_valid;
   fix.n_samples = used.n_samples; fix.n_total = used.n_total; fix.n_frames = used.n_frames;
   return launch_augment(a->out, g->out, a->batch, a->n_mels, used.n_frames_out, g->warp_params, g->mask_params, g->extremes,
@@ -982,7 +671,7 @@ int wft_time_warp_draw(uint64_t seed, uint64_t clip_offset, int32_t batch, int32
   if (!(p >= 0.0f && p <= 1.0f)) return fail(WFT_ERR_INVALID, "spec_augment p must be between 0 and 1");
   if (warp_params_out == nullptr) return fail(WFT_ERR_INVALID, "warp_params_out is NULL");
   if ((reinterpret_cast<uintptr_t>(warp_params_out) & 7) != 0) return fail(WFT_ERR_INVALID, "warp_params_out must be 8-byte aligned");
-  time_warp_draw_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(seed, clip_offset, batch, n_frames, time_warp_w, p,
+  wft::time_warp_draw_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(seed, clip_offset, batch, n_frames, time_warp_w, p,
                                                                  warp_params_out);
   ++g_launches;
   WFT_CUDA(cudaGetLastError());
