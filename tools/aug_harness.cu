@@ -28,5 +28,13 @@ int main(int argc, char** argv) {
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   double bytes = 2.0 * n * 4;
   printf("augment B=%d spline_f32=%d: %.1f us per launch, %.0f GB/s (%s)\n", B, f32, ms * 1e3 / iters, bytes / (ms * 1e-3 / iters) / 1e9, cudaGetErrorString(e));
+  // reference: a device-to-device copy of the same buffers (what one read + one write of this size can reach at all)
+  for (int it = 0; it < 4; ++it) cudaMemcpyAsync(out[it % NB], in[it % NB], n * 4, cudaMemcpyDeviceToDevice, 0);
+  cudaEventRecord(e0);
+  for (int it = 0; it < iters; ++it) cudaMemcpyAsync(out[it % NB], in[it % NB], n * 4, cudaMemcpyDeviceToDevice, 0);
+  cudaEventRecord(e1);
+  cudaDeviceSynchronize();
+  cudaEventElapsedTime(&ms, e0, e1);
+  printf("cudaMemcpyAsync D2D of the same %.1f MB: %.1f us per copy, %.0f GB/s\n", n * 4 / 1e6, ms * 1e3 / iters, bytes / (ms * 1e-3 / iters) / 1e9);
   return 0;
 }

@@ -106,6 +106,10 @@ __device__ __forceinline__ float warp_source_coord(int t, int T, int warp_p, int
 // One thread derives {xa, 1 / dx, c0 .. c3} for both segments (the three float64 divisions of the knot slopes live here: with
 // every thread evaluating its own frames they were half of the kernel's instructions), every frame is then 1 multiply + 3 FMAs.
 __device__ __forceinline__ void spline_segments(int T, int warp_p, int warp_d, double* __restrict__ seg /* [2][6] */) {
+#if defined(WFT_AUG_KO) && (WFT_AUG_KO & 1)   // knock-out build (timing only): no float64 divisions, the identity map
+  for (int k = 0; k < 2; ++k) { seg[6 * k] = 0.0; seg[6 * k + 1] = 1.0 / 2999.0; seg[6 * k + 2] = -1.0; seg[6 * k + 3] = 2.0; seg[6 * k + 4] = 0.0; seg[6 * k + 5] = 0.0; }
+  return;
+#endif
   const double x1 = static_cast<double>(warp_p), x2 = static_cast<double>(T - 1);
   const double y0 = -1.0, y1 = static_cast<double>(warp_p - warp_d) * 2.0 / (T - 1.0) - 1.0, y2 = 1.0;
   const double s0 = (y1 - y0) / x1, s1 = (y2 - y1) / (x2 - x1);
@@ -166,15 +170,36 @@ __device__ __forceinline__ float aug_finish(float v, uint32_t kind, bool ragged,
 
 // What both kernels do before their first __syncthreads: the CTA's row table, the clip's parameters (drawn before the wait
 // for the producing grid, loaded after it) and, for the kFix instances, what finishing a cell needs.
-template <bool kF32, int kFix>
+// kFix instances: what finishing a cell needs.  The front-end grid is complete once griddepcontrol.wait has returned, so its
+// statistics are final.  Load and publication are separate so that a kernel can keep the loads in flight across a barrier.
+__device__ __forceinline__ int4 aug_fix_load(int b, const AugFix& fix) {
+  int4 raw;
+  raw.x = static_cast<int>(__ldcg(&fix.stats[b].max_enc));
+  raw.y = static_cast<int>(__ldcg(&fix.stats[b].min_inv));
+  raw.z = fix.lengths != nullptr ? __ldg(fix.lengths + b) : fix.n_samples;
+  raw.w = fix.n_valid != nullptr ? __ldg(fix.n_valid + b) : -1;
+  return raw;
+}
+__device__ __forceinline__ void aug_fix_publish(int4 raw, const AugFix& fix, int* __restrict__ s_fix) {
+  const float floorn = floor_feature(dec_ordered(static_cast<uint32_t>(raw.x)));
+  const float padv = fmaxf(feature_of_l2(dec_ordered(~static_cast<uint32_t>(raw.y))), floorn);
+  const int len = raw.z < 0 ? 0 : (raw.z < fix.n_samples ? raw.z : fix.n_samples);
+  s_fix[0] = __float_as_int(floorn);
+  s_fix[1] = __float_as_int(padv);
+  s_fix[2] = (raw.w >= 0 && raw.w < fix.n_frames) ? raw.w : fix.n_frames;   // kept_frames()
+  s_fix[3] = len;
+  s_fix[4] = __float_as_int(feature_of_l2(silent_l2()));
+}
+
+template <bool kF32, int kFix, bool kPublishFix, int kRows>
 __device__ __forceinline__ void aug_prologue(int b, int32_t R, int32_t T, const int32_t* __restrict__ warp_params,
                                              const int32_t* __restrict__ mask_params, const AugDraw& draw, const AugFix& fix,
                                              int* __restrict__ s_draw, int* __restrict__ s_fix, double* __restrict__ s_seg,
                                              int4* __restrict__ s_row) {
   // source row(s) of every output row of the group: grid_sample's y coordinate of row r (the identity up to float32 rounding,
   // which can put a sliver of weight on the next row -- restated, not assumed), once per CTA instead of once per thread and row
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + kAugRowsPerCta) {
-    const int r = blockIdx.y * kAugRowsPerCta + (threadIdx.x - 64);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kRows) {
+    const int r = blockIdx.y * kRows + (threadIdx.x - 64);
     const float step = 2.0f / static_cast<float>(R - 1);  // torch.linspace(-1, 1, R)
     const float gy = (r < R / 2) ? (-1.0f + step * static_cast<float>(r)) : (1.0f - step * static_cast<float>(R - 1 - r));
     const float iy = ((gy + 1.0f) / 2.0f) * static_cast<float>(R - 1);
@@ -212,20 +237,7 @@ __device__ __forceinline__ void aug_prologue(int b, int32_t R, int32_t T, const 
       if (!kF32 && w.x > 0 && w.x < T - 1) spline_segments(T, w.x, w.y, s_seg);
     }
   }
-  if (kFix != 0 && threadIdx.x == 96) {   // the front-end grid is complete (griddepcontrol.wait above): its statistics are final
-    const float floorn = floor_feature(dec_ordered(__ldcg(&fix.stats[b].max_enc)));
-    const float padv = fmaxf(feature_of_l2(dec_ordered(~__ldcg(&fix.stats[b].min_inv))), floorn);
-    int len = fix.n_samples;
-    if (fix.lengths != nullptr) {
-      const int l = __ldg(fix.lengths + b);
-      len = l < 0 ? 0 : (l < len ? l : len);
-    }
-    s_fix[0] = __float_as_int(floorn);
-    s_fix[1] = __float_as_int(padv);
-    s_fix[2] = kept_frames(fix.n_valid, b, fix.n_frames);
-    s_fix[3] = len;
-    s_fix[4] = __float_as_int(feature_of_l2(silent_l2()));
-  }
+  if (kFix != 0 && kPublishFix && threadIdx.x == 96) aug_fix_publish(aug_fix_load(b, fix), fix, s_fix);
 }
 
 // kFix: 0 = `in` holds finished features; 1 = finish on load, full-length clips without a cut (the floor is all there is);
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(kAugThreads, kFix == 2 ? 4 : 5) augment_kernel
   __shared__ int s_fix[5];    // kFix: floor feature, pad value (float bits), kept frames, clip length in samples, clamp feature
   __shared__ double s_seg[12];
   __shared__ int4 s_row[kAugRowsPerCta];   // per output row of this CTA: source row, its weight, the next row's weight (bits), -
-  aug_prologue<kF32, kFix>(b, R, T, warp_params, mask_params, draw, fix, s_draw, s_fix, s_seg, s_row);
+  aug_prologue<kF32, kFix, true, kAugRowsPerCta>(b, R, T, warp_params, mask_params, draw, fix, s_draw, s_fix, s_seg, s_row);
   __syncthreads();
   const int tbase = blockIdx.x * kAugThreads * kAugFramesPerThread + threadIdx.x;
   constexpr int kStep = kAugThreads;   // frame k of this thread = tbase + k * kStep
@@ -398,20 +410,32 @@ __global__ void __launch_bounds__(kAugThreads, kFix == 2 ? 4 : 5) augment_kernel
 #undef AUG_FINISH
 
 // ---- the staged instance ------------------------------------------------------------------------------------------------
-// ncu on augment_kernel (B = 64): 28 M warp-instructions for 24.6 M cells, three quarters of them 64-bit address arithmetic
-// for 4-byte loads the compiler would not keep pointers for, long-scoreboard stalls on top: 47 us for 196.6 MB.  Here the loads
-// are not instructions at all.  A CTA owns 512 output frames x 16 rows.  Once its threads know their source columns (block
-// min / max: the window is exact, whatever the spline does), one thread sends the window of every source row the CTA needs
-// global -> shared memory as a bulk copy (one mbarrier per row, all rows in flight at once, ~34 KB per CTA, 4 CTAs per SM);
-// a thread's taps are then two 4-byte shared-memory loads per cell at an immediate offset from ONE per-frame register, and
-// the row loop is loads, 2 FMUL + 2 FFMA per cell and a store.  A window wider than the buffer (output frames of a steep piece
-// of the map, ~2 % of all CTAs), a clip without a warp and rows nobody needs fall back to / skip the global path.
+// ncu on augment_kernel (B = 64): 28 M warp-instructions for 24.6 M cells, three quarters of them 64-bit address arithmetic for
+// 4-byte loads, long-scoreboard stalls on top: 47 us for 196.6 MB, and the same 47 us with the stores removed.  Here the loads
+// are not instructions at all.  A CTA owns 1024 output frames x 8 rows.  Once its threads know their source columns (block
+// min / max: the window is exact, whatever the spline does), warp 0 sends the window of every source row the CTA needs global
+// -> shared memory as bulk copies (TMA; one mbarrier counts the bytes of all of them, ~40 KB in flight per CTA, 4 CTAs per SM);
+// a thread's taps are then two 4-byte shared-memory loads per cell at an immediate offset from ONE per-frame register, and the
+// row loop is 2 LDS + 2 FMUL + 2 FFMA + a select + a store per cell.  A window wider than the buffer (output frames on a steep
+// piece of the map, ~2 % of all CTAs) and a clip without a warp take the global path inside the same kernel.
 constexpr int kStgThreads = 256;
-constexpr int kStgFrames = 2;                          // frames per thread, 256 apart
-constexpr int kStgBlock = kStgThreads * kStgFrames;    // 512 output frames per CTA
-constexpr int kStgSrcRows = kAugRowsPerCta + 2;        // source rows a row group can touch: r0 - 1 .. r0 + 16
-constexpr int kStgCols = 672;                          // staged source columns per row (multiple of 4)
-constexpr int kStgSmemBytes = kStgSrcRows * kStgCols * 4;   // 48 384 B dynamic
+constexpr int kStgFrames = 4;                          // frames per thread, 256 apart
+constexpr int kStgBlock = kStgThreads * kStgFrames;    // 1024 output frames per CTA
+constexpr int kStgRows = 8;                            // output rows per CTA
+constexpr int kStgSrcRows = kStgRows + 2;              // source rows a row group can touch: r0 - 1 .. r0 + 8
+constexpr int kStgCols = 1216;                         // staged source columns per row (multiple of 4)
+constexpr int kStgSmemBytes = kStgSrcRows * kStgCols * 4;   // 48 640 B dynamic
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32_4(uint32_t addr) {   // the neighbouring column
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1 + 4];" : "=f"(v) : "r"(addr));
+  return v;
+}
 
 template <bool kF32, int kFix>
 __global__ void __launch_bounds__(kStgThreads, 4) augment_staged_kernel(const float* __restrict__ in, float* __restrict__ out,
@@ -424,23 +448,26 @@ __global__ void __launch_bounds__(kStgThreads, 4) augment_staged_kernel(const fl
   __shared__ int s_draw[8];
   __shared__ int s_fix[5];
   __shared__ double s_seg[12];
-  __shared__ int4 s_row[kAugRowsPerCta];
+  __shared__ int4 s_row[kStgRows];
   __shared__ int s_win[2];                       // min / max left source column over the CTA's live frames
-  __shared__ __align__(8) uint64_t s_bar[kStgSrcRows];
+  __shared__ __align__(8) uint64_t s_bar;        // completion of all the CTA's bulk copies
   const int tid = threadIdx.x;
   if (tid == 128) {
     s_win[0] = 0x7fffffff;
     s_win[1] = -1;
-#pragma unroll 1
-    for (int i = 0; i < kStgSrcRows; ++i) mbar_init(&s_bar[i], 1);
+    mbar_init(&s_bar, 1);
   }
-  aug_prologue<kF32, kFix>(b, R, T, warp_params, mask_params, draw, fix, s_draw, s_fix, s_seg, s_row);
+  aug_prologue<kF32, kFix, false, kStgRows>(b, R, T, warp_params, mask_params, draw, fix, s_draw, s_fix, s_seg, s_row);
+  // (thread 96: the loads for s_fix are requested here and used behind the second barrier -- nothing in front of the row loop
+  // needs them, and a round trip to L2 would otherwise sit on every CTA's way to its bulk copies)
+  int4 fix_raw = make_int4(0, 0, 0, 0);
+  if (kFix != 0 && tid == 96) fix_raw = aug_fix_load(b, fix);
   __syncthreads();
   const int tbase = blockIdx.x * kStgBlock + tid;
   constexpr int kStep = kStgThreads;
   const int wp = s_draw[4], wd = s_draw[5];
   const int4 mk = make_int4(s_draw[0], s_draw[1], s_draw[2], s_draw[3]);
-  const int r0 = blockIdx.y * kAugRowsPerCta;
+  const int r0 = blockIdx.y * kStgRows;
   uint32_t rowbits = 0;
   {
     int lo_rows = 0, hi_rows = 0;
@@ -449,8 +476,8 @@ __global__ void __launch_bounds__(kStgThreads, 4) augment_staged_kernel(const fl
       lo_rows = ex.x; hi_rows = ex.y;
     }
     auto rows = [r0](int a, int e) {
-      a = min(max(a - r0, 0), kAugRowsPerCta);
-      e = min(max(e - r0, 0), kAugRowsPerCta);
+      a = min(max(a - r0, 0), kStgRows);
+      e = min(max(e - r0, 0), kStgRows);
       return e > a ? (1u << e) - (1u << a) : 0u;
     };
     rowbits = rows(mk.z, mk.w) | rows(0, lo_rows) | rows(R - hi_rows, R);
@@ -499,25 +526,30 @@ __global__ void __launch_bounds__(kStgThreads, 4) augment_staged_kernel(const fl
   const int n = (s_win[1] + 2 - c0 + 3) & ~3;
   const bool staged = warp && s_win[1] >= 0 && n <= kStgCols;
   const int smin = max(r0 - 1, 0);                       // first source row the group can touch
-  const int n_rows = min(R - r0, kAugRowsPerCta);
-  if (staged && tid == 0) {
-    // every source row a live output row of the group reads, each as one bulk copy with its own mbarrier
-    uint32_t need = 0;
-#pragma unroll 1
-    for (int i = 0; i < n_rows; ++i) {
-      if ((rowbits >> i) & 1u) continue;
-      const int4 rr = s_row[i];
-      need |= 1u << (rr.x - smin);
-      if (rr.w >= 0) need |= 1u << (rr.w - smin);
+  const int n_rows = min(R - r0, kStgRows);
+  if (staged && tid < 32) {
+    // every source row a live output row of the group reads, as one bulk copy each; warp 0 finds the rows (lane <-> output row),
+    // lane 0 announces the bytes of all of them and lane s sends source row s (one thread issuing them all took ~2 us of every
+    // CTA's life)
+    uint32_t bits = 0;
+    if (tid < n_rows && !((rowbits >> tid) & 1u)) {
+      const int4 rr = s_row[tid];
+      bits = 1u << (rr.x - smin);
+      if (rr.w >= 0) bits |= 1u << (rr.w - smin);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const float* g = in + (static_cast<size_t>(b) * R + smin) * T + c0;
-#pragma unroll 1
-    for (int srow = 0; srow < kStgSrcRows; ++srow, g += T) {
-      if (!((need >> srow) & 1u)) continue;
-      mbar_expect_tx(&s_bar[srow], static_cast<uint32_t>(n) * 4u);
-      tma_bulk_g2s(s_buf + srow * kStgCols, g, static_cast<uint32_t>(n) * 4u, &s_bar[srow]);
+    const uint32_t need = __reduce_or_sync(0xffffffffu, bits);
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&s_bar, static_cast<uint32_t>(__popc(need)) * static_cast<uint32_t>(n) * 4u);
     }
+    __syncwarp();
+    if (tid < kStgSrcRows && ((need >> tid) & 1u))
+      tma_bulk_g2s(s_buf + tid * kStgCols, in + (static_cast<size_t>(b) * R + smin + tid) * T + c0, static_cast<uint32_t>(n) * 4u,
+                   &s_bar);
+  }
+  if constexpr (kFix != 0) {
+    if (tid == 96) aug_fix_publish(fix_raw, fix, s_fix);
+    __syncthreads();
   }
   if (tbase >= T) return;
   float floorn = 0.0f;
@@ -538,21 +570,22 @@ __global__ void __launch_bounds__(kStgThreads, 4) augment_staged_kernel(const fl
     }
   }
 #define AUG_FINISH(v, k, tap) aug_finish(v, (kinds >> (4 * (k) + 2 * (tap))) & 3u, ragged, floorn, s_fix)
-  // shared-memory byte offset of this thread's left tap inside a staged row
+  // shared-memory address of this thread's left tap in staged row 0 (a frame beyond T is not part of the window: any valid
+  // address will do)
   uint32_t lo[kStgFrames];
+  const uint32_t buf0 = smem_u32(s_buf);
 #pragma unroll
-  for (int k = 0; k < kStgFrames; ++k)   // (a frame beyond T is not part of the window: any valid offset will do)
-    lo[k] = (staged && tbase + k * kStep < T) ? (e[k] - static_cast<uint32_t>(c0)) * 4u : 0u;
-  uint32_t ready = 0;                            // staged rows this thread has already seen complete
-  const float* src = in + origin + tbase;
+  for (int k = 0; k < kStgFrames; ++k)
+    lo[k] = buf0 + ((staged && tbase + k * kStep < T) ? (e[k] - static_cast<uint32_t>(c0)) * 4u : 0u);
+  if (staged) mbar_wait(&s_bar, 0u);            // all source rows of the CTA have landed
   float* dst = out + origin + tbase;
-  for (int i = 0; i < n_rows; ++i, src += T, dst += T) {
-    asm volatile("" : "+l"(src), "+l"(dst));
+  for (int i = 0; i < n_rows; ++i, dst += T) {
     float v[kStgFrames];
     if ((rowbits >> i) & 1u) {
 #pragma unroll
       for (int k = 0; k < kStgFrames; ++k) v[k] = mask_value;
     } else if (!warp) {
+      const float* src = in + (dst - out);
 #pragma unroll
       for (int k = 0; k < kStgFrames; ++k) {
         if constexpr (kFix != 0) v[k] = on[k] ? AUG_FINISH(__ldg(src + k * kStep), k, 0) : mask_value;
@@ -562,73 +595,59 @@ __global__ void __launch_bounds__(kStgThreads, 4) augment_staged_kernel(const fl
       const int4 rr = s_row[i];
       const float wy0 = __int_as_float(rr.y), wy1 = __int_as_float(rr.z);
       const bool use1 = rr.w >= 0;
-      float t0a[kStgFrames], t0c[kStgFrames], t1a[kStgFrames], t1c[kStgFrames];
-      if (staged) {
-        const int s0 = rr.x - smin;
-        if (!((ready >> s0) & 1u)) {
-          mbar_wait(&s_bar[s0], 0u);
-          ready |= 1u << s0;
-        }
-        const char* b0 = reinterpret_cast<const char*>(s_buf + s0 * kStgCols);
-#pragma unroll
-        for (int k = 0; k < kStgFrames; ++k) {
-          t0a[k] = *reinterpret_cast<const float*>(b0 + lo[k]);
-          t0c[k] = *reinterpret_cast<const float*>(b0 + lo[k] + 4);
-        }
-        if (use1) {
-          const int s1 = rr.w - smin;
-          if (!((ready >> s1) & 1u)) {
-            mbar_wait(&s_bar[s1], 0u);
-            ready |= 1u << s1;
-          }
-          const char* b1 = reinterpret_cast<const char*>(s_buf + s1 * kStgCols);
+      // the taps of source row `which` (0: rr.x, 1: rr.w) for this thread's frames, finished if the instance finishes cells
+      float ta[kStgFrames], tc[kStgFrames], acc[kStgFrames];
+      auto taps = [&](int srow) {
+        if (staged) {
+          const uint32_t o = static_cast<uint32_t>(srow - smin) * (kStgCols * 4u);
 #pragma unroll
           for (int k = 0; k < kStgFrames; ++k) {
-            t1a[k] = *reinterpret_cast<const float*>(b1 + lo[k]);
-            t1c[k] = *reinterpret_cast<const float*>(b1 + lo[k] + 4);
+            ta[k] = lds_f32(lo[k] + o);
+            tc[k] = lds_f32_4(lo[k] + o);
           }
-        }
-      } else {
-        const float* row0 = in + origin + (rr.x - r0) * T;
-#pragma unroll
-        for (int k = 0; k < kStgFrames; ++k) {
-          const float* q = elem_ptr(row0, e[k]);
-          t0a[k] = __ldg(q);
-          t0c[k] = __ldg(q + 1);
-        }
-        if (use1) {
-          const float* row1 = in + origin + (rr.w - r0) * T;
+        } else {
+          const float* row = in + origin + (srow - r0) * T;
 #pragma unroll
           for (int k = 0; k < kStgFrames; ++k) {
-            const float* q = elem_ptr(row1, e[k]);
-            t1a[k] = __ldg(q);
-            t1c[k] = __ldg(q + 1);
+            const float* q = elem_ptr(row, e[k]);
+            ta[k] = __ldg(q);
+            tc[k] = __ldg(q + 1);
           }
         }
-      }
-#pragma unroll
-      for (int k = 0; k < kStgFrames; ++k) {
         if constexpr (kFix != 0) {
-          t0a[k] = AUG_FINISH(t0a[k], k, 0);
-          t0c[k] = AUG_FINISH(t0c[k], k, 1);
-        }
-        float acc = 0.0f;          // taps accumulate in grid_sample's order
-        acc += t0a[k] * (wa[k] * wy0);
-        acc += t0c[k] * (wc[k] * wy0);
-        if (use1) {
-          if constexpr (kFix != 0) {
-            t1a[k] = AUG_FINISH(t1a[k], k, 0);
-            t1c[k] = AUG_FINISH(t1c[k], k, 1);
+#pragma unroll
+          for (int k = 0; k < kStgFrames; ++k) {
+            ta[k] = AUG_FINISH(ta[k], k, 0);
+            tc[k] = AUG_FINISH(tc[k], k, 1);
           }
-          acc += t1a[k] * (wa[k] * wy1);
-          acc += t1c[k] * (wc[k] * wy1);
         }
-        v[k] = on[k] ? acc : mask_value;
+      };
+      taps(rr.x);
+#pragma unroll
+      for (int k = 0; k < kStgFrames; ++k) {   // taps accumulate in grid_sample's order
+        acc[k] = 0.0f;
+        acc[k] += ta[k] * (wa[k] * wy0);
+        acc[k] += tc[k] * (wc[k] * wy0);
       }
+      if (use1) {      // warp-uniform: a sliver of weight on the next row (float32 rounding of the row coordinate)
+        taps(rr.w);
+#pragma unroll
+        for (int k = 0; k < kStgFrames; ++k) {
+          acc[k] += ta[k] * (wa[k] * wy1);
+          acc[k] += tc[k] * (wc[k] * wy1);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kStgFrames; ++k) v[k] = on[k] ? acc[k] : mask_value;
     }
 #pragma unroll
-    for (int k = 0; k < kStgFrames; ++k)
+    for (int k = 0; k < kStgFrames; ++k) {
+#if defined(WFT_AUG_KO) && (WFT_AUG_KO & 2)   // knock-out build (timing only): no stores
+      if (tbase + k * kStep < T && v[k] != v[k]) dst[k * kStep] = v[k];
+#else
       if (tbase + k * kStep < T) dst[k * kStep] = v[k];
+#endif
+    }
   }
 #undef AUG_FINISH
 }

@@ -580,7 +580,7 @@ static int launch_augment(const float* in, float* out, int32_t batch, int32_t n_
   // generic instance (tests compare the two bit for bit)
   const bool stage = (n_frames & 3) == 0 && n_frames >= 8 && !g_debug_aug_generic;
   if (stage) {
-    cfg.gridDim = dim3((n_frames + wft::kStgBlock - 1) / wft::kStgBlock, (n_rows + wft::kAugRowsPerCta - 1) / wft::kAugRowsPerCta, batch);
+    cfg.gridDim = dim3((n_frames + wft::kStgBlock - 1) / wft::kStgBlock, (n_rows + wft::kStgRows - 1) / wft::kStgRows, batch);
     cfg.blockDim = dim3(wft::kStgThreads);
     cfg.dynamicSmemBytes = wft::kStgSmemBytes;
   }
