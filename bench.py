@@ -530,7 +530,7 @@ def run_ours(args):
             "what": "ONE call, two grids: front-end grid -> fused epilogue grid (finishes the cells on load: max-8 floor / pad; time-warp "
                     "W=80 -> time mask -> frequency mask) that draws the clip's warp point and mask intervals itself; device-resident "
                     "PCM, same blocks / stream as `value`",
-            "epilogue_roofline": {"bound": "hbm", "kernel": "augment_kernel<false, 0>", "kernel_ms": epi_ms,
+            "epilogue_roofline": {"bound": "hbm", "kernel": "augment_staged_kernel<false, 0>", "kernel_ms": epi_ms,
                                   "algorithmic_bytes_per_launch": epi_bytes, "achieved": epi_bytes / (epi_ms * 1e-3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": epi_bytes / (epi_ms * 1e-3) / 1e9 / peak}}
         if multi is not None:

@@ -87,9 +87,10 @@ class FrontEnd:
                 and pcm.dtype in (torch.float32, torch.int16) and pcm.stride(1) == 1):
             # the production batch (configs/*: time_warp_w = 80) as ONE call: front-end grid -> ONE epilogue grid that finishes the
             # cells as it loads them (floor / pad / silent tiles) and draws the clip's warp point and mask intervals itself.  The
-            # un-warped features go through a rotation of scratch buffers (up to 1 GiB of them, 2 .. 16), so that the following
-            # batches' front-end grids may run under this batch's epilogue (wft.set_overlap: an independent launch has to stay
-            # clear of every call that may still be in flight, see ops._LAST_CALL)
+            # un-warped features go through a rotation of scratch buffers, so that the following batches' front-end grids may run
+            # under this batch's epilogue (wft.set_overlap: an independent launch has to stay clear of every call that may still
+            # be in flight, see ops._LAST_CALL -- two buffers once the epilogue's grid outgrows the device, which bounds what can
+            # be in flight to the call in front; up to 16 (1 GiB at most) for the small batches that fit on the GPU side by side)
             from .audio import as_i32_on
 
             if torch.cuda.is_current_stream_capturing():
@@ -99,7 +100,10 @@ class FrontEnd:
                 turn = self._scratch_turn.get(st, 0)
                 self._scratch_turn[st] = turn + 1
                 nbytes = B * self.n_mels * self.n_frames * 4
-                key = (st, B, turn % max(2, min(16, (1 << 30) // nbytes)))
+                from .ops import _epilogue_outgrows_device
+
+                ring = 2 if _epilogue_outgrows_device(self.device, B, self.n_mels, self.n_frames) else max(2, min(16, (1 << 30) // nbytes))
+                key = (st, B, turn % ring)
                 plain = self._scratch.get(key)
                 if plain is None:
                     for k in [k for k in self._scratch if k[0] == st and k[1] != B]:   # batch size changed on this stream

@@ -145,7 +145,13 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
                 flags |= _lib.WFT_LAUNCH_OVERLAP
                 hist.append((reads, writes))
             else:
-                _LAST_CALL[(dev.index, stream)] = [(reads, writes)]
+                hist = _LAST_CALL[(dev.index, stream)] = [(reads, writes)]
+            if aug is not None and _epilogue_outgrows_device(dev, B, n_mels, out.shape[2]):
+                # The grid behind this call's epilogue may only be scheduled once every epilogue CTA has started, and this
+                # epilogue has more CTAs than the device can hold at once: some of them will have finished by then, i.e. got
+                # past their wait for this call's front-end grid -- and grids complete in order, so everything in front of
+                # this call is complete as well.  Nothing older than this call can be in flight next to a later launch.
+                del hist[:-1]
         args = _lib.FrontendArgs(
             pcm=pcm.data_ptr(),
             pcm_dtype=_lib.WFT_PCM_F32 if pcm.dtype == torch.float32 else _lib.WFT_PCM_I16,
@@ -177,6 +183,18 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
         if rc != 0 and key is not None:
             _WORKSPACES.pop(key, None)   # a launch that did not happen leaves the ring bookkeeping undefined
         _lib.check(rc)
+
+
+_SM_COUNT = {}
+
+
+def _epilogue_outgrows_device(dev: torch.device, batch: int, n_rows: int, n_frames: int) -> bool:
+    """More CTAs in the augmentation epilogue's grid than can be resident at once?  (Either instance of the kernel covers at
+    most 1024 frames x 16 rows with a 256-thread CTA; 2048 threads per SM bound the residents whatever else limits them.)"""
+    sms = _SM_COUNT.get(dev.index)
+    if sms is None:
+        sms = _SM_COUNT[dev.index] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return ((n_frames + 1023) // 1024) * ((n_rows + 15) // 16) * batch > sms * 8
 
 
 def _frames(pcm: Tensor, padding: int, n_frames_out: int) -> int:
