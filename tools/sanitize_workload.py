@@ -1,8 +1,9 @@
 """The workload run under compute-sanitizer (memcheck / synccheck / racecheck): every kernel of the library, and every path of
 the fused kernel and its fix-up grid -- ragged lengths (silent tiles), partial-segment cuts, masks, int16 / 80 mel, capped
 grids, one long clip whose floor binds, a config-3 style batch, overlapping independent batches on the workspace ring
-(more than one trip round it), intervals drawn inside the kernel, the fused augmentation epilogue, the draws, pad_or_trim
-and the activation mask."""
+(more than one trip round it), intervals drawn inside the kernel, the production call (front-end grid -> staged epilogue that
+finishes the cells on load) with its generic instance and under CUDA graph replay, the fused augmentation epilogue, the
+draws, pad_or_trim and the activation mask."""
 import os
 import sys
 
@@ -54,6 +55,31 @@ for i in range(20):
 w.set_overlap(old)
 torch.cuda.synchronize()
 assert torch.equal(bufs[1], fe_plain(pcm, lengths=lengths_d, n_valid_frames=nv_d))
+# the production call on full-length clips (front-end grid -> staged epilogue that finishes the cells on load, floor-only
+# instance), the same through the generic epilogue instance, an odd frame count (generic only), and a captured + replayed call
+fe_full = w.FrontEnd(n_mels=128, spec_augment=True, seed=4,
+                     spec_augment_params={"time_mask_param": 100, "freq_mask_param": 27, "time_warp_w": 80, "p": 1.0})
+quiet = pcm.clone()
+quiet[1, 100000:] = 0.0                       # the floor binds
+y_staged = fe_full(quiet, clip_offset=7)
+lib.wft_debug_set_augment_generic(1)
+y_generic = fe_full(quiet, clip_offset=7)
+lib.wft_debug_set_augment_generic(0)
+assert torch.equal(y_staged, y_generic)
+odd = w.augment_epilogue(out[:, :, :2999].contiguous(), w.draw_warp_params(1, 0, 3, 2999, 80), masks, None)
+static_in, static_out = quiet.clone(), torch.empty_like(y_staged)
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    fe_full(static_in, clip_offset=7, out=static_out)
+torch.cuda.current_stream().wait_stream(side)
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    fe_full(static_in, clip_offset=7, out=static_out)
+graph.replay()
+graph.replay()
+torch.cuda.synchronize()
+assert torch.equal(static_out, y_staged)
 wp = w.draw_warp_params(1, 0, 3, 3000, 80)
 tw = w.time_warp(out, wp)
 ep = w.augment_epilogue(out, wp, masks, None, spline="f32")
