@@ -270,22 +270,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 }
 
 // interior tile: the 2800 samples travel as 9 bulk copies (8 blocks of 320 samples + a 240-sample tail), block b landing
-// at element (320 + skew) * b (the skew keeps stage A's stride-20 gathers conflict free).  The issue is SPLIT over the five
-// warps -- lane 0 of warp w sends blocks w and w + 5 and announces their bytes with its own arrive.expect_tx (the mbarrier
-// expects kWarps arrivals per phase): a single thread issuing all nine copies held its warp back by ~2000 cycles per tile
-// (per-warp clock stamps, tools/timeline.cu), and every phase of a tile ends on a CTA barrier.
+// at element (320 + skew) * b (the skew keeps stage A's stride-20 gathers conflict free).  ONE warp issues them, lane b sends
+// block b and lane 0 announces the bytes of the whole tile (the mbarrier expects one arrival per phase): the issue sequence
+// (~40 instructions: fence, shared-window addresses, cache policy, the copy) then costs the CTA once.  A single THREAD issuing
+// all nine held its warp back by ~2000 cycles per tile (tools/timeline.cu); lane 0 of every warp sending two blocks each
+// fixed that, but all five warps then executed the sequence -- 300 of a tile's 4600 warp-instructions.
+constexpr int kPrefetchWarp = 2;   // (not warp 0: it describes the next tile and publishes the statistics)
 template <typename PcmT>
-__device__ __forceinline__ void prefetch_audio_part(PcmT* __restrict__ sm_audio, const PcmT* __restrict__ src, uint64_t* bar, int warp) {
+__device__ __forceinline__ void prefetch_audio_tile(PcmT* __restrict__ sm_audio, const PcmT* __restrict__ src, uint64_t* bar, int lane) {
   constexpr int kBlocks = (kTileSamples + kSkewBlock - 1) / kSkewBlock;  // 9
   constexpr uint32_t kFull = kSkewBlock * sizeof(PcmT), kTail = (kTileSamples - (kBlocks - 1) * kSkewBlock) * sizeof(PcmT);
-  static_assert(kBlocks > kWarps && kBlocks <= 2 * kWarps, "every warp sends one or two blocks");
-  const int b1 = warp + kWarps;
-  const bool two = b1 < kBlocks;
-  const uint32_t bytes1 = b1 == kBlocks - 1 ? kTail : kFull;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the region comes first
-  mbar_expect_tx(bar, kFull + (two ? bytes1 : 0u));
-  tma_bulk_g2s(sm_audio + warp * (kSkewBlock + Skew<PcmT>::value), src + warp * kSkewBlock, kFull, bar);
-  if (two) tma_bulk_g2s(sm_audio + b1 * (kSkewBlock + Skew<PcmT>::value), src + b1 * kSkewBlock, bytes1, bar);
+  static_assert(kBlocks <= 32, "one lane per block");
+  if (lane < kBlocks) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy use of the region comes first
+  if (lane == 0) mbar_expect_tx(bar, kTileSamples * sizeof(PcmT));
+  __syncwarp();
+  if (lane < kBlocks)
+    tma_bulk_g2s(sm_audio + lane * (kSkewBlock + Skew<PcmT>::value), src + lane * kSkewBlock, lane == kBlocks - 1 ? kTail : kFull, bar);
 }
 
 // generic synchronous staging (clip edges, ragged lengths, unaligned sources)
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   if (draw_cache != nullptr) __syncthreads();   // the first describe_tile below reads the drawn intervals
   if (tid == 0) {
     sm_ctl[kCtlMemo] = -1;
-    mbar_init(audio_bar, kWarps);   // one arrive.expect_tx per warp and tile (prefetch_audio_part)
+    mbar_init(audio_bar, 1);   // one arrive.expect_tx per tile (prefetch_audio_tile)
     const int first = static_cast<int>(atomicAdd(p.tile_counter, static_cast<uint32_t>(p.chunk)));
     sm_ctl[kCtlChunkNext] = first + 1;
     sm_ctl[kCtlChunkLeft] = p.chunk - 1;
@@ -882,9 +882,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
   }
   __syncthreads();
   // a tile of kind kTileInterior always arrives by TMA: the first one is sent here, every later one under the tile before it
-  if (lane == 0 && sm_ctl[kCtlDesc + kDescKind] == kTileInterior) {
+  if (warp == kPrefetchWarp && sm_ctl[kCtlDesc + kDescKind] == kTileInterior) {
     const long long off = (static_cast<long long>(sm_ctl[kCtlDesc + kDescPcmHi]) << 32) | static_cast<unsigned int>(sm_ctl[kCtlDesc + kDescPcmLo]);
-    prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
+    prefetch_audio_tile<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, lane);
   }
   // loop state in ONE register: bit 4 (kCtlSlot) = descriptor slot of the CURRENT tile, bit 0 = parity of the audio mbarrier
   int lstate = 0;
@@ -1012,10 +1012,10 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
         __syncthreads();  // exchange is dead: the region becomes power tile (bottom) + next audio tile (top)
         WFT_TL(7);
         // prefetch the NEXT tile's PCM into the top of the region (its descriptor stays in sm_ctl until the loop ends)
-        if (lane == 0 && NDESC[kDescKind] == kTileInterior) {
+        if (warp == kPrefetchWarp && NDESC[kDescKind] == kTileInterior) {
           const long long off = (static_cast<long long>(NDESC[kDescPcmHi]) << 32) | static_cast<unsigned int>(NDESC[kDescPcmLo]);
           WFT_TL(13);
-          prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
+          prefetch_audio_tile<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, lane);
           WFT_TL(14);
         }
 
@@ -1100,9 +1100,9 @@ __global__ void __launch_bounds__(kThreads, 6) frontend_kernel(const FrontendPar
       __syncthreads();  // the previous tile's last readers of the other descriptor slot are done
       if (tid == 0) DESCRIBE_NEXT();
       __syncthreads();
-      if (lane == 0 && NDESC[kDescKind] == kTileInterior) {
+      if (warp == kPrefetchWarp && NDESC[kDescKind] == kTileInterior) {
         const long long off = (static_cast<long long>(NDESC[kDescPcmHi]) << 32) | static_cast<unsigned int>(NDESC[kDescPcmLo]);
-        prefetch_audio_part<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, warp);
+        prefetch_audio_tile<PcmT>(sm_audio, reinterpret_cast<const PcmT*>(p.pcm) + off, audio_bar, lane);
       }
       if (lane == 0) {
         const int clip = d_top.y, t0 = d_top.z, kind = d_top.w;   // (short path: the loop-top read is still in registers)
