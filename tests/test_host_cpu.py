@@ -321,3 +321,45 @@ def test_torch_custom_ops_are_registered_with_fake_kernels(wft):
         act = torch.empty(2, 1500, 1280, device="cuda", dtype=torch.bfloat16, requires_grad=True)
         z = torch.ops.wft.mask_bsd(act, 1, 2, 3, 4)
         assert z.dtype == torch.bfloat16 and z.requires_grad, "the autograd formula is registered"
+
+
+def test_independent_launch_bookkeeping(wft):
+    """ops._record_call: a front-end call is launched as an independent batch (WFT_LAUNCH_OVERLAP: it waits for nothing) only
+    if its buffers stay clear of EVERY call enqueued since the last waiting launch -- with small batches whole calls run side
+    by side, so the call directly in front is not the only one that may still be in flight -- and a call whose epilogue grid
+    outgrows the device bounds that set to itself."""
+    from whisper_finetune_b200.ops import _record_call
+
+    def call(pcm, out, scratch=None):
+        return [(pcm, pcm + 100)], [(out, out + 100)] + ([(scratch, scratch + 100)] if scratch is not None else [])
+
+    # first call on a stream: nothing to be independent of
+    ind, hist = _record_call(None, *call(0, 1000), may_overlap=True, bounds_in_flight=False)
+    assert not ind and len(hist) == 1
+    # distinct buffers: independent, the history grows
+    ind, hist = _record_call(hist, *call(200, 1200), may_overlap=True, bounds_in_flight=False)
+    assert ind and len(hist) == 2
+    ind, hist = _record_call(hist, *call(400, 1400), may_overlap=True, bounds_in_flight=False)
+    assert ind and len(hist) == 3
+    # re-using the output of the call THREE back: must wait (it may still be running), the history restarts
+    ind, hist = _record_call(hist, *call(600, 1000), may_overlap=True, bounds_in_flight=False)
+    assert not ind and len(hist) == 1
+    # reading what an earlier call writes, or writing what it reads: wait
+    ind, hist2 = _record_call(hist, *call(1000, 1600), may_overlap=True, bounds_in_flight=False)
+    assert not ind
+    ind, hist2 = _record_call(hist, *call(700, 600), may_overlap=True, bounds_in_flight=False)
+    assert not ind
+    # overlap switched off / ring wrap: never independent
+    ind, hist2 = _record_call(hist, *call(800, 1800), may_overlap=False, bounds_in_flight=False)
+    assert not ind and len(hist2) == 1
+    # production calls with two alternating scratch buffers: fine once the epilogue grid bounds what is in flight ...
+    hist = None
+    for k in range(6):
+        ind, hist = _record_call(hist, *call(5000, 6000 + 200 * k, scratch=9000 + 200 * (k % 2)), may_overlap=True, bounds_in_flight=True)
+        assert ind == (k > 0) and len(hist) == 1
+    # ... and a conflict with the call two back when it does not (small batches)
+    hist, seen = None, []
+    for k in range(6):
+        ind, hist = _record_call(hist, *call(5000, 6000 + 200 * k, scratch=9000 + 200 * (k % 2)), may_overlap=True, bounds_in_flight=False)
+        seen.append(ind)
+    assert seen == [False, True, False, True, False, True]

@@ -3,11 +3,13 @@
 // data/utils.py:41-190), optionally finishing the cells the front-end kernel could not (wft_frontend_augment_forward).
 //
 // Two kernels compute the same function, bit for bit:
-//   augment_staged_kernel  the production instance (n_frames % 4 == 0, 16-byte aligned tensors).  A CTA owns 512 output frames
-//                          x 16 rows; the window of source columns its taps fall into travels global -> shared memory as ONE
-//                          bulk copy (TMA, mbarrier completion) per source row, all rows of the CTA in flight at once while the
-//                          threads are still evaluating the spline; the taps are then shared-memory loads at immediate offsets.
+//   augment_staged_kernel  the production instance (n_frames % 4 == 0, 16-byte aligned tensors).  A CTA owns 1024 output frames
+//                          x 8 rows; the window of source columns its taps fall into travels global -> shared memory as ONE
+//                          bulk copy (TMA, mbarrier completion) per source row, all rows of the CTA in flight at once; the taps
+//                          are then shared-memory loads at immediate offsets.
 //   augment_kernel         any shape / alignment: taps straight from global memory (L1).
+// Both keep ONE source column per frame: the bilinear taps are the in-row pair e, e + 1 with the weights re-assigned at the row
+// ends, so that no load is conditional and the second one sits at an immediate offset from the first.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -148,12 +150,7 @@ struct AugFix {
   int32_t n_samples, n_total, n_frames;   // of the front-end call (frames the clip really has; T is n_frames_out)
 };
 
-// grid = (frame blocks of 1024, row groups of 16, clips); a thread owns 4 output frames, 256 apart (lane <-> consecutive frames:
-// a warp's store is one 128-byte line and the two source taps of a smooth, monotone map fall into one or two lines -- with 4
-// ADJACENT frames per thread every scalar load of a warp was spread over 4-8 lines and the kernel sat at 0.40 of the HBM peak
-// on the L1 data pipe); it evaluates the 4 source coordinates once and walks the 16 rows of its group with 8 independent
-// loads in flight per row (bilinear taps mirror grid_sample's float32 arithmetic, zeros outside).
-// base + 4 * idx as ONE instruction (IMAD.WIDE.U32): left to itself the compiler widens, adds and scales in four
+// base + 4 * idx (the compiler, left to itself, widens, adds and scales in four instructions per load)
 __device__ __forceinline__ const float* elem_ptr(const float* base, uint32_t idx) {
   uint64_t a;
   asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(idx), "l"(reinterpret_cast<uint64_t>(base)));
@@ -240,6 +237,12 @@ __device__ __forceinline__ void aug_prologue(int b, int32_t R, int32_t T, const 
   if (kFix != 0 && kPublishFix && threadIdx.x == 96) aug_fix_publish(aug_fix_load(b, fix), fix, s_fix);
 }
 
+// ---- the generic instance -------------------------------------------------------------------------------------------------
+// grid = (frame blocks of 1024, row groups of 16, clips); a thread owns 4 output frames, 256 apart (lane <-> consecutive frames:
+// a warp's store is one 128-byte line and the two source taps of a smooth map fall into one or two lines -- with 4 ADJACENT
+// frames per thread every scalar load of a warp was spread over 4-8 lines); it evaluates the 4 source coordinates once and
+// walks the 16 rows of its group with 8 independent loads in flight per row (bilinear taps mirror grid_sample's float32
+// arithmetic, zeros outside).
 // kFix: 0 = `in` holds finished features; 1 = finish on load, full-length clips without a cut (the floor is all there is);
 // 2 = finish on load, ragged batch (lengths / cuts / output longer than the clip: per-tap kinds; 64 registers, 4 CTAs per SM)
 template <bool kF32, int kFix>
@@ -279,13 +282,13 @@ __global__ void __launch_bounds__(kAugThreads, kFix == 2 ? 4 : 5) augment_kernel
   const bool warp = wp > 0 && wp < T - 1;          // anything else (the draw's "gate rejected" marker is -1) = no warp
   const int r0 = blockIdx.y * kAugRowsPerCta;
   const size_t origin = (static_cast<size_t>(b) * R + r0) * T;   // cell (b, r0, 0)
-  // Per frame, once: the left one of two neighbouring source columns e, e + 1 and their weights, and whether the cell is live.  The taps of grid_sample are columns a = floor(ix) and a + 1 with "zeros" padding; here they are
-  // always the in-row pair e = clamp(a, 0, T - 2), e + 1 -- both loads unconditional, the second one at an immediate offset --
-  // and a tap that falls outside gets weight 0 on a finite cell (0 * finite adds exactly nothing; at a = -1 / a = T - 1 the one
-  // live tap keeps its weight and the two products swap places in the sum, which changes no bit: x + 0 = 0 + x).  A row then
-  // costs one uniform row pointer and ONE integer instruction per frame (elem_ptr) for its eight loads; the row loop used to
-  // spend four per load, and with the store address re-derived from %tid every row, three quarters of all instructions of the
-  // kernel were address arithmetic (ncu: 28 M warp-instructions per B = 64 launch, 36 per output cell).
+  // Per frame, once: the left one of two neighbouring source columns e, e + 1, their weights, and whether the cell is live.
+  // The taps of grid_sample are columns a = floor(ix) and a + 1 with "zeros" padding; here they are always the in-row pair
+  // e = clamp(a, 0, T - 2), e + 1 -- both loads unconditional, the second one at an immediate offset -- and a tap that falls
+  // outside gets weight 0 on a finite cell (0 * finite adds exactly nothing; at a = -1 / a = T - 1 the one live tap keeps its
+  // weight and the two products swap places in the sum, which changes no bit: x + 0 = 0 + x).  A row then costs one uniform
+  // row pointer and one address per frame for its eight loads (ncu on the version with two clamped columns per frame: 28 M
+  // warp-instructions per B = 64 launch, 36 per output cell, three quarters of them 64-bit address arithmetic).
   uint32_t e[kAugFramesPerThread];
   float wa[kAugFramesPerThread], wc[kAugFramesPerThread];
   bool on[kAugFramesPerThread];

@@ -138,20 +138,13 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
             if aug is not None:
                 reads += [_span(t) for t in aug[1]]
                 writes += [_span(aug[2])]
-            hist = _LAST_CALL.get((dev.index, stream))
-            if (_OVERLAP["enabled"] and hist and mode != _lib.WFT_WS_RING       # (ring position 0: the memset waits anyway)
-                    and all(_disjoint(w, q) for prev_reads, prev_writes in hist for w in writes for q in prev_writes + prev_reads)
-                    and all(_disjoint(r, q) for _, prev_writes in hist for r in reads for q in prev_writes)):
+            independent, hist = _record_call(
+                _LAST_CALL.get((dev.index, stream)), reads, writes,
+                may_overlap=_OVERLAP["enabled"] and mode != _lib.WFT_WS_RING,      # (ring position 0: the memset waits anyway)
+                bounds_in_flight=aug is not None and _epilogue_outgrows_device(dev, B, n_mels, out.shape[2]))
+            _LAST_CALL[(dev.index, stream)] = hist
+            if independent:
                 flags |= _lib.WFT_LAUNCH_OVERLAP
-                hist.append((reads, writes))
-            else:
-                hist = _LAST_CALL[(dev.index, stream)] = [(reads, writes)]
-            if aug is not None and _epilogue_outgrows_device(dev, B, n_mels, out.shape[2]):
-                # The grid behind this call's epilogue may only be scheduled once every epilogue CTA has started, and this
-                # epilogue has more CTAs than the device can hold at once: some of them will have finished by then, i.e. got
-                # past their wait for this call's front-end grid -- and grids complete in order, so everything in front of
-                # this call is complete as well.  Nothing older than this call can be in flight next to a later launch.
-                del hist[:-1]
         args = _lib.FrontendArgs(
             pcm=pcm.data_ptr(),
             pcm_dtype=_lib.WFT_PCM_F32 if pcm.dtype == torch.float32 else _lib.WFT_PCM_I16,
@@ -183,6 +176,25 @@ def _launch_frontend(pcm: Tensor, n_mels: int, padding: int, lengths: Optional[T
         if rc != 0 and key is not None:
             _WORKSPACES.pop(key, None)   # a launch that did not happen leaves the ring bookkeeping undefined
         _lib.check(rc)
+
+
+def _record_call(hist, reads, writes, may_overlap: bool, bounds_in_flight: bool):
+    """The launch decision for a front-end call on a stream whose calls since the last waiting launch are ``hist`` (a list of
+    ``(reads, writes)`` byte ranges, or None) -> ``(independent, new_hist)``.
+
+    The call may be launched as an independent batch (it will not wait for anything in front of it) only if it writes nothing
+    any call in ``hist`` reads or writes and reads nothing any of them writes; otherwise it waits, and everything in front of
+    a waiting launch is complete by the time it runs, so the history starts again with this call.  ``bounds_in_flight``: this
+    call's epilogue grid has more CTAs than the device can hold.  The grid behind it may only be scheduled once every
+    epilogue CTA has started, so some of them will have finished by then, i.e. got past their wait for this call's front-end
+    grid -- and grids of a stream complete in order: nothing older than this call can be in flight next to a later launch."""
+    independent = bool(may_overlap and hist
+                       and all(_disjoint(w, q) for prev_reads, prev_writes in hist for w in writes for q in prev_writes + prev_reads)
+                       and all(_disjoint(r, q) for _, prev_writes in hist for r in reads for q in prev_writes))
+    hist = (hist + [(reads, writes)]) if independent else [(reads, writes)]
+    if bounds_in_flight:
+        hist = hist[-1:]
+    return independent, hist
 
 
 _SM_COUNT = {}
