@@ -171,35 +171,44 @@ __global__ void min_reduce_kernel(const float* __restrict__ in, int64_t n, uint3
 }
 
 // out[o, l, i] = l < len_in ? in[o, l, i] : min(in)      (data/utils.py:380-404)
+// grid.y walks `outer`, grid.x x threads walk the len_out * inner cells of one outer slice: the cell index splits into (l, i)
+// with 32-bit arithmetic (or none at all when inner == 1, the axis = -1 case of data_loader.py:282) instead of two 64-bit
+// divisions per element.
 __global__ void pad_or_trim_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t outer,
                                    int64_t len_in, int64_t inner, int64_t len_out,
                                    const uint32_t* __restrict__ min_inv) {
-  const int64_t n = outer * len_out * inner;
   const float fill = (len_out > len_in) ? (min_inv[1] != 0u ? __int_as_float(0x7fc00000) : wft::dec_ordered(~min_inv[0])) : 0.0f;
-  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < n;
-       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t i = k % inner;
-    const int64_t l = (k / inner) % len_out;
-    const int64_t o = k / (inner * len_out);
-    out[k] = (l < len_in) ? __ldg(in + (o * len_in + l) * inner + i) : fill;
+  const int64_t per_out = len_out * inner, per_in = len_in * inner;
+  const int64_t live = (len_in < len_out ? len_in : len_out) * inner;   // cells [0, live) of a slice are copies, the rest the fill
+  for (int64_t o = blockIdx.y; o < outer; o += gridDim.y) {
+    const float* src = in + o * per_in;
+    float* dst = out + o * per_out;
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < per_out;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x)
+      dst[j] = j < live ? __ldg(src + j) : fill;
   }
 }
 
 // torchaudio mask_along_axis for time then frequency (data_loader.py:286-287), explicit intervals
+// grid = (frame chunks, row chunks, clips): rows and frames are walked by their own indices (no division); a masked row is
+// written without being read, an in-place call only touches the masked cells
 __global__ void specaug_apply_kernel(const float* __restrict__ in, float* __restrict__ out, int32_t n_rows,
                                      int32_t n_frames, const int32_t* __restrict__ mask_params, float mask_value) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.z;
   const int4 mk = __ldg(reinterpret_cast<const int4*>(mask_params) + b);
   const int64_t per_clip = static_cast<int64_t>(n_rows) * n_frames;
   const float* src = in + b * per_clip;
   float* dst = out + b * per_clip;
-  for (int64_t k = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; k < per_clip;
-       k += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(k / n_frames);
-    const int t = static_cast<int>(k - static_cast<int64_t>(r) * n_frames);
-    const bool masked = (t >= mk.x && t < mk.y) || (r >= mk.z && r < mk.w);
-    if (masked) dst[k] = mask_value;
-    else if (src != dst) dst[k] = src[k];
+  const bool in_place = src == dst;
+  for (int r = blockIdx.y; r < n_rows; r += gridDim.y) {
+    const bool rowmask = r >= mk.z && r < mk.w;
+    const float* s = src + static_cast<int64_t>(r) * n_frames;
+    float* d = dst + static_cast<int64_t>(r) * n_frames;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_frames; t += gridDim.x * blockDim.x) {
+      const bool masked = rowmask || (t >= mk.x && t < mk.y);
+      if (masked) d[t] = mask_value;
+      else if (!in_place) d[t] = __ldg(s + t);
+    }
   }
 }
 
@@ -483,8 +492,12 @@ int wft_pad_or_trim_f32(const float* in, int64_t outer, int64_t len_in, int64_t 
   } else if (in == nullptr) {
     return fail(WFT_ERR_INVALID, "in is NULL");
   }
-  pad_or_trim_kernel<<<grid_1d(n_out, 256), 256, 0, stream>>>(in, out, outer, len_in, inner, len_out,
-                                                               static_cast<const uint32_t*>(scratch));
+  {
+    const int gx = grid_1d(len_out * inner, 256);
+    const int64_t gy_want = outer < 1 ? 1 : outer, gy_cap = (148 * 16 + gx - 1) / gx;
+    const dim3 grid(gx, static_cast<unsigned>(gy_want < gy_cap ? gy_want : (gy_cap < 1 ? 1 : gy_cap)));
+    pad_or_trim_kernel<<<grid, 256, 0, stream>>>(in, out, outer, len_in, inner, len_out, static_cast<const uint32_t*>(scratch));
+  }
   ++g_launches;
   WFT_CUDA(cudaGetLastError());
   return WFT_OK;
@@ -498,7 +511,10 @@ int wft_specaug_apply_f32(const float* in, float* out, int32_t batch, int32_t n_
   if (in == nullptr || out == nullptr || mask_params == nullptr) return fail(WFT_ERR_INVALID, "NULL pointer");
   if ((reinterpret_cast<uintptr_t>(mask_params) & 15) != 0) return fail(WFT_ERR_INVALID, "mask_params must be 16-byte aligned");
   if (batch > 65535) return fail(WFT_ERR_INVALID, "batch too large for one launch (max 65535)");
-  dim3 grid(grid_1d(static_cast<int64_t>(n_rows) * n_frames, 256), batch);
+  const int gx = grid_1d(n_frames, 256);
+  int gy = (148 * 16 + gx * batch - 1) / (gx * batch);
+  gy = gy < 1 ? 1 : (gy > n_rows ? n_rows : gy);
+  dim3 grid(gx, gy, batch);
   specaug_apply_kernel<<<grid, 256, 0, stream>>>(in, out, n_rows, n_frames, mask_params, mask_value);
   ++g_launches;
   WFT_CUDA(cudaGetLastError());
