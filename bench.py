@@ -416,14 +416,14 @@ def run_ours(args):
     epi_ms = epi_block_ms / args.steps
 
     # end to end through the public API with host buffers (pinned): H2D + kernels + D2H every step
-    def run_e2e(pcm_dtype, readback):
+    def run_e2e(pcm_dtype, readback, front_end=None):
         host_pcm = [synth_pcm(BATCH, SEED + 1000 * rank + s) for s in range(2)]
         if pcm_dtype == torch.int16:
             host_pcm = [(x * 32767).round().to(torch.int16) for x in host_pcm]
         host_pcm = [x.pin_memory() for x in host_pcm]
         shape = (BATCH, N_MELS, N_FRAMES) if readback == "features" else (BATCH,)
         host_out = [torch.empty(shape).pin_memory() for _ in range(2)]
-        pipe = wft.HostPipeline(fe, BATCH, pcm_dtype=pcm_dtype, n_chunks=4, n_streams=2, readback=readback)
+        pipe = wft.HostPipeline(front_end or fe, BATCH, pcm_dtype=pcm_dtype, n_chunks=4, n_streams=2, readback=readback)
         steps = max(3, min(args.steps, 20))
         for i in range(2):
             pipe(host_pcm[i % 2], host_out[i % 2], clip_offset=i * BATCH)
@@ -455,6 +455,10 @@ def run_ours(args):
                          ("f32_pcm_features_stay_on_device", torch.float32, "probe")):
         v, h2d, d2h, _, _ = run_e2e(dt, rb)
         e2e_variants[name] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    # the declared shape with the production configs' time-warp (front-end grid -> epilogue grid per chunk): the bus is still
+    # what bounds it
+    v, h2d, d2h, _, _ = run_e2e(torch.int16, "probe", front_end=fe_warp)
+    e2e_variants["int16_pcm_time_warp_features_stay_on_device"] = {"value": v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
     # multi-GPU correctness on the hardware (outside every timed region): each rank computes ITS DistributedSampler shard of
     # a fixed set of 8 * world clips (masks keyed by the global clip index), the shards are all-gathered over NCCL, and

@@ -553,7 +553,8 @@ __device__ __forceinline__ int kept_frames(const int32_t* n_valid, int clip, int
 
 constexpr int kFixThreads = 128;
 constexpr int kFixWarps = kFixThreads / 32;
-constexpr int kFixTiles = 32;   // tiles per CTA: one per lane of the scan
+constexpr int kFixTiles = 32;       // lean instance: tiles per warp and pass of the scan, one per lane
+constexpr int kFixTilesHeavy = 8;   // ragged batches rewrite a third or more of all tiles: smaller groups = four times the warps
 
 // what a lane found out about ITS tile during the scan; broadcast to the warp when the tile is rewritten
 struct FixTile {
@@ -563,14 +564,58 @@ struct FixTile {
 };
 
 // one warp finishes one tile; `constant` = nothing was written yet (silent or pad-only tile): every kept cell is the clamp value
-template <int NM, int kBatch>
+template <int NM, int kBatch, bool kHoist>
 __device__ __forceinline__ void fixup_tile(const FixupParams& p, const FixTile& ft, bool constant, int lane) {
   const float vsilent = feature_of_l2(silent_l2());
   const float floorn = ft.floorn, padv = ft.padv, mv = p.mask_value;
   const int keep = ft.keep, t0 = ft.t0, mt0 = ft.mt0, mt1 = ft.mt1, mf0 = ft.mf0, mf1 = ft.mf1;
   const int pitch = p.n_frames_out;
   float* base = p.out + static_cast<size_t>(ft.clip) * NM * pitch;
-  if ((pitch & 3) == 0) {
+  if (kHoist && (pitch & 3) == 0) {
+    constexpr int kGroups = kTileFrames / 4;        // float4 groups per row (4)
+    constexpr int kRowsPerPass = 32 / kGroups;      // 8 rows per warp-wide access
+    // kBatch = rows in flight per lane (2 in the lean instance, which has to stay within 32 registers)
+    static_assert(NM % (kRowsPerPass * kBatch) == 0, "row loop");
+    const int f = t0 + ((lane & (kGroups - 1)) << 2);
+    if (f >= pitch) return;
+    // A lane's four columns are the same for every row: which of them are pad / inside the time mask is decided once, and so
+    // is the whole value of a cell that needs no load (a tile that was never computed, columns beyond the kept frames) --
+    // ncu on a ragged batch: the per-cell selects were 770 warp-instructions per rewritten tile, 19 M per launch at IPC 0.9.
+    uint32_t padbits = 0, maskbits = 0;
+    float cv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int fc = f + c;
+      if (fc >= keep) padbits |= 1u << c;
+      if (fc >= mt0 && fc < mt1) maskbits |= 1u << c;
+      cv[c] = (fc >= mt0 && fc < mt1) ? mv : (fc >= keep ? padv : fmaxf(vsilent, floorn));
+    }
+    const float4 cv4 = make_float4(cv[0], cv[1], cv[2], cv[3]), mv4 = make_float4(mv, mv, mv, mv);
+    const bool load = !constant && f < keep;
+#pragma unroll 1
+    for (int r0 = lane / kGroups; r0 < NM; r0 += kRowsPerPass * kBatch) {
+      float4 v[kBatch];
+#pragma unroll
+      for (int it = 0; it < kBatch; ++it) {
+        const int row = r0 + kRowsPerPass * it;
+        const bool rowmask = row >= mf0 && row < mf1;
+        if (load && !rowmask) v[it] = __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * pitch + f));
+      }
+#pragma unroll
+      for (int it = 0; it < kBatch; ++it) {
+        const int row = r0 + kRowsPerPass * it;
+        const bool rowmask = row >= mf0 && row < mf1;
+        float4 o = rowmask ? mv4 : cv4;
+        if (load && !rowmask) {
+          float e[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) e[c] = ((maskbits >> c) & 1u) ? mv : (((padbits >> c) & 1u) ? padv : fmaxf(e[c], floorn));
+          o = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        *reinterpret_cast<float4*>(base + static_cast<size_t>(row) * pitch + f) = o;
+      }
+    }
+  } else if ((pitch & 3) == 0) {   // the lean instance (32 registers): everything per cell
     constexpr int kGroups = kTileFrames / 4;        // float4 groups per row (4)
     constexpr int kRowsPerPass = 32 / kGroups;      // 8 rows per warp-wide access
     // kBatch = rows in flight per lane (2 in the lean instance, which has to stay within 32 registers)
@@ -633,12 +678,13 @@ __global__ void __launch_bounds__(kFixThreads, kLean ? 16 : 4) fixup_kernel(cons
   // a WARP owns groups of 32 consecutive tiles (lane <-> tile), grid-stride: no shared memory, no barrier.  Every lane
   // gathers everything its own tile's rewrite needs (clip statistics, kept frames, mask intervals) -- 32 tiles' worth of
   // dependent loads in parallel -- and the warp then rewrites the flagged tiles one after the other from broadcast values.
-  for (int base = (static_cast<int>(blockIdx.x) * kFixWarps + warp) * kFixTiles; base < p.total_tiles;
-       base += static_cast<int>(gridDim.x) * kFixWarps * kFixTiles) {
+  constexpr int kGroup = kLean ? kFixTiles : kFixTilesHeavy;   // tiles per warp and pass (lanes beyond the group idle in the scan)
+  for (int base = (static_cast<int>(blockIdx.x) * kFixWarps + warp) * kGroup; base < p.total_tiles;
+       base += static_cast<int>(gridDim.x) * kFixWarps * kGroup) {
     const int tile = base + lane;
     bool needs = false, constant = false;
     FixTile ft{};
-    if (tile < p.total_tiles) {
+    if (lane < kGroup && tile < p.total_tiles) {
       ft.clip = tile / p.tiles_per_clip;
       ft.t0 = (tile - ft.clip * p.tiles_per_clip) * kTileFrames;
       if (ft.t0 < p.n_frames_out) {
@@ -684,7 +730,7 @@ __global__ void __launch_bounds__(kFixThreads, kLean ? 16 : 4) fixup_kernel(cons
       b.floorn = __shfl_sync(0xffffffffu, ft.floorn, l); b.padv = __shfl_sync(0xffffffffu, ft.padv, l);
       b.mt0 = __shfl_sync(0xffffffffu, ft.mt0, l); b.mt1 = __shfl_sync(0xffffffffu, ft.mt1, l);
       b.mf0 = __shfl_sync(0xffffffffu, ft.mf0, l); b.mf1 = __shfl_sync(0xffffffffu, ft.mf1, l);
-      fixup_tile<NM, 2>(p, b, ((cst >> l) & 1u) != 0u, lane);   // (8 rows in flight in the heavy instance: 113 registers, same time)
+      fixup_tile<NM, 2, !kLean>(p, b, ((cst >> l) & 1u) != 0u, lane);   // (8 rows in flight in the heavy instance: 113 registers, same time)
     }
   }
 }

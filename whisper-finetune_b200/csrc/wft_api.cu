@@ -114,9 +114,10 @@ int launch_frontend(const wft::FrontendParams& p, cudaStream_t stream, int launc
   f.draw_fparam = p.draw_fparam; f.draw_p = p.draw_p;
   f.n_samples = p.n_samples; f.n_total = p.n_total; f.n_frames = p.n_frames; f.n_frames_out = p.n_frames_out;
   f.tiles_per_clip = p.tiles_per_clip; f.total_tiles = p.total_tiles; f.mask_value = p.mask_value;
-  const int groups = (p.total_tiles + wft::kFixTiles * wft::kFixWarps - 1) / (wft::kFixTiles * wft::kFixWarps);
-  // ragged inputs (lengths / cuts / output longer than the clip) mean many constant-fill tiles: more CTAs per SM
+  // ragged inputs (lengths / cuts / output longer than the clip) mean many constant-fill tiles: more CTAs per SM, smaller groups
   const bool heavy = p.lengths != nullptr || p.n_valid != nullptr || p.n_frames_out > p.n_frames;
+  const int fix_per_cta = (heavy ? wft::kFixTilesHeavy : wft::kFixTiles) * wft::kFixWarps;
+  const int groups = (p.total_tiles + fix_per_cta - 1) / fix_per_cta;
   int fix_ctas = (ctas_full / 6) * (heavy ? 8 : 1);
   if (fix_ctas > groups) fix_ctas = groups;
   if (g_debug_max_ctas > 0 && fix_ctas > g_debug_max_ctas) fix_ctas = g_debug_max_ctas;
