@@ -57,6 +57,32 @@ def ncu_traffic():
         return None, f"no committed ncu capture ({type(e).__name__})"
 
 
+def other_bounds(kernel_ms, sm_count, sm_mhz):
+    """The bounds next to HBM that north_star asks about ("the slower of bytes at the HBM peak and DFT + mel FLOPs at the FMA
+    peak"), plus the SM resource ncu shows closest to saturation (L1 / shared-memory data pipe, one wavefront per cycle and
+    SM).  Numerators are COUNTED per B=64 launch by the committed ncu capture (profiles/ncu_traffic.json), the time is this
+    run's kernel_ms; None if there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+        hz = sm_mhz * 1e6
+        fma_peak = sm_count * 128 * 2 * hz                      # fp32: 128 FFMA lanes per SM and cycle
+        flops = float(d["fp32_flops_per_launch"])
+        wf = float(d["lsu_wavefronts_per_sm"])
+        t = kernel_ms * 1e-3
+        return {"fma_fp32": {"flops_per_launch": flops, "achieved_tflops": flops / t / 1e12, "peak_tflops": fma_peak / 1e12,
+                             "frac": flops / t / fma_peak, "ms_at_peak": flops / fma_peak * 1e3,
+                             "what": "fp32 operations the kernel executes (ncu thread-instruction counts: FFMA = 2, FFMA2 = 4), "
+                                     "peak = SMs x 128 FFMA x 2 x SM clock; smaller time than the HBM bound, so HBM stays the roofline"},
+                "l1_data_pipe": {"wavefronts_per_sm_per_launch": wf, "ms_at_peak": wf / hz * 1e3, "frac": wf / hz / t,
+                                 "what": "L1 / shared-memory data-pipe wavefronts per SM (ncu l1tex__data_pipe_lsu_wavefronts), one "
+                                         "per cycle at best: the SM resource that binds this kernel (FFT exchange, power tile, "
+                                         "mel taps through shared memory)"},
+                "source": "profiles/ncu_traffic.json (counted by ncu, not live)"}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def workload_config(n_gpus):
     return {
         "workload": "large-v3 front end: n_mels=128, 64 x 30 s float32 PCM per GPU per step, log-mel + SpecAugment "
@@ -537,6 +563,9 @@ def run_ours(args):
             "epilogue_roofline": {"bound": "hbm", "kernel": "augment_staged_kernel<false, 0>", "kernel_ms": epi_ms,
                                   "algorithmic_bytes_per_launch": epi_bytes, "achieved": epi_bytes / (epi_ms * 1e-3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": epi_bytes / (epi_ms * 1e-3) / 1e9 / peak}}
+        props = torch.cuda.get_device_properties(local_rank)
+        sm_mhz = (line["clocks"] or {}).get("sm_mhz") or (line["clocks"] or {}).get("sm_max_mhz") or 1965.0
+        line["roofline"]["other_bounds"] = other_bounds(kernel_ms, props.multi_processor_count, float(sm_mhz))
         if multi is not None:
             line["multi_gpu"] = multi
             line["shard_union_equal"] = multi["shard_union_equal"]

@@ -128,6 +128,29 @@ def main():
     regions.append(cur)
     tot_e = sum(x["exec"] for x in regions)
     tot_s = sum(x["samp"] for x in regions) or 1.0
+    # fp32 flops the launch really executed (thread-level, predicated-on): FFMA = 2, packed FFMA2 = 4, FADD2 / FMUL2 = 2,
+    # scalar add / mul / min-max / MUFU = 1 -- the numerator of the FMA-peak bound north_star asks to be compared with HBM
+    flop_w = {"FFMA": 2, "FFMA2": 4, "FADD2": 2, "FMUL2": 2, "FADD": 1, "FMUL": 1, "FMNMX": 1, "FMNMX3": 2, "MUFU": 1}
+    flops = 0.0
+    for r in data:
+        s = r[ix["Source"]].strip()
+        op = (s.split()[1] if s.startswith("@") else s.split()[0]).split(".")[0]
+        flops += flop_w.get(op, 0) * f(r, "Predicated-On Thread Instructions Executed")
+    try:
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json")
+        t = json.load(open(tpath))
+        t["fp32_flops_per_launch"] = flops
+        t["warp_instructions_per_launch"] = tot_e
+        t["lsu_wavefronts_per_sm"] = float(d.get("SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg", "nan"))
+        t["data_pipe_pct_of_peak_under_ncu"] = float(d.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "nan"))
+        with open(tpath, "w") as fh:
+            json.dump(t, fh)
+            fh.write("\n")
+        out += ["", f"fp32 operations executed by the launch (FFMA = 2, FFMA2 = 4, other packed = 2, scalar = 1): "
+                f"{flops / 1e9:.2f} GFLOP = {flops / 64 / 1e6:.1f} MFLOP per clip; L1 data-pipe wavefronts per SM: "
+                f"{t['lsu_wavefronts_per_sm']:.0f} (one per cycle at best)."]
+    except Exception as e:  # noqa: BLE001
+        out += ["", f"(flop / wavefront record not written: {e})"]
     out += ["", f"### Instructions per barrier-delimited region of the SASS ({len(data)} instructions = {len(data) * 16 / 1024:.0f} KB)",
             "", "Regions in program order: 0-1 prologue / loop top / edge staging, 2 audio gather + window (+ first butterflies), 3 stage A "
             "DFT + twiddles + exchange stores (+ describe_tile), 4 stage B row loads + DFT + mirror shuffles, 5 power tile, 6 mel "
