@@ -466,9 +466,11 @@ enum { kFlagFast = 1,        // the mel phase may take the branch-free path
        kFlagAllKept = 2,     // (fast tiles) every frame survives the partial-segment cut -> counts for the pad minimum
        kFlagAllMasked = 4 }; // (fast tiles) every frame lies inside the SpecAugment time mask
 
-// ---- mel projection, edge tiles (generic, one frame at a time): the clip's last tile, the two tiles a time mask or the
-// partial-segment cut passes through, unaligned outputs.  Same thread <-> (row, frames) map and the same summation order as
-// mel_fast, so a cell's value does not depend on the path that produced it. ------------------------------------------------
+// ---- mel projection, edge tiles (generic): the clip's last tile, the two tiles a time mask or the partial-segment cut
+// passes through, unaligned outputs -- three of a full clip's 188 tiles.  Same thread <-> (row, 8 frames) map, the same 16-byte
+// loads of the power tile and the same summation order as mel_fast (tap 0 is a product, every later tap one FMA), so a cell's
+// value does not depend on the path that produced it; what differs is that the tap count is a run-time value (one copy of the
+// code for every warp and pass) and that every frame carries its own live / kept / stored / time-masked bit. ------------------
 template <int NM>
 __device__ __noinline__ void mel_edge(const float* __restrict__ sm_region, const float* __restrict__ sm_melw,
                                       const int* __restrict__ desc, uint32_t mel_desc, float* __restrict__ out, int n_frames,
@@ -485,30 +487,58 @@ __device__ __noinline__ void mel_edge(const float* __restrict__ sm_region, const
     }
   const int f0 = (lane >> 4) * 8;
   const int clip = desc[kDescClip], t0 = desc[kDescT0], keep = desc[kDescKeep];
-  const uint32_t live = frame_window(0, n_frames, t0), kept = frame_window(0, keep, t0),
-                 store = frame_window(0, n_frames < n_frames_out ? n_frames : n_frames_out, t0),
-                 tmask = frame_window(desc[kDescMask], desc[kDescMask + 1], t0);
+  // this thread's 8 frames: bit i = frame t0 + f0 + i
+  const uint32_t live = (frame_window(0, n_frames, t0) >> f0) & 0xffu, kept = (frame_window(0, keep, t0) >> f0) & 0xffu,
+                 store = (frame_window(0, n_frames < n_frames_out ? n_frames : n_frames_out, t0) >> f0) & 0xffu,
+                 tmask = (frame_window(desc[kDescMask], desc[kDescMask + 1], t0) >> f0) & 0xffu;
   float mx = -INFINITY, mn_kept = INFINITY, mn_live = INFINITY;
 #pragma unroll 1
   for (int ps = 0; ps < passes; ++ps) {
     const int T = ps ? T1 : T0;
     const int row = static_cast<int>((mel_desc >> (ps ? 15 : 0)) & 0x7fu);
-    const float* pk = sm_region + ((mel_desc >> (ps ? 22 : 7)) & 0xffu) * kPStride;
+    const float* pk = sm_region + ((mel_desc >> (ps ? 22 : 7)) & 0xffu) * kPStride + f0;
     const float* wp = sm_melw + wbase + (ps ? T0 * kMelSlots : 0) + (lane & (kMelSlots - 1));
     const bool rowmask = row >= desc[kDescMask + 2] && row < desc[kDescMask + 3];
-    float* dst = out + (static_cast<size_t>(clip) * NM + row) * n_frames_out + t0;
+    float* dst = out + (static_cast<size_t>(clip) * NM + row) * n_frames_out + t0 + f0;
+    cpx acc[4];
+    {
+      const cpx ww = splat(wp[0]);
+      const float4 va = *reinterpret_cast<const float4*>(pk), vb = *reinterpret_cast<const float4*>(pk + 4);
+      acc[0] = cmul(ww, make_float2(va.x, va.y));
+      acc[1] = cmul(ww, make_float2(va.z, va.w));
+      acc[2] = cmul(ww, make_float2(vb.x, vb.y));
+      acc[3] = cmul(ww, make_float2(vb.z, vb.w));
+    }
 #pragma unroll 1
-    for (int f = f0; f < f0 + 8; ++f) {
-      float a = 0.0f;
-#pragma unroll 1
-      for (int j = 0; j < T; ++j) a = fmaf(wp[j * kMelSlots], pk[j * kPStride + f], a);
+    for (int j = 1; j < T; ++j) {
+      const cpx ww = splat(wp[j * kMelSlots]);
+      const float4 va = *reinterpret_cast<const float4*>(pk + j * kPStride), vb = *reinterpret_cast<const float4*>(pk + j * kPStride + 4);
+      acc[0] = cfma(ww, make_float2(va.x, va.y), acc[0]);
+      acc[1] = cfma(ww, make_float2(va.z, va.w), acc[1]);
+      acc[2] = cfma(ww, make_float2(vb.x, vb.y), acc[2]);
+      acc[3] = cfma(ww, make_float2(vb.z, vb.w), acc[3]);
+    }
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = (i & 1) ? acc[i >> 1].y : acc[i >> 1].x;
       const float l2 = fast_log2(fmaxf(a, 1e-10f));
-      if ((live >> f) & 1u) {
+      if ((live >> i) & 1u) {
         mx = fmaxf(mx, l2);
         mn_live = fminf(mn_live, l2);
       }
-      if ((kept >> f) & 1u) mn_kept = fminf(mn_kept, l2);
-      if ((store >> f) & 1u) dst[f] = (rowmask || ((tmask >> f) & 1u)) ? mask_value : feature_of_l2(l2);
+      if ((kept >> i) & 1u) mn_kept = fminf(mn_kept, l2);
+      v[i] = (rowmask || ((tmask >> i) & 1u)) ? mask_value : feature_of_l2(l2);
+    }
+    if (store == 0xffu && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      // two 16-byte stores: inside this predicated branch ptxas 12.9 turned the st.global.v8.f32 of st_global_256 into a single
+      // 4-byte STG (seen in the SASS and on the device: only frame 0 of the clip's last tile was written)
+      reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((store >> i) & 1u) dst[i] = v[i];
     }
   }
   mx = warp_max(mx);
