@@ -292,8 +292,20 @@ __device__ __forceinline__ void prefetch_audio_tile(PcmT* __restrict__ sm_audio,
 template <typename PcmT>
 __device__ __noinline__ void stage_audio_edge(PcmT* __restrict__ sm_audio, const PcmT* __restrict__ x, int g0,
                                               int len, int n_total, int tid) {
-  for (int m = tid; m < kTileSamples; m += kThreads)
-    sm_audio[m + Skew<PcmT>::value * (m / kSkewBlock)] = load_sample(x, g0 + m, len, n_total);
+  // every load of the thread in flight before its first store: as a loop of dependent round trips (18 x global latency) an
+  // edge-staged tile -- the first and the last tile of every clip -- took nearly twice as long as an interior one
+  constexpr int kPer = (kTileSamples + kThreads - 1) / kThreads;   // 18
+  PcmT v[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int m = tid + k * kThreads;
+    v[k] = m < kTileSamples ? load_sample(x, g0 + m, len, n_total) : PcmT(0);
+  }
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int m = tid + k * kThreads;
+    if (m < kTileSamples) sm_audio[m + Skew<PcmT>::value * (m / kSkewBlock)] = v[k];
+  }
 }
 
 __device__ __forceinline__ float pcm_as_float(float v) { return v; }
