@@ -363,3 +363,26 @@ def test_independent_launch_bookkeeping(wft):
         ind, hist = _record_call(hist, *call(5000, 6000 + 200 * k, scratch=9000 + 200 * (k % 2)), may_overlap=True, bounds_in_flight=False)
         seen.append(ind)
     assert seen == [False, True, False, True, False, True]
+
+
+def test_bench_other_bounds_come_from_the_committed_ncu_counts():
+    """roofline.other_bounds (fp32 FMA-peak bound, L1 data-pipe bound) is arithmetic on profiles/ncu_traffic.json: the HBM
+    bound must stay the slower of HBM and FMA (north_star's roofline rule), and the data pipe the tighter SM resource."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("_bench_for_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    for k in ("dram_bytes_per_launch", "fp32_flops_per_launch", "lsu_wavefronts_per_sm"):
+        assert rec[k] > 0, k
+    kernel_ms = 0.083
+    ob = bench.other_bounds(kernel_ms, 148, 1965.0)
+    assert ob is not None
+    fma, pipe = ob["fma_fp32"], ob["l1_data_pipe"]
+    assert abs(fma["peak_tflops"] - 148 * 128 * 2 * 1.965e9 / 1e12) < 1e-6
+    assert abs(fma["frac"] - rec["fp32_flops_per_launch"] / (kernel_ms * 1e-3) / (fma["peak_tflops"] * 1e12)) < 1e-9
+    assert abs(pipe["ms_at_peak"] - rec["lsu_wavefronts_per_sm"] / 1.965e9 * 1e3) < 1e-9
+    hbm_ms = bench.BATCH * bench.BYTES_PER_CLIP / 6547.2e9 * 1e3
+    assert fma["ms_at_peak"] < hbm_ms < pipe["ms_at_peak"] < kernel_ms
+    assert 0.0 < fma["frac"] < pipe["frac"] < 1.0

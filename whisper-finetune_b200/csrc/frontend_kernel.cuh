@@ -409,6 +409,8 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
   return r;
 }
 
+// (only on paths the compiler cannot if-convert: ptxas 12.9 turned this asm into ONE 4-byte STG when it sat in a short
+// predicated branch of mel_edge -- that path uses two 16-byte stores)
 __device__ __forceinline__ void st_global_256(float* dst, const float (&v)[8]) {   // one full 32-byte sector per thread
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
