@@ -15,6 +15,7 @@ from typing import Optional
 import torch
 
 from .audio import N_FRAMES, N_SAMPLES, frontend_forward, resolve_device
+from . import ops as _ops
 from .augment import augment_epilogue, draw_mask_params, draw_warp_params
 
 
@@ -78,7 +79,7 @@ class FrontEnd:
 
             if out is None:
                 out = torch.empty((B, self.n_mels, self.n_frames), dtype=torch.float32, device=self.device)
-            torch.ops.wft.frontend_forward_drawn_out(pcm, self.n_mels, self.n_samples - N, as_i32_on(lengths, self.device, (B,), "lengths"),
+            _ops.run_eager(_ops.frontend_forward_drawn_out, pcm, self.n_mels, self.n_samples - N, as_i32_on(lengths, self.device, (B,), "lengths"),
                                                      self.n_frames, as_i32_on(n_valid_frames, self.device, (B,), "n_valid_frames"),
                                                      self.seed, int(clip_offset), self.time_mask_param, self.freq_mask_param,
                                                      self.spec_augment_p, 0.0, out)
@@ -112,7 +113,7 @@ class FrontEnd:
             if out is None:
                 out = torch.empty((B, self.n_mels, self.n_frames), dtype=torch.float32, device=self.device)
             ext = None if extremes is None else torch.as_tensor(extremes, dtype=torch.int32).to(self.device).contiguous()
-            torch.ops.wft.frontend_augment_drawn_out(pcm, self.n_mels, self.n_samples - N, as_i32_on(lengths, self.device, (B,), "lengths"),
+            _ops.run_eager(_ops.frontend_augment_drawn_out, pcm, self.n_mels, self.n_samples - N, as_i32_on(lengths, self.device, (B,), "lengths"),
                                                      self.n_frames, as_i32_on(n_valid_frames, self.device, (B,), "n_valid_frames"),
                                                      self.seed, int(clip_offset), self.time_mask_param, self.freq_mask_param,
                                                      self.time_warp_w, self.spec_augment_p, ext, 0.0, self.warp_spline == "f32",
