@@ -386,3 +386,32 @@ def test_bench_other_bounds_come_from_the_committed_ncu_counts():
     hbm_ms = bench.BATCH * bench.BYTES_PER_CLIP / 6547.2e9 * 1e3
     assert fma["ms_at_peak"] < hbm_ms < pipe["ms_at_peak"] < kernel_ms
     assert 0.0 < fma["frac"] < pipe["frac"] < 1.0
+
+
+def test_run_eager_takes_the_dispatcher_whenever_a_mode_is_active(wft):
+    """ops.run_eager: the package's eager hot paths call an op's Python function directly only when nothing needs the
+    dispatcher; under a dispatch mode (fake tensors, tracing) or a torch-function mode the registered op is what runs."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from torch.overrides import TorchFunctionMode
+    from whisper_finetune_b200 import ops
+
+    assert not ops._dispatch_modes_active()
+    with FakeTensorMode():
+        assert ops._dispatch_modes_active()
+    with TorchFunctionMode():
+        assert ops._dispatch_modes_active()
+    assert not ops._dispatch_modes_active()
+
+    class _Op:   # stands in for a CustomOpDef: __call__ = dispatcher, _init_fn = the registered function
+        def __call__(self, *a):
+            return ("dispatcher", a)
+
+        @staticmethod
+        def _init_fn(*a):
+            return ("direct", a)
+
+    assert ops.run_eager(_Op(), 1, 2) == ("direct", (1, 2))
+    with FakeTensorMode():
+        assert ops.run_eager(_Op(), 1, 2) == ("dispatcher", (1, 2))
+    for op in (ops.frontend_forward, ops.frontend_forward_out, ops.frontend_forward_drawn_out, ops.frontend_augment_drawn_out):
+        assert callable(op._init_fn)

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from . import ops  # noqa: F401  (registers torch.ops.wft.*)
+from . import ops  # (registers torch.ops.wft.*)
 
 SAMPLE_RATE = 16000
 N_FFT = 400
@@ -75,7 +75,7 @@ def frontend_forward(pcm: torch.Tensor, n_mels: int, padding: int = 0, lengths: 
                      n_frames_out: int = 0, n_valid_frames: Optional[torch.Tensor] = None,
                      mask_params: Optional[torch.Tensor] = None, mask_value: float = 0.0,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """One launch of ``wft_frontend_forward`` (through ``torch.ops.wft.frontend_forward``) on a CUDA ``[B, N]`` float32 /
+    """One launch of ``wft_frontend_forward`` (``wft::frontend_forward`` / ``wft::frontend_forward_out``, see ``ops.run_eager``) on a CUDA ``[B, N]`` float32 /
     int16 batch -> ``[B, n_mels, T]``."""
     _lib.load()   # fail loudly, before any tensor work, if the CUDA library is missing
     if n_mels not in (80, 128):
@@ -97,10 +97,10 @@ def frontend_forward(pcm: torch.Tensor, n_mels: int, padding: int = 0, lengths: 
     mask_params = _i32(mask_params, "mask_params", (B, 4))
     T = n_frames_out if n_frames_out and n_frames_out > 0 else (N + padding) // HOP_LENGTH
     if out is None:
-        return torch.ops.wft.frontend_forward(pcm, n_mels, padding, lengths, T, n_valid_frames, mask_params, float(mask_value))
+        return ops.run_eager(ops.frontend_forward, pcm, n_mels, padding, lengths, T, n_valid_frames, mask_params, float(mask_value))
     if not out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != (B, n_mels, T) or not out.is_contiguous():
         raise ValueError(f"out must be a contiguous CUDA float32 tensor of shape {(B, n_mels, T)}")
-    torch.ops.wft.frontend_forward_out(pcm, n_mels, padding, lengths, T, n_valid_frames, mask_params, float(mask_value), out)
+    ops.run_eager(ops.frontend_forward_out, pcm, n_mels, padding, lengths, T, n_valid_frames, mask_params, float(mask_value), out)
     return out
 
 
