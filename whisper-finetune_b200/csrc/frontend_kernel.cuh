@@ -38,7 +38,7 @@
 //   [audio tile at the top] -> stage A->B exchange -> [power tile at the bottom | next audio tile at the top],
 // plus ~8.4 KB of window / twiddle / mel-weight tables, drawn intervals and control words.  The thread order and every stride
 // in here were chosen against measured shared-memory wavefront costs (tools/micro/smem_wavefronts.cu,
-// profiles/r01_smem_wavefront_probe.md): the SM (L1 data pipe 84 %, FMA pipe 51 %, issue 2.3 of 4), not HBM, is what bounds
+// profiles/r01_smem_wavefront_probe.md): the SM (L1 data pipe at 0.80 of its peak, FMA pipe 48 %, issue 2.3 of 4), not HBM, is what bounds
 // this kernel (profiles/r02_ncu_summary.md, profiles/r02_ab_experiments.md).  The hot loop is one DFT20 copy per stage and
 // ~2.8 k SASS instructions so that it stays resident in the SM's instruction cache.
 #pragma once
